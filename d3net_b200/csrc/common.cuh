@@ -1,0 +1,134 @@
+// Shared helpers for the sm_100a PointGroup kernels (error plumbing, launch math, small device utils).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/pg_b200.h"
+
+namespace pg {
+
+constexpr int kWarp = 32;
+constexpr int kNumSM = 148;  // B200: 2 dies x 74 SMs; grids of persistent kernels are sized from this
+
+void set_error(const char *fmt, ...);
+
+#define PG_CHECK_ARG(cond, msg)                           \
+    do {                                                  \
+        if (!(cond)) {                                    \
+            pg::set_error("%s: %s", __func__, msg);       \
+            return PG_EINVAL;                             \
+        }                                                 \
+    } while (0)
+
+#define PG_CUDA(expr)                                                                   \
+    do {                                                                                \
+        cudaError_t _e = (expr);                                                        \
+        if (_e != cudaSuccess) {                                                        \
+            pg::set_error("%s: %s failed: %s", __func__, #expr, cudaGetErrorString(_e)); \
+            return (int)_e;                                                             \
+        }                                                                               \
+    } while (0)
+
+#define PG_LAUNCH_CHECK()                                                                     \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess) {                                                              \
+            pg::set_error("%s: kernel launch failed: %s", __func__, cudaGetErrorString(_e));  \
+            return (int)_e;                                                                   \
+        }                                                                                     \
+    } while (0)
+
+#define PG_TRY(expr)             \
+    do {                         \
+        int _rc = (expr);        \
+        if (_rc != PG_OK) return _rc; \
+    } while (0)
+
+inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t a, size_t b = 256) { return (a + b - 1) / b * b; }
+
+// Bump allocator over the caller-provided workspace; both phases of a two-phase op replay the same
+// sequence of take() calls so they see the same layout.
+struct Arena {
+    char *base;
+    size_t size, used;
+    bool ok;
+    Arena(void *p, size_t n) : base((char *)p), size(n), used(0), ok(p != nullptr || n == 0) {}
+    template <typename T>
+    T *take(size_t count) {
+        size_t bytes = align_up(count * sizeof(T));
+        if (used + bytes > size) { ok = false; used += bytes; return nullptr; }
+        T *r = (T *)(base + used);
+        used += bytes;
+        return r;
+    }
+};
+
+__device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// float <-> order-preserving uint32 (total order on non-NaN floats)
+__device__ __forceinline__ unsigned f2ord(float f) {
+    unsigned u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__device__ __forceinline__ unsigned hash4(int a, int b, int c, int d) {
+    unsigned h = 0x9E3779B9u;
+    h ^= (unsigned)a; h *= 0x85EBCA6Bu; h ^= h >> 15;
+    h ^= (unsigned)b; h *= 0xC2B2AE35u; h ^= h >> 13;
+    h ^= (unsigned)c; h *= 0x27D4EB2Fu; h ^= h >> 16;
+    h ^= (unsigned)d; h *= 0x165667B1u; h ^= h >> 15;
+    return h;
+}
+
+// ---- host-side primitives (prim.cu) ------------------------------------------------------------
+// Exclusive prefix sum of int32 `in[0..n)` into `out` (may alias `in`).  `total` (device int64, may
+// be null) receives the grand total.  `tmp` must hold scan_tmp_count(n) int64 values.
+size_t scan_tmp_count(int64_t n);
+int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, int64_t *total, int64_t *tmp,
+                       cudaStream_t st);
+
+// Stable LSD radix sort of (key, value) pairs on the low `bits` bits of the key (8-bit digits).
+// Pass 0 reads (keys_src, vals_src) -- vals_src == nullptr means "values are 0..n-1" -- and the
+// passes ping-pong between the A and B buffers, so the source arrays are never written.
+// *result_buf = 0 when the sorted pairs end in (keysA, valsA), 1 for (keysB, valsB).
+size_t radix_tmp_count(int64_t n);  // int32 count for the histogram scratch
+int radix_sort_pairs(const uint32_t *keys_src, const uint32_t *vals_src, uint32_t *keysA, uint32_t *valsA,
+                     uint32_t *keysB, uint32_t *valsB, int64_t n, int bits, int32_t *hist, int64_t *scan_tmp,
+                     cudaStream_t st, int *result_buf);
+
+// Group n int4 keys: gid[i] = group id numbered by first occurrence in input order; *nGroups (device
+// int64) = number of groups; cnt[g] = group size.  The open-addressing table (cap slots, cap a power
+// of two >= 2n) stays usable afterwards through group_lookup(): slot_rep[s] = a point holding the
+// slot's key (-1 empty), slot_gid[s] = its group id.
+struct GroupTable {
+    int32_t *slot_rep;  // [cap]
+    int32_t *slot_gid;  // [cap]  (min point index while building, group id afterwards)
+    uint32_t cap;
+};
+uint32_t group_table_cap(int64_t n);
+int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot /*[n] scratch*/,
+               int32_t *gid /*[n]*/, int32_t *cnt /*[n]*/, int64_t *nGroups, int64_t *scan_tmp,
+               cudaStream_t st);
+
+__device__ __forceinline__ int group_lookup(const int4 *keys, const GroupTable &tab, int4 k) {
+    unsigned h = hash4(k.x, k.y, k.z, k.w) & (tab.cap - 1);
+    for (;;) {
+        int rep = tab.slot_rep[h];
+        if (rep < 0) return -1;
+        int4 o = keys[rep];
+        if (o.x == k.x && o.y == k.y && o.z == k.z && o.w == k.w) return tab.slot_gid[h];
+        h = (h + 1) & (tab.cap - 1);
+    }
+}
+
+}  // namespace pg

@@ -1,0 +1,320 @@
+// Device-wide primitives used by several ops: exclusive scan, stable LSD radix sort of pairs, and
+// hash grouping of int4 keys (first-occurrence numbering).  Hand-written; no CUB/Thrust.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace pg {
+
+// ---------------------------------------------------------------------------------------------
+// error string
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char *last_error() { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan (reduce / spine / apply)
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanRounds = 16;
+constexpr int kScanTile = kScanThreads * kScanRounds;
+
+// inclusive block scan of one int per thread; returns inclusive value, *block_total = sum over block
+__device__ __forceinline__ int block_scan_incl(int v, int *warp_tot /*[32] smem*/, int *block_total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) warp_tot[w] = v;
+    __syncthreads();
+    int before = 0, all = 0;
+    for (int i = 0; i < nw; i++) {
+        int t = warp_tot[i];
+        if (i < w) before += t;
+        all += t;
+    }
+    __syncthreads();
+    *block_total = all;
+    return v + before;
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const int32_t *__restrict__ in, int64_t n,
+                                                              int64_t *__restrict__ block_sums) {
+    __shared__ long long wsum[kScanThreads / 32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    long long s = 0;
+#pragma unroll 4
+    for (int r = 0; r < kScanRounds; r++) {
+        int64_t i = base + r * kScanThreads + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long t = 0;
+        for (int i = 0; i < kScanThreads / 32; i++) t += wsum[i];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_scan_spine(int64_t *__restrict__ block_sums, int64_t nb,
+                                                     int64_t *__restrict__ total) {
+    __shared__ long long wtot[32];
+    __shared__ long long carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int64_t c = 0; c < nb; c += 1024) {
+        int64_t i = c + threadIdx.x;
+        long long v = (i < nb) ? block_sums[i] : 0, x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            long long t = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += t;
+        }
+        if (lane == 31) wtot[w] = x;
+        __syncthreads();
+        long long before = 0, all = 0;
+        for (int k = 0; k < 32; k++) {
+            long long t = wtot[k];
+            if (k < w) before += t;
+            all += t;
+        }
+        long long carry = carry_s;
+        if (i < nb) block_sums[i] = carry + before + x - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + all;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        block_sums[nb] = carry_s;
+        if (total) *total = carry_s;
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const int32_t *__restrict__ in,
+                                                             int32_t *__restrict__ out, int64_t n,
+                                                             const int64_t *__restrict__ block_offs) {
+    __shared__ int warp_tot[32];
+    const int64_t base = (int64_t)blockIdx.x * kScanTile;
+    int carry = (int)block_offs[blockIdx.x];
+    for (int r = 0; r < kScanRounds; r++) {
+        int64_t i = base + r * kScanThreads + threadIdx.x;
+        if (base + r * kScanThreads >= n) break;
+        int v = (i < n) ? in[i] : 0, tot;
+        int inc = block_scan_incl(v, warp_tot, &tot);
+        if (i < n) out[i] = carry + inc - v;
+        carry += tot;
+    }
+}
+
+size_t scan_tmp_count(int64_t n) { return (size_t)div_up(n > 0 ? n : 1, kScanTile) + 2; }
+
+int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, int64_t *total, int64_t *tmp,
+                       cudaStream_t st) {
+    if (n <= 0) {
+        if (total) PG_CUDA(cudaMemsetAsync(total, 0, sizeof(int64_t), st));
+        return PG_OK;
+    }
+    const int64_t nb = div_up(n, kScanTile);
+    k_scan_reduce<<<(unsigned)nb, kScanThreads, 0, st>>>(in, n, tmp);
+    k_scan_spine<<<1, 1024, 0, st>>>(tmp, nb, total);
+    k_scan_apply<<<(unsigned)nb, kScanThreads, 0, st>>>(in, out, n, tmp);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stable LSD radix sort, 8-bit digits: histogram -> scan -> ranked scatter per pass
+// ---------------------------------------------------------------------------------------------
+constexpr int kRadixThreads = 256;
+constexpr int kRadixRounds = 8;
+constexpr int kRadixTile = kRadixThreads * kRadixRounds;
+
+__global__ void __launch_bounds__(kRadixThreads) k_radix_hist(const uint32_t *__restrict__ keys, int64_t n,
+                                                              int shift, int32_t *__restrict__ hist, int nb) {
+    __shared__ int h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kRadixTile;
+#pragma unroll
+    for (int r = 0; r < kRadixRounds; r++) {
+        int64_t i = base + r * kRadixThreads + threadIdx.x;
+        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1);
+    }
+    __syncthreads();
+    hist[(int64_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kRadixThreads)
+k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
+                const int32_t *__restrict__ hist, int nb) {
+    __shared__ int base_s[256];                       // global base of this tile's run for each digit
+    __shared__ int wcnt[kRadixThreads / 32][256];     // per-warp digit counts of the current round
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    base_s[threadIdx.x] = hist[(int64_t)threadIdx.x * nb + blockIdx.x];
+    for (int k = 0; k < kRadixThreads / 32; k++) wcnt[k][threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t tile = (int64_t)blockIdx.x * kRadixTile;
+    for (int r = 0; r < kRadixRounds; r++) {
+        const int64_t i0 = tile + r * kRadixThreads;
+        if (i0 >= n) break;
+        const int64_t i = i0 + threadIdx.x;
+        const bool live = i < n;
+        uint32_t key = 0, val = 0;
+        unsigned d = 256;                             // dead lanes never match a real digit
+        if (live) {
+            key = keys_in[i];
+            val = vals_in ? vals_in[i] : (uint32_t)i;
+            d = (key >> shift) & 255u;
+        }
+        unsigned peers = __match_any_sync(0xffffffffu, d);
+        int rank = __popc(peers & lanemask_lt());
+        if (live && rank == 0) wcnt[w][d] = __popc(peers);
+        __syncthreads();
+        if (live) {
+            int before = 0;
+            for (int k = 0; k < w; k++) before += wcnt[k][d];
+            int pos = base_s[d] + before + rank;
+            keys_out[pos] = key;
+            vals_out[pos] = val;
+        }
+        __syncthreads();
+        {
+            int all = 0;
+#pragma unroll
+            for (int k = 0; k < kRadixThreads / 32; k++) {
+                all += wcnt[k][threadIdx.x];
+                wcnt[k][threadIdx.x] = 0;
+            }
+            base_s[threadIdx.x] += all;
+        }
+        __syncthreads();
+    }
+}
+
+size_t radix_tmp_count(int64_t n) { return (size_t)256 * (size_t)div_up(n > 0 ? n : 1, kRadixTile) + 16; }
+
+int radix_sort_pairs(const uint32_t *keys_src, const uint32_t *vals_src, uint32_t *keysA, uint32_t *valsA,
+                     uint32_t *keysB, uint32_t *valsB, int64_t n, int bits, int32_t *hist, int64_t *scan_tmp,
+                     cudaStream_t st, int *result_buf) {
+    *result_buf = 0;
+    if (n <= 0) return PG_OK;
+    int passes = (bits + 7) / 8;
+    if (passes < 1) passes = 1;
+    const int nb = (int)div_up(n, kRadixTile);
+    uint32_t *k[2] = {keysA, keysB}, *v[2] = {valsA, valsB};
+    const uint32_t *kin = keys_src, *vin = vals_src;
+    int dst = 0;
+    for (int p = 0; p < passes; p++) {
+        const int shift = 8 * p;
+        k_radix_hist<<<nb, kRadixThreads, 0, st>>>(kin, n, shift, hist, nb);
+        PG_TRY(scan_exclusive_i32(hist, hist, (int64_t)256 * nb, nullptr, scan_tmp, st));
+        k_radix_scatter<<<nb, kRadixThreads, 0, st>>>(kin, vin, k[dst], v[dst], n, shift, hist, nb);
+        kin = k[dst];
+        vin = v[dst];
+        *result_buf = dst;
+        dst ^= 1;
+    }
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hash grouping of int4 keys
+// ---------------------------------------------------------------------------------------------
+uint32_t group_table_cap(int64_t n) {
+    uint64_t c = 1024;
+    while (c < (uint64_t)(n > 0 ? n : 1) * 2) c <<= 1;
+    return (uint32_t)c;
+}
+
+__global__ void k_group_init(int32_t *__restrict__ slot_rep, int32_t *__restrict__ slot_min, uint32_t cap) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
+        slot_rep[i] = -1;
+        slot_min[i] = 0x7fffffff;
+    }
+}
+
+__global__ void k_group_insert(const int4 *__restrict__ keys, int64_t n, int32_t *slot_rep, int32_t *slot_min,
+                               uint32_t cap, int32_t *__restrict__ pslot) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int4 k = keys[i];
+    unsigned h = hash4(k.x, k.y, k.z, k.w) & (cap - 1);
+    for (;;) {
+        int rep = slot_rep[h];
+        if (rep < 0) {
+            int prev = atomicCAS(&slot_rep[h], -1, (int)i);
+            rep = (prev < 0) ? (int)i : prev;
+        }
+        if (rep == (int)i) break;
+        const int4 o = keys[rep];
+        if (o.x == k.x && o.y == k.y && o.z == k.z && o.w == k.w) break;
+        h = (h + 1) & (cap - 1);
+    }
+    atomicMin(&slot_min[h], (int)i);
+    pslot[i] = (int)h;
+}
+
+// flag[i] = 1 when i is the first (lowest-index) point of its group
+__global__ void k_group_flag(const int32_t *__restrict__ pslot, const int32_t *__restrict__ slot_min, int64_t n,
+                             int32_t *__restrict__ flag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flag[i] = (slot_min[pslot[i]] == (int)i) ? 1 : 0;
+}
+
+// first points publish their rank (= group id) into the slot; needs the pre-scan flags, which after
+// the in-place scan are recovered as rank[i+1] - rank[i] (or total - rank[n-1])
+__global__ void k_group_publish(const int32_t *__restrict__ pslot, int32_t *slot_min, const int32_t *__restrict__ rank,
+                                const int64_t *__restrict__ total, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int r = rank[i];
+    int next = (i + 1 < n) ? rank[i + 1] : (int)*total;
+    if (next != r) slot_min[pslot[i]] = r;
+}
+
+__global__ void k_group_assign(const int32_t *__restrict__ pslot, const int32_t *__restrict__ slot_gid, int64_t n,
+                               int32_t *__restrict__ gid, int32_t *__restrict__ cnt) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int g = slot_gid[pslot[i]];
+    gid[i] = g;
+    atomicAdd(&cnt[g], 1);
+}
+
+int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot, int32_t *gid, int32_t *cnt,
+               int64_t *nGroups, int64_t *scan_tmp, cudaStream_t st) {
+    if (n <= 0) {
+        PG_CUDA(cudaMemsetAsync(nGroups, 0, sizeof(int64_t), st));
+        return PG_OK;
+    }
+    const int T = 256;
+    const unsigned nb = (unsigned)div_up(n, T);
+    k_group_init<<<kNumSM * 8, T, 0, st>>>(tab.slot_rep, tab.slot_gid, tab.cap);
+    PG_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(int32_t), st));
+    k_group_insert<<<nb, T, 0, st>>>(keys, n, tab.slot_rep, tab.slot_gid, tab.cap, pslot);
+    k_group_flag<<<nb, T, 0, st>>>(pslot, tab.slot_gid, n, gid);
+    PG_TRY(scan_exclusive_i32(gid, gid, n, nGroups, scan_tmp, st));
+    k_group_publish<<<nb, T, 0, st>>>(pslot, tab.slot_gid, gid, nGroups, n);
+    k_group_assign<<<nb, T, 0, st>>>(pslot, tab.slot_gid, n, gid, cnt);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
+}  // namespace pg
+
+extern "C" const char *pg_last_error(void) { return pg::last_error(); }
+extern "C" int pg_abi_version(void) { return 1; }

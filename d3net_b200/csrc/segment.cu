@@ -1,0 +1,371 @@
+// Segment reductions over proposals: roipool_fp / roipool_bp, sec_mean / sec_min / sec_max, get_iou.
+// Reference behaviour: lib/pointgroup_ops/src/{roipool/roipool.cu, sec_mean/sec_mean.cu, get_iou/get_iou.cu}.
+#include "common.cuh"
+
+namespace pg {
+
+// =================================================================================================
+// max / min (+ argmax) over row segments.
+//
+// Work is cut by ROWS, not by proposals: one warp owns a tile of R consecutive rows and walks the
+// pieces of the proposals that overlap it, so a 50-point proposal and a 300k-point floor cost the
+// same per row and no warp is left with a giant segment.  A lane owns V consecutive channels of
+// every G-th row (G = 32 / (C/V) row groups per warp-wide load, fully coalesced); the row groups are
+// folded with shuffles and the piece result is merged into the proposal's slot with one atomic per
+// channel.  Order-independence is what makes this legal: max with "lowest row wins ties"
+// (roipool.cu:22-26) is a max over the key (value, -row), min/max over values are plain lattices.
+// =================================================================================================
+enum SegMode { kMaxArg = 0, kMax = 1, kMin = 2 };
+
+__device__ __forceinline__ unsigned long long pack_key(float v, int row) {
+    return ((unsigned long long)f2ord(v) << 32) | (unsigned long long)(0xffffffffu - (unsigned)row);
+}
+
+template <int MODE>
+__global__ void k_seg_init(void *slots, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (MODE == kMaxArg) ((unsigned long long *)slots)[i] = pack_key(-INFINITY, -1);
+        else if (MODE == kMax) ((unsigned *)slots)[i] = f2ord(-INFINITY);
+        else ((unsigned *)slots)[i] = f2ord(INFINITY);
+    }
+}
+
+template <int MODE>
+__global__ void k_seg_decode(void *slots, float *__restrict__ out, int32_t *__restrict__ maxidx, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (MODE == kMaxArg) {
+            unsigned long long k = ((const unsigned long long *)slots)[i];
+            out[i] = ord2f((unsigned)(k >> 32));
+            maxidx[i] = (int)(0xffffffffu - (unsigned)(k & 0xffffffffu));
+        } else {
+            out[i] = ord2f(((const unsigned *)slots)[i]);   // in place: slots == out
+        }
+    }
+}
+
+template <int MODE>
+__device__ __forceinline__ void seg_acc(float x, int row, float &best, int &arg) {
+    if (MODE == kMin) { if (x < best) best = x; }
+    else if (x > best) { best = x; arg = row; }
+}
+// merge (v2, a2) into (best, arg) where the two come from different rows
+template <int MODE>
+__device__ __forceinline__ void seg_merge(float v2, int a2, float &best, int &arg) {
+    if (MODE == kMin) { if (v2 < best) best = v2; }
+    else if (v2 > best || (MODE == kMaxArg && v2 == best && (unsigned)a2 < (unsigned)arg)) { best = v2; arg = a2; }
+}
+
+template <int MODE, int V>
+__global__ void __launch_bounds__(256) k_seg_reduce(const float *__restrict__ inp, const int32_t *__restrict__ offsets,
+                                                    void *slots, int32_t nRows, int32_t nP, int32_t C, int32_t R) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int64_t r0 = tile * R, r1 = r0 + R;
+    const int first = __ldg(offsets), last = __ldg(offsets + nP);
+    if (r0 < first) r0 = first;
+    if (r1 > last) r1 = last;
+    if (r1 > nRows) r1 = nRows;
+    if (r0 >= r1) return;
+    // proposal containing r0: largest p with offsets[p] <= r0
+    int lo = 0, hi = nP;   // invariant: offsets[lo] <= r0 < offsets[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(offsets + mid) <= r0) lo = mid; else hi = mid;
+    }
+    const int CV = C / V;                       // vector columns per row
+    const int G = CV >= 32 ? 1 : 32 / CV;       // row groups per warp-wide load
+    const int g = CV >= 32 ? 0 : lane / CV;     // this lane's row group
+    const int c0 = CV >= 32 ? lane : lane - g * CV;
+    const bool lane_on = CV >= 32 ? true : (g < G);
+    for (int p = lo; p < nP; p++) {
+        const int64_t ps = __ldg(offsets + p), pe = __ldg(offsets + p + 1);
+        if (ps >= r1) break;
+        const int64_t a = ps > r0 ? ps : r0, b = pe < r1 ? pe : r1;
+        if (a >= b) continue;
+        for (int cv = c0; cv < CV; cv += 32) {   // one trip unless C/V > 32
+            float best[V];
+            int arg[V];
+#pragma unroll
+            for (int k = 0; k < V; k++) { best[k] = (MODE == kMin) ? INFINITY : -INFINITY; arg[k] = -1; }
+            if (lane_on) {
+                int64_t row = a + g;
+                for (; row + 3 * G < b; row += 4 * G) {   // four loads in flight per lane
+                    float x[4][V];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const float *q = inp + (row + (int64_t)u * G) * C + (int64_t)cv * V;
+                        if constexpr (V == 4) { float4 t = __ldg((const float4 *)q); x[u][0] = t.x; x[u][1] = t.y; x[u][2] = t.z; x[u][3] = t.w; }
+                        else if constexpr (V == 2) { float2 t = __ldg((const float2 *)q); x[u][0] = t.x; x[u][1] = t.y; }
+                        else x[u][0] = __ldg(q);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+#pragma unroll
+                        for (int k = 0; k < V; k++) seg_acc<MODE>(x[u][k], (int)(row + (int64_t)u * G), best[k], arg[k]);
+                }
+                for (; row < b; row += G) {
+                    const float *q = inp + row * C + (int64_t)cv * V;
+#pragma unroll
+                    for (int k = 0; k < V; k++) seg_acc<MODE>(__ldg(q + k), (int)row, best[k], arg[k]);
+                }
+            }
+            // fold the row groups: lane (g, c0) <- lanes (g + s, c0)
+            if (CV < 32) {
+                for (int s = 1; s < G; s <<= 1) {
+#pragma unroll
+                    for (int k = 0; k < V; k++) {
+                        const int src = lane + s * CV;
+                        float v2 = __shfl_sync(0xffffffffu, best[k], src & 31);
+                        int a2 = __shfl_sync(0xffffffffu, arg[k], src & 31);
+                        if (lane_on && src < G * CV && (g % (2 * s)) == 0 && g + s < G) seg_merge<MODE>(v2, a2, best[k], arg[k]);
+                    }
+                }
+            }
+            if (lane_on && g == 0) {
+#pragma unroll
+                for (int k = 0; k < V; k++) {
+                    const int64_t slot = (int64_t)p * C + (int64_t)cv * V + k;
+                    if (MODE == kMaxArg) {
+                        if (arg[k] >= 0) atomicMax((unsigned long long *)slots + slot, pack_key(best[k], arg[k]));
+                    } else if (MODE == kMax) {
+                        atomicMax((unsigned *)slots + slot, f2ord(best[k]));
+                    } else {
+                        atomicMin((unsigned *)slots + slot, f2ord(best[k]));
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int MODE>
+static int seg_reduce_launch(const float *inp, const int32_t *offsets, float *out, int32_t *maxidx, void *slots,
+                             int32_t nRows, int32_t nP, int32_t C, cudaStream_t st) {
+    PG_CHECK_ARG(nRows >= 0 && nP >= 0 && C >= 0, "negative size");
+    const int64_t nslot = (int64_t)nP * C;
+    if (nslot == 0) return PG_OK;
+    PG_CHECK_ARG(offsets && out && slots && (inp || nRows == 0), "null pointer");
+    const unsigned ig = (unsigned)(div_up(nslot, 256) < kNumSM * 8 ? div_up(nslot, 256) : kNumSM * 8);
+    k_seg_init<MODE><<<ig, 256, 0, st>>>(slots, nslot);
+    if (nRows > 0) {
+        int V = 1;
+        if (C % 4 == 0 && (uintptr_t)inp % 16 == 0) V = 4;
+        else if (C % 2 == 0 && (uintptr_t)inp % 8 == 0) V = 2;
+        int R = 4096 / (C > 0 ? C : 1);
+        if (R < 32) R = 32;
+        const int64_t tiles = div_up(nRows, R);
+        const unsigned grid = (unsigned)div_up(tiles, 8);
+        if (V == 4) k_seg_reduce<MODE, 4><<<grid, 256, 0, st>>>(inp, offsets, slots, nRows, nP, C, R);
+        else if (V == 2) k_seg_reduce<MODE, 2><<<grid, 256, 0, st>>>(inp, offsets, slots, nRows, nP, C, R);
+        else k_seg_reduce<MODE, 1><<<grid, 256, 0, st>>>(inp, offsets, slots, nRows, nP, C, R);
+    }
+    k_seg_decode<MODE><<<ig, 256, 0, st>>>(slots, out, maxidx, nslot);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
+// roipool_bp: d_feats[argmax][c] += d_out[p][c]  (roipool.cu:42-49)
+__global__ void k_roipool_bp(float *d_feats, const int32_t *__restrict__ maxidx, const float *__restrict__ d_out,
+                             int64_t n, int32_t C) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int a = __ldg(maxidx + i);
+        if (a >= 0) atomicAdd(d_feats + (int64_t)a * C + (i % C), __ldg(d_out + i));
+    }
+}
+
+// =================================================================================================
+// sec_mean: mean = sum_i fl(x_i / count), accumulated strictly left to right (sec_mean.cu:17-25).
+// The serial fp32 add chain is the semantics, so the chain is all that stays serial: the block
+// streams the segment through a double-buffered shared tile (coalesced loads in flight while the
+// previous tile is consumed), applies the IEEE division in parallel on the way in, and threads
+// 0..C-1 run one add chain per channel out of shared memory.
+// =================================================================================================
+constexpr int kMeanThreads = 128;
+constexpr int kMeanPer = 16;                          // floats prefetched per thread
+constexpr int kMeanTile = kMeanThreads * kMeanPer;    // 2048 floats per buffer
+
+__global__ void __launch_bounds__(kMeanThreads) k_sec_mean(const float *__restrict__ inp,
+                                                           const int32_t *__restrict__ offsets,
+                                                           float *__restrict__ out, int32_t nP, int32_t C) {
+    __shared__ float buf[2][kMeanTile];
+    const int tid = threadIdx.x;
+    const int rowsPerTile = kMeanTile / C;            // C <= kMeanTile guaranteed by the launcher
+    const int tileFloats = rowsPerTile * C;
+    for (int p = blockIdx.x; p < nP; p += gridDim.x) {
+        const int64_t start = __ldg(offsets + p), end = __ldg(offsets + p + 1);
+        const int64_t len = end - start;
+        const float count = (float)(int)len;
+        const float *base = inp + start * C;
+        const int64_t total = len > 0 ? len * C : 0;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};          // channels tid, tid+128, ... (C <= 512 on this path)
+        float reg[kMeanPer];
+        int64_t pos = 0;
+        int cur = 0;
+        // prefetch tile 0
+#pragma unroll
+        for (int k = 0; k < kMeanPer; k++) {
+            const int64_t e = pos + k * kMeanThreads + tid;
+            reg[k] = (k * kMeanThreads + tid < tileFloats && e < total) ? __ldg(base + e) : 0.f;
+        }
+        while (pos < total) {
+            const int64_t nflt = (total - pos < tileFloats) ? (total - pos) : tileFloats;
+#pragma unroll
+            for (int k = 0; k < kMeanPer; k++) buf[cur][k * kMeanThreads + tid] = __fdiv_rn(reg[k], count);
+            __syncthreads();
+            const int64_t npos = pos + tileFloats;
+            if (npos < total) {
+#pragma unroll
+                for (int k = 0; k < kMeanPer; k++) {
+                    const int64_t e = npos + k * kMeanThreads + tid;
+                    reg[k] = (k * kMeanThreads + tid < tileFloats && e < total) ? __ldg(base + e) : 0.f;
+                }
+            }
+            const int rows = (int)(nflt / C);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int c = tid + j * kMeanThreads;
+                if (c < C) {
+                    const float *b = &buf[cur][c];
+                    float a = acc[j];
+                    int r = 0;
+                    for (; r + 8 <= rows; r += 8) {
+                        float q0 = b[(r + 0) * C], q1 = b[(r + 1) * C], q2 = b[(r + 2) * C], q3 = b[(r + 3) * C];
+                        float q4 = b[(r + 4) * C], q5 = b[(r + 5) * C], q6 = b[(r + 6) * C], q7 = b[(r + 7) * C];
+                        a = __fadd_rn(a, q0); a = __fadd_rn(a, q1); a = __fadd_rn(a, q2); a = __fadd_rn(a, q3);
+                        a = __fadd_rn(a, q4); a = __fadd_rn(a, q5); a = __fadd_rn(a, q6); a = __fadd_rn(a, q7);
+                    }
+                    for (; r < rows; r++) a = __fadd_rn(a, b[r * C]);
+                    acc[j] = a;
+                }
+            }
+            pos = npos;
+            cur ^= 1;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int c = tid + j * kMeanThreads;
+            if (c < C) out[(int64_t)p * C + c] = acc[j];
+        }
+        __syncthreads();   // the next proposal's first store must not overtake this one's last chain
+    }
+}
+
+// any C: one thread per (proposal, channel), straight from global memory
+__global__ void k_sec_mean_wide(const float *__restrict__ inp, const int32_t *__restrict__ offsets,
+                                float *__restrict__ out, int32_t nP, int32_t C) {
+    const int64_t n = (int64_t)nP * C;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int p = (int)(t / C), c = (int)(t - (int64_t)p * C);
+        const int64_t start = __ldg(offsets + p), end = __ldg(offsets + p + 1);
+        const float count = (float)(int)(end - start);
+        float a = 0.f;
+        for (int64_t i = start; i < end; i++) a = __fadd_rn(a, __fdiv_rn(__ldg(inp + i * C + c), count));
+        out[t] = a;
+    }
+}
+
+// =================================================================================================
+// get_iou: one block per proposal builds the histogram of its points' instance labels in shared
+// memory (one pass over the proposal instead of one pass per instance, get_iou.cu:19-25), then
+// every thread finishes some instances with the reference's mixed fp32/fp64 formula (:26).
+// =================================================================================================
+constexpr int kIouBins = 8192;
+
+__global__ void __launch_bounds__(256) k_get_iou(const int32_t *__restrict__ pidx, const int32_t *__restrict__ poff,
+                                                 const int64_t *__restrict__ labels, const int32_t *__restrict__ pointnum,
+                                                 float *__restrict__ iou, int32_t nInst, int32_t nP) {
+    __shared__ int hist[kIouBins];
+    for (int p = blockIdx.x; p < nP; p += gridDim.x) {
+        const int start = __ldg(poff + p), end = __ldg(poff + p + 1);
+        const int ptotal = end - start;
+        for (int g0 = 0; g0 < nInst; g0 += kIouBins) {
+            const int nb = min(kIouBins, nInst - g0);
+            for (int g = threadIdx.x; g < nb; g += blockDim.x) hist[g] = 0;
+            __syncthreads();
+            for (int i = start + threadIdx.x; i < end; i += blockDim.x) {
+                const int l = (int)__ldg(labels + __ldg(pidx + i)) - g0;   // (int) narrowing as in :22
+                if (l >= 0 && l < nb) atomicAdd(&hist[l], 1);
+            }
+            __syncthreads();
+            for (int g = threadIdx.x; g < nb; g += blockDim.x) {
+                const int inter = hist[g];
+                const int itotal = __ldg(pointnum + g0 + g);
+                const double den = (double)(float)(ptotal + itotal - inter) + 1e-5;
+                iou[(int64_t)p * nInst + g0 + g] = (float)((double)(float)inter / den);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" size_t pg_roipool_workspace_bytes(int32_t nProposal, int32_t C) {
+    if (nProposal < 0 || C < 0) return 0;
+    return (size_t)nProposal * (size_t)C * 8 + 256;
+}
+
+extern "C" int pg_roipool_fp(const float *feats, const int32_t *offsets, float *out, int32_t *maxidx, int32_t nRows,
+                             int32_t nProposal, int32_t C, void *ws, size_t ws_bytes, void *stream) {
+    if ((int64_t)nProposal * C > 0) {
+        PG_CHECK_ARG(maxidx, "null maxidx");
+        if (!ws || ws_bytes < (size_t)nProposal * C * 8) { set_error("pg_roipool_fp: workspace too small"); return PG_EWORKSPACE; }
+        PG_CHECK_ARG((uintptr_t)ws % 8 == 0, "workspace must be 8-byte aligned");
+    }
+    return seg_reduce_launch<kMaxArg>(feats, offsets, out, maxidx, ws, nRows, nProposal, C, (cudaStream_t)stream);
+}
+
+extern "C" int pg_roipool_bp(float *d_feats, const int32_t *offsets, const int32_t *maxidx, const float *d_out,
+                             int32_t nProposal, int32_t C, void *stream) {
+    (void)offsets;
+    PG_CHECK_ARG(nProposal >= 0 && C >= 0, "negative size");
+    const int64_t n = (int64_t)nProposal * C;
+    if (n == 0) return PG_OK;
+    PG_CHECK_ARG(d_feats && maxidx && d_out, "null pointer");
+    const unsigned grid = (unsigned)(div_up(n, 256) < kNumSM * 16 ? div_up(n, 256) : kNumSM * 16);
+    k_roipool_bp<<<grid, 256, 0, (cudaStream_t)stream>>>(d_feats, maxidx, d_out, n, C);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
+extern "C" int pg_sec_max(const float *inp, const int32_t *offsets, float *out, int32_t nRows, int32_t nProposal,
+                          int32_t C, void *stream) {
+    return seg_reduce_launch<kMax>(inp, offsets, out, nullptr, out, nRows, nProposal, C, (cudaStream_t)stream);
+}
+extern "C" int pg_sec_min(const float *inp, const int32_t *offsets, float *out, int32_t nRows, int32_t nProposal,
+                          int32_t C, void *stream) {
+    return seg_reduce_launch<kMin>(inp, offsets, out, nullptr, out, nRows, nProposal, C, (cudaStream_t)stream);
+}
+
+extern "C" int pg_sec_mean(const float *inp, const int32_t *offsets, float *out, int32_t nRows, int32_t nProposal,
+                           int32_t C, void *stream) {
+    (void)nRows;
+    PG_CHECK_ARG(nProposal >= 0 && C >= 0, "negative size");
+    if ((int64_t)nProposal * C == 0) return PG_OK;
+    PG_CHECK_ARG(offsets && out, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (C <= 4 * kMeanThreads) {
+        const unsigned grid = (unsigned)(nProposal < kNumSM * 8 ? nProposal : kNumSM * 8);
+        k_sec_mean<<<grid, kMeanThreads, 0, st>>>(inp, offsets, out, nProposal, C);
+    } else {
+        const int64_t n = (int64_t)nProposal * C;
+        k_sec_mean_wide<<<(unsigned)div_up(n, 128), 128, 0, st>>>(inp, offsets, out, nProposal, C);
+    }
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
+extern "C" int pg_get_iou(const int32_t *proposals_idx, const int32_t *proposals_offset,
+                          const int64_t *instance_labels, const int32_t *instance_pointnum, float *proposals_iou,
+                          int32_t nInstance, int32_t nProposal, void *stream) {
+    PG_CHECK_ARG(nInstance >= 0 && nProposal >= 0, "negative size");
+    if ((int64_t)nInstance * nProposal == 0) return PG_OK;
+    PG_CHECK_ARG(proposals_offset && instance_pointnum && proposals_iou, "null pointer");
+    const unsigned grid = (unsigned)(nProposal < kNumSM * 16 ? nProposal : kNumSM * 16);
+    k_get_iou<<<grid, 256, 0, (cudaStream_t)stream>>>(proposals_idx, proposals_offset, instance_labels,
+                                                      instance_pointnum, proposals_iou, nInstance, nProposal);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}

@@ -1,0 +1,277 @@
+// voxelize_idx (GPU hash grouping + stable sort), voxelize_fp / voxelize_bp (segment mean scatter /
+// gather), point_recover.  Reference behaviour: lib/pointgroup_ops/src/voxelize/voxelize.{cpp,cu}.
+#include "common.cuh"
+
+namespace pg {
+
+// =================================================================================================
+// voxelize_idx
+// =================================================================================================
+struct VoxWs {
+    int4 *keys;
+    GroupTable tab;
+    int32_t *pslot, *cnt, *voff;
+    uint32_t *kA, *vA, *kB, *vB;
+    int32_t *hist;
+    int64_t *scan_tmp;
+    int64_t *scalars;  // [0] nGroups, [1] maxActive
+    bool ok;
+    size_t used;
+};
+
+static VoxWs vox_layout(void *ws, size_t ws_bytes, int64_t N) {
+    Arena a(ws, ws_bytes);
+    VoxWs w;
+    const size_t n = (size_t)(N > 0 ? N : 1);
+    w.tab.cap = group_table_cap(N);
+    w.keys = a.take<int4>(n);
+    w.tab.slot_rep = a.take<int32_t>(w.tab.cap);
+    w.tab.slot_gid = a.take<int32_t>(w.tab.cap);
+    w.pslot = a.take<int32_t>(n);
+    w.cnt = a.take<int32_t>(n + 1);
+    w.voff = a.take<int32_t>(n + 1);
+    w.kA = a.take<uint32_t>(n);
+    w.vA = a.take<uint32_t>(n);
+    w.kB = a.take<uint32_t>(n);
+    w.vB = a.take<uint32_t>(n);
+    w.hist = a.take<int32_t>(radix_tmp_count(N));
+    w.scan_tmp = a.take<int64_t>(scan_tmp_count((int64_t)(n + radix_tmp_count(N))));
+    w.scalars = a.take<int64_t>(4);
+    w.ok = a.ok;
+    w.used = a.used;
+    return w;
+}
+
+// int64 [N,4] -> int4 keys; every column narrowed to int32 like Point<3>/Int (voxelize.cpp:95-97)
+__global__ void k_vox_keys(const int64_t *__restrict__ coords, int64_t N, int4 *__restrict__ keys) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const longlong2 *p = reinterpret_cast<const longlong2 *>(coords) + i * 2;
+    longlong2 a = __ldg(p), b = __ldg(p + 1);
+    keys[i] = make_int4((int)a.x, (int)a.y, (int)b.x, (int)b.y);
+}
+
+__global__ void k_max_i32(const int32_t *__restrict__ v, const int64_t *__restrict__ n_dev, int64_t *out) {
+    const int64_t n = *n_dev;
+    int m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, v[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax((unsigned long long *)out, (unsigned long long)m);
+}
+
+// output_map rows [cnt, p0 < p1 < ..., 0-pad] (voxelize.cpp:139-149; modes 0/1/2: :121-138) and
+// output_coords = coords row of rule[1] (voxelize.cpp:39-47)
+__global__ void k_vox_fill(const int64_t *__restrict__ coords, const int32_t *__restrict__ cnt,
+                           const int32_t *__restrict__ voff, const uint32_t *__restrict__ sorted, int32_t M,
+                           int32_t W, int mode, int64_t *__restrict__ out_coords, int32_t *__restrict__ out_map) {
+    const int64_t total = (int64_t)M * W;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(t / W), j = (int)(t - (int64_t)v * W);
+        const int n = cnt[v], off = voff[v];
+        int val;
+        if (mode == 3 || mode == 4) {
+            val = (j == 0) ? n : (j <= n ? (int)sorted[off + j - 1] : 0);
+        } else {
+            val = (j == 0) ? 1 : (int)sorted[mode == 2 ? off + n - 1 : off];
+        }
+        out_map[t] = val;
+    }
+    const int64_t total_c = (int64_t)M * 4;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total_c;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(t >> 2), c = (int)(t & 3);
+        const int n = cnt[v], off = voff[v];
+        const int first = (int)sorted[mode == 2 ? off + n - 1 : off];
+        out_coords[t] = coords[(int64_t)first * 4 + c];
+    }
+}
+
+// =================================================================================================
+// voxelize_fp / voxelize_bp
+// One thread owns one (voxel row, vector column): the per-element operation order is the
+// reference's -- fl(mult * x) added left to right starting from +0 (voxelize.cu:15-19) -- so the
+// result is bit-identical, while consecutive threads touch consecutive addresses of both the voxel
+// row and the gathered point row.
+// =================================================================================================
+template <int V> struct Vec;
+template <> struct Vec<1> { using T = float; };
+template <> struct Vec<2> { using T = float2; };
+template <> struct Vec<4> { using T = float4; };
+
+template <int V> __device__ __forceinline__ void vzero(typename Vec<V>::T &a);
+template <> __device__ __forceinline__ void vzero<1>(float &a) { a = 0.f; }
+template <> __device__ __forceinline__ void vzero<2>(float2 &a) { a = make_float2(0.f, 0.f); }
+template <> __device__ __forceinline__ void vzero<4>(float4 &a) { a = make_float4(0.f, 0.f, 0.f, 0.f); }
+
+__device__ __forceinline__ void vmuladd(float &a, float m, float x) { a = __fadd_rn(a, __fmul_rn(m, x)); }
+__device__ __forceinline__ void vmuladd(float2 &a, float m, float2 x) {
+    vmuladd(a.x, m, x.x); vmuladd(a.y, m, x.y);
+}
+__device__ __forceinline__ void vmuladd(float4 &a, float m, float4 x) {
+    vmuladd(a.x, m, x.x); vmuladd(a.y, m, x.y); vmuladd(a.z, m, x.z); vmuladd(a.w, m, x.w);
+}
+__device__ __forceinline__ float vscale(float m, float x) { return __fmul_rn(m, x); }
+__device__ __forceinline__ float2 vscale(float m, float2 x) { return make_float2(__fmul_rn(m, x.x), __fmul_rn(m, x.y)); }
+__device__ __forceinline__ float4 vscale(float m, float4 x) {
+    return make_float4(__fmul_rn(m, x.x), __fmul_rn(m, x.y), __fmul_rn(m, x.z), __fmul_rn(m, x.w));
+}
+__device__ __forceinline__ void vred(float *p, float v) { atomicAdd(p, v); }
+__device__ __forceinline__ void vred(float2 *p, float2 v) { atomicAdd(p, v); }
+__device__ __forceinline__ void vred(float4 *p, float4 v) { atomicAdd(p, v); }
+
+template <int V>
+__global__ void __launch_bounds__(256) k_voxelize_fp(const float *__restrict__ feats, float *__restrict__ out,
+                                                     const int32_t *__restrict__ rules, int32_t M, int32_t W,
+                                                     int32_t Cv, int average) {
+    using T = typename Vec<V>::T;
+    const T *__restrict__ f = reinterpret_cast<const T *>(feats);
+    T *__restrict__ o = reinterpret_cast<T *>(out);
+    const int64_t total = (int64_t)M * Cv;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(t / Cv), c = (int)(t - (int64_t)v * Cv);
+        const int32_t *r = rules + (int64_t)v * W;
+        const int n = __ldg(r);
+        const float mult = (average && n > 0) ? __fdiv_rn(1.0f, (float)n) : 1.0f;
+        T acc;
+        vzero<V>(acc);
+        int i = 1;
+        for (; i + 3 <= n; i += 4) {   // four independent gathers in flight, then the ordered adds
+            const int r0 = __ldg(r + i), r1 = __ldg(r + i + 1), r2 = __ldg(r + i + 2), r3 = __ldg(r + i + 3);
+            const T x0 = __ldg(f + (int64_t)r0 * Cv + c), x1 = __ldg(f + (int64_t)r1 * Cv + c);
+            const T x2 = __ldg(f + (int64_t)r2 * Cv + c), x3 = __ldg(f + (int64_t)r3 * Cv + c);
+            vmuladd(acc, mult, x0); vmuladd(acc, mult, x1); vmuladd(acc, mult, x2); vmuladd(acc, mult, x3);
+        }
+        for (; i <= n; i++) {
+            const int r0 = __ldg(r + i);
+            vmuladd(acc, mult, __ldg(f + (int64_t)r0 * Cv + c));
+        }
+        __stcs(o + t, acc);
+    }
+}
+
+template <int V>
+__global__ void __launch_bounds__(256) k_voxelize_bp(const float *__restrict__ d_out, float *d_feats,
+                                                     const int32_t *__restrict__ rules, int32_t M, int32_t W,
+                                                     int32_t Cv, int average) {
+    using T = typename Vec<V>::T;
+    const T *__restrict__ g = reinterpret_cast<const T *>(d_out);
+    T *df = reinterpret_cast<T *>(d_feats);
+    const int64_t total = (int64_t)M * Cv;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(t / Cv), c = (int)(t - (int64_t)v * Cv);
+        const int32_t *r = rules + (int64_t)v * W;
+        const int n = __ldg(r);
+        if (n <= 0) continue;
+        const float mult = average ? __fdiv_rn(1.0f, (float)n) : 1.0f;
+        const T val = vscale(mult, __ldcs(g + t));
+        for (int i = 1; i <= n; i++) vred(df + (int64_t)__ldg(r + i) * Cv + c, val);
+    }
+}
+
+static int pick_vec(const void *a, const void *b, int C) {
+    const uintptr_t pa = (uintptr_t)a, pb = (uintptr_t)b;
+    if (C % 4 == 0 && pa % 16 == 0 && pb % 16 == 0) return 4;
+    if (C % 2 == 0 && pa % 8 == 0 && pb % 8 == 0) return 2;
+    return 1;
+}
+
+static int voxelize_launch(bool fp, const float *src, float *dst, const int32_t *rules, int32_t M,
+                           int32_t maxActive, int32_t C, int average, cudaStream_t st) {
+    PG_CHECK_ARG(M >= 0 && maxActive >= 0 && C >= 0, "negative size");
+    if (M == 0 || C == 0) return PG_OK;
+    PG_CHECK_ARG(src && dst && rules, "null pointer");
+    const int V = pick_vec(src, dst, C);
+    const int Cv = C / V, W = maxActive + 1;
+    const int64_t total = (int64_t)M * Cv;
+    const unsigned grid = (unsigned)(div_up(total, 256) < (int64_t)kNumSM * 64 ? div_up(total, 256) : (int64_t)kNumSM * 64);
+#define PG_VOX(VV)                                                                                     \
+    if (fp) k_voxelize_fp<VV><<<grid, 256, 0, st>>>(src, dst, rules, M, W, Cv, average);               \
+    else k_voxelize_bp<VV><<<grid, 256, 0, st>>>(src, dst, rules, M, W, Cv, average)
+    if (V == 4) { PG_VOX(4); } else if (V == 2) { PG_VOX(2); } else { PG_VOX(1); }
+#undef PG_VOX
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
+}  // namespace pg
+
+using namespace pg;
+
+extern "C" size_t pg_voxelize_idx_workspace_bytes(int64_t N) {
+    if (N < 0) N = 0;
+    return vox_layout(nullptr, 0, N).used + 256;
+}
+
+extern "C" int pg_voxelize_idx_map(const int64_t *coords, int64_t N, int mode, int32_t *input_map, void *ws,
+                                   size_t ws_bytes, int32_t *host_sizes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PG_CHECK_ARG(N >= 0 && N < 0x7fffffff, "N out of range");
+    PG_CHECK_ARG(mode >= 0 && mode <= 4, "mode must be 0..4");
+    PG_CHECK_ARG(host_sizes, "null host_sizes");
+    host_sizes[0] = 0;
+    host_sizes[1] = 1;   // voxelize.cpp:139 -- maxActive starts at 1, also for N == 0
+    if (N == 0) return PG_OK;
+    PG_CHECK_ARG(coords && input_map && ws, "null pointer");
+    VoxWs w = vox_layout(ws, ws_bytes, N);
+    if (!w.ok) { set_error("pg_voxelize_idx_map: workspace too small (%zu < %zu)", ws_bytes, w.used); return PG_EWORKSPACE; }
+    PG_CUDA(cudaMemsetAsync(w.scalars, 0, 4 * sizeof(int64_t), st));
+    k_vox_keys<<<(unsigned)div_up(N, 256), 256, 0, st>>>(coords, N, w.keys);
+    PG_TRY(group_int4(w.keys, N, w.tab, w.pslot, input_map, w.cnt, w.scalars, w.scan_tmp, st));
+    k_max_i32<<<kNumSM * 4, 256, 0, st>>>(w.cnt, w.scalars, w.scalars + 1);
+    PG_LAUNCH_CHECK();
+    int64_t h[2];
+    PG_CUDA(cudaMemcpyAsync(h, w.scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaStreamSynchronize(st));
+    host_sizes[0] = (int32_t)h[0];
+    host_sizes[1] = (mode == 3 || mode == 4) ? (int32_t)(h[1] > 1 ? h[1] : 1) : 1;
+    return PG_OK;
+}
+
+extern "C" int pg_voxelize_idx_fill(const int64_t *coords, const int32_t *input_map, int64_t N, int32_t M,
+                                    int32_t maxActive, int mode, void *ws, size_t ws_bytes, int64_t *output_coords, int32_t *output_map,
+                                    void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PG_CHECK_ARG(N >= 0 && M >= 0 && M <= N && maxActive >= 1, "bad sizes");
+    PG_CHECK_ARG(mode >= 0 && mode <= 4, "mode must be 0..4");
+    if (N == 0 || M == 0) return PG_OK;
+    PG_CHECK_ARG(coords && input_map && ws && output_coords && output_map, "null pointer");
+    VoxWs w = vox_layout(ws, ws_bytes, N);
+    if (!w.ok) { set_error("pg_voxelize_idx_fill: workspace too small"); return PG_EWORKSPACE; }
+    int bits = 0;
+    while ((1ll << bits) < (long long)M) bits++;
+    int res = 0;
+    // stable sort of (voxel id, point) by voxel id: points end up ascending inside every voxel
+    PG_TRY(radix_sort_pairs(reinterpret_cast<const uint32_t *>(input_map), nullptr, w.kA, w.vA, w.kB, w.vB, N, bits, w.hist, w.scan_tmp, st, &res));
+    const uint32_t *sorted = res == 0 ? w.vA : w.vB;
+    PG_TRY(scan_exclusive_i32(w.cnt, w.voff, M, nullptr, w.scan_tmp, st));
+    const int W = maxActive + 1;
+    const int64_t total = (int64_t)M * W;
+    const unsigned grid = (unsigned)(div_up(total, 256) < (int64_t)kNumSM * 32 ? div_up(total, 256) : (int64_t)kNumSM * 32);
+    k_vox_fill<<<grid, 256, 0, st>>>(coords, w.cnt, w.voff, sorted, M, W, mode, output_coords, output_map);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
+extern "C" int pg_voxelize_fp(const float *feats, float *out, const int32_t *rules, int32_t M, int32_t maxActive,
+                              int32_t C, int average, void *stream) {
+    return voxelize_launch(true, feats, out, rules, M, maxActive, C, average, (cudaStream_t)stream);
+}
+extern "C" int pg_voxelize_bp(const float *d_out, float *d_feats, const int32_t *rules, int32_t M,
+                              int32_t maxActive, int32_t C, int average, void *stream) {
+    return voxelize_launch(false, d_out, d_feats, rules, M, maxActive, C, average, (cudaStream_t)stream);
+}
+// point_recover_fp = voxelize_bp(average = false), point_recover_bp = voxelize_fp(average = false)
+// (voxelize.cpp:189,201)
+extern "C" int pg_point_recover_fp(const float *feats, float *out, const int32_t *rules, int32_t M,
+                                   int32_t maxActive, int32_t C, void *stream) {
+    return voxelize_launch(false, feats, out, rules, M, maxActive, C, 0, (cudaStream_t)stream);
+}
+extern "C" int pg_point_recover_bp(const float *d_out, float *d_feats, const int32_t *rules, int32_t M,
+                                   int32_t maxActive, int32_t C, void *stream) {
+    return voxelize_launch(true, d_out, d_feats, rules, M, maxActive, C, 0, (cudaStream_t)stream);
+}

@@ -1,0 +1,291 @@
+"""The reference's Python operator API (lib/pointgroup_ops/functions/pointgroup_ops.py) on the
+B200 kernels: the same ten callables -- voxelization_idx, voxelization, point_recover,
+ballquery_batch_p, bfs_cluster, roipool, get_iou, sec_mean, sec_min, sec_max -- with the same
+argument meaning, return conventions, autograd behaviour and assertion behaviour, so
+model/pointgroup.py, lib/dataset/pipeline.py and lib/solver/pointgroup.py can import this module in
+place of the original.
+
+What changed underneath (none of it visible in results):
+  * outputs that the kernels fully overwrite are allocated uninitialised instead of zero-filled;
+  * ball query is count -> exact allocation -> fill, so the reference's grow-and-retry loop
+    (functions/pointgroup_ops.py:135-142) is gone and ``meanActive`` is only a hint;
+  * voxelization_idx and bfs_cluster -- CPU-only in the reference -- run on the GPU.  CPU inputs (what
+    the reference's callers pass, model/pointgroup.py:169,297) are staged through the current CUDA
+    device and the results come back on the input's device; CUDA inputs stay on the device.
+There is no CPU fallback: without the CUDA library or a GPU these functions raise.
+"""
+import torch
+from torch.autograd import Function
+
+from . import PG_OP
+
+
+def _cuda_of(t):
+    return t if t.is_cuda else t.to(PG_OP._compute_device(t))
+
+
+class Voxelization_Idx(Function):
+    @staticmethod
+    def forward(ctx, coords, batchsize, mode=4):
+        '''
+        :param coords:  long (N, dimension + 1), dimension = 3, column 0 = batch index
+        :param batchsize
+        :param mode: int 4=mean
+        :return: output_coords:  long (M, dimension + 1) (M <= N)
+        :return: input_map: int (N,)
+        :return: output_map: int (M, (maxActive + 1))
+        (functions/pointgroup_ops.py:11-39; all three on coords.device)
+        '''
+        assert coords.is_contiguous()
+        oc, im, om = PG_OP.voxelize_idx_impl(_cuda_of(coords), mode)
+        if not coords.is_cuda:
+            oc, im, om = oc.cpu(), im.cpu(), om.cpu()
+        ctx.mark_non_differentiable(oc, im, om)
+        return oc, im, om
+
+    @staticmethod
+    def backward(ctx, a=None, b=None, c=None):
+        return None, None, None
+
+
+voxelization_idx = Voxelization_Idx.apply
+
+
+class Voxelization(Function):
+    @staticmethod
+    def forward(ctx, feats, map_rule, mode=4):
+        '''
+        :param map_rule: cuda int (M, (maxActive + 1))
+        :param feats: cuda float (N, C)
+        :return: output_feats: cuda float (M, C)
+        (functions/pointgroup_ops.py:42-75)
+        '''
+        assert map_rule.is_contiguous()
+        assert feats.is_contiguous()
+        N, C = feats.size()
+        M = map_rule.size(0)
+        maxActive = map_rule.size(1) - 1
+        output_feats = torch.empty((M, C), dtype=torch.float32, device=feats.device)
+        ctx.for_backwards = (map_rule, mode, maxActive, N)
+        PG_OP.voxelize_fp(feats, output_feats, map_rule, mode, M, maxActive, C)
+        return output_feats
+
+    @staticmethod
+    def backward(ctx, d_output_feats):
+        map_rule, mode, maxActive, N = ctx.for_backwards
+        M, C = d_output_feats.size()
+        d_feats = torch.zeros((N, C), dtype=torch.float32, device=d_output_feats.device)
+        PG_OP.voxelize_bp(d_output_feats.contiguous(), d_feats, map_rule, mode, M, maxActive, C)
+        return d_feats, None, None
+
+
+voxelization = Voxelization.apply
+
+
+class PointRecover(Function):
+    @staticmethod
+    def forward(ctx, feats, map_rule, nPoint):
+        '''
+        :param feats: cuda float M * C
+        :param map_rule: cuda int M * (maxActive + 1)
+        :param nPoint: int
+        :return: output_feats: cuda float N * C
+        (functions/pointgroup_ops.py:78-112)
+        '''
+        assert map_rule.is_contiguous()
+        assert feats.is_contiguous()
+        M, C = feats.size()
+        maxActive = map_rule.size(1) - 1
+        output_feats = torch.zeros((nPoint, C), dtype=torch.float32, device=feats.device)
+        ctx.for_backwards = (map_rule, maxActive, M)
+        PG_OP.point_recover_fp(feats, output_feats, map_rule, M, maxActive, C)
+        return output_feats
+
+    @staticmethod
+    def backward(ctx, d_output_feats):
+        map_rule, maxActive, M = ctx.for_backwards
+        N, C = d_output_feats.size()
+        d_feats = torch.empty((M, C), dtype=torch.float32, device=d_output_feats.device)
+        PG_OP.point_recover_bp(d_output_feats.contiguous(), d_feats, map_rule, M, maxActive, C)
+        return d_feats, None, None
+
+
+point_recover = PointRecover.apply
+
+
+class BallQueryBatchP(Function):
+    @staticmethod
+    def forward(ctx, coords, batch_idxs, batch_offsets, radius, meanActive):
+        '''
+        :param coords: (n, 3) float
+        :param batch_idxs: (n) int
+        :param batch_offsets: (B+1) int
+        :param radius: float
+        :param meanActive: int (the reference's initial buffer guess; unused here)
+        :return: idx (nActive), int -- per point ascending, segments laid out in point order
+        :return: start_len (n, 2), int
+        (functions/pointgroup_ops.py:115-150)
+        '''
+        assert coords.is_contiguous() and coords.is_cuda
+        assert batch_idxs.is_contiguous() and batch_idxs.is_cuda
+        assert batch_offsets.is_contiguous() and batch_offsets.is_cuda
+        start_len, nActive, ws = PG_OP.ballquery_count_impl(coords, batch_idxs, batch_offsets, radius)
+        idx = torch.empty(nActive, dtype=torch.int32, device=coords.device)
+        PG_OP.ballquery_fill_impl(coords, radius, start_len, idx, ws)
+        ctx.mark_non_differentiable(idx, start_len)
+        return idx, start_len
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None, None, None, None
+
+
+ballquery_batch_p = BallQueryBatchP.apply
+
+
+class BFSCluster(Function):
+    @staticmethod
+    def forward(ctx, semantic_label, ball_query_idxs, start_len, threshold):
+        '''
+        :param semantic_label: (N), int
+        :param ball_query_idxs: (nActive), int
+        :param start_len: (N, 2), int
+        :return: cluster_idxs:  int (sumNPoint, 2), dim 0 for cluster_id, dim 1 for corresponding point idxs in N
+        :return: cluster_offsets: int (nCluster + 1)
+        (functions/pointgroup_ops.py:153-182; outputs on semantic_label.device like semantic_label.new())
+        '''
+        assert semantic_label.is_contiguous()
+        assert ball_query_idxs.is_contiguous()
+        assert start_len.is_contiguous()
+        dev = PG_OP._compute_device(semantic_label)
+        ci, co, _ = PG_OP.bfs_cluster_impl(semantic_label.to(dev), ball_query_idxs.to(dev), start_len.to(dev),
+                                           threshold)
+        if not semantic_label.is_cuda:
+            ci, co = ci.cpu(), co.cpu()
+        ctx.mark_non_differentiable(ci, co)
+        return ci, co
+
+    @staticmethod
+    def backward(ctx, a=None, b=None):
+        return None, None, None, None
+
+
+bfs_cluster = BFSCluster.apply
+
+
+class RoiPool(Function):
+    @staticmethod
+    def forward(ctx, feats, proposals_offset):
+        '''
+        :param feats: (sumNPoint, C) float
+        :param proposals_offset: (nProposal + 1) int
+        :return: output_feats (nProposal, C) float
+        (functions/pointgroup_ops.py:185-221)
+        '''
+        nProposal = proposals_offset.size(0) - 1
+        sumNPoint, C = feats.size()
+        assert feats.is_contiguous()
+        assert proposals_offset.is_contiguous()
+        output_feats = torch.empty((nProposal, C), dtype=torch.float32, device=feats.device)
+        output_maxidx = torch.empty((nProposal, C), dtype=torch.int32, device=feats.device)
+        PG_OP.roipool_fp(feats, proposals_offset, output_feats, output_maxidx, nProposal, C)
+        ctx.for_backwards = (output_maxidx, proposals_offset, sumNPoint)
+        return output_feats
+
+    @staticmethod
+    def backward(ctx, d_output_feats):
+        nProposal, C = d_output_feats.size()
+        output_maxidx, proposals_offset, sumNPoint = ctx.for_backwards
+        d_feats = torch.zeros((sumNPoint, C), dtype=torch.float32, device=d_output_feats.device)
+        PG_OP.roipool_bp(d_feats, proposals_offset, output_maxidx, d_output_feats.contiguous(), nProposal, C)
+        return d_feats, None
+
+
+roipool = RoiPool.apply
+
+
+class GetIoU(Function):
+    @staticmethod
+    def forward(ctx, proposals_idx, proposals_offset, instance_labels, instance_pointnum):
+        '''
+        :param proposals_idx: (sumNPoint), int
+        :param proposals_offset: (nProposal + 1), int
+        :param instance_labels: (N), long, 0~total_nInst-1, -1
+        :param instance_pointnum: (total_nInst), int
+        :return: proposals_iou: (nProposal, total_nInst), float
+        (functions/pointgroup_ops.py:224-253)
+        '''
+        nInstance = instance_pointnum.size(0)
+        nProposal = proposals_offset.size(0) - 1
+        assert proposals_idx.is_contiguous() and proposals_idx.is_cuda
+        assert proposals_offset.is_contiguous() and proposals_offset.is_cuda
+        assert instance_labels.is_contiguous() and instance_labels.is_cuda
+        assert instance_pointnum.is_contiguous() and instance_pointnum.is_cuda
+        proposals_iou = torch.empty((nProposal, nInstance), dtype=torch.float32, device=proposals_idx.device)
+        PG_OP.get_iou(proposals_idx, proposals_offset, instance_labels, instance_pointnum, proposals_iou,
+                      nInstance, nProposal)
+        return proposals_iou
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None, None, None
+
+
+get_iou = GetIoU.apply
+
+
+def _sec_forward(fn, inp, offsets):
+    nProposal = offsets.size(0) - 1
+    C = inp.size(1)
+    assert inp.is_contiguous()
+    assert offsets.is_contiguous()
+    out = torch.empty((nProposal, C), dtype=torch.float32, device=inp.device)
+    fn(inp, offsets, out, nProposal, C)
+    return out
+
+
+class SecMean(Function):
+    @staticmethod
+    def forward(ctx, inp, offsets):
+        '''
+        :param inp: (N, C) float
+        :param offsets: (nProposal + 1) int
+        :return: out (nProposal, C) float
+        (functions/pointgroup_ops.py:256-281)
+        '''
+        return _sec_forward(PG_OP.sec_mean, inp, offsets)
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None
+
+
+sec_mean = SecMean.apply
+
+
+class SecMin(Function):
+    @staticmethod
+    def forward(ctx, inp, offsets):
+        '''(functions/pointgroup_ops.py:284-309)'''
+        return _sec_forward(PG_OP.sec_min, inp, offsets)
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None
+
+
+sec_min = SecMin.apply
+
+
+class SecMax(Function):
+    @staticmethod
+    def forward(ctx, inp, offsets):
+        '''(functions/pointgroup_ops.py:312-337)'''
+        return _sec_forward(PG_OP.sec_max, inp, offsets)
+
+    @staticmethod
+    def backward(ctx, a=None):
+        return None, None
+
+
+sec_max = SecMax.apply

@@ -1,0 +1,152 @@
+/*
+ * pg_b200.h -- C ABI of libpg_b200.so: the PointGroup proposal ops of D3Net (lib/pointgroup_ops)
+ * as hand-written sm_100a CUDA kernels.
+ *
+ * This is the drop-in boundary.  Every entry point replaces one function of the reference's native
+ * module PG_OP (lib/pointgroup_ops/src/pointgroup_ops_api.cpp:6-24); the citation on each
+ * declaration names the reference interface it stands in for.  Signatures carry plain pointers and
+ * sizes only -- no torch types.  All data pointers are DEVICE pointers on the current CUDA device
+ * unless the name starts with `host_`.  `stream` is a cudaStream_t passed as void*.
+ *
+ * Conventions
+ *   - return value: 0 (PG_OK) on success, otherwise a negative PG_E* code or a positive cudaError_t;
+ *     pg_last_error() returns a thread-local message for the last failure.  Nothing calls exit()
+ *     (the reference's ball query does, bfs_cluster.cu:82-86).
+ *   - fixed-size outputs are written in place.  Ops that ACCUMULATE (voxelize_bp, roipool_bp) add
+ *     onto what the buffer holds, exactly like the reference's atomicAdd kernels, so the caller
+ *     zero-fills them (functions/pointgroup_ops.py:57,70,93,106,215).  All other outputs are fully
+ *     overwritten and need no zero fill.
+ *   - variable-size outputs (voxelize_idx, ballquery, bfs_cluster) are two-phase: `*_count`/`*_map`
+ *     computes the sizes, synchronises `stream` once and stores them through a host pointer; the
+ *     caller allocates exactly and calls `*_fill`.  The workspace passed to both phases must be the
+ *     same untouched buffer.  This replaces the reference's resize_() inside native code
+ *     (voxelize.cpp:22-26, bfs_cluster.cpp:103-106) and its ball-query retry loop
+ *     (functions/pointgroup_ops.py:135-142).
+ *   - the library keeps no state between calls, owns no device memory and never allocates:
+ *     scratch space is a caller-provided workspace sized by the matching `*_workspace_bytes`.
+ *   - kernels are launched on `stream`; only the `*_count`/`*_map` phases synchronise it.
+ */
+#ifndef PG_B200_H_
+#define PG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PG_OK 0
+#define PG_EINVAL (-1)     /* bad argument (null pointer, negative size, unsupported mode) */
+#define PG_EWORKSPACE (-2) /* workspace too small */
+#define PG_EOVERFLOW (-3)  /* a count does not fit the int32 the reference's tensors use */
+
+#define PG_BALLQUERY_CAP 1000 /* bfs_cluster.cu:20,38 -- at most the first 1000 neighbours by index */
+
+const char *pg_last_error(void);
+int pg_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * voxelize_idx     replaces PG_OP.voxelize_idx (src/pointgroup_ops.cpp:13, voxelize.cpp:11-152)
+ * coords: int64 [N,4] (batch, x, y, z); every column is narrowed to int32 like the reference's
+ * Point<3>/Int (datatype.h:9-11).  Voxel ids follow first occurrence in input order.
+ * phase 1 writes input_map[N] and host_sizes = {M, maxActive}; phase 2 writes
+ * output_coords int64 [M,4] and output_map int32 [M, maxActive+1] = [cnt, p0 < p1 < ..., 0-pad].
+ * mode: 0/1 keep the first point, 2 the last, 3 sum, 4 mean (maxActive = 1 unless mode is 3 or 4).
+ * ---------------------------------------------------------------------------------------------- */
+size_t pg_voxelize_idx_workspace_bytes(int64_t N);
+int pg_voxelize_idx_map(const int64_t *coords, int64_t N, int mode, int32_t *input_map, void *ws,
+                        size_t ws_bytes, int32_t *host_sizes, void *stream);
+int pg_voxelize_idx_fill(const int64_t *coords, const int32_t *input_map, int64_t N, int32_t M,
+                         int32_t maxActive, int mode, void *ws, size_t ws_bytes, int64_t *output_coords,
+                         int32_t *output_map, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * voxelize_fp / voxelize_bp     replace PG_OP.voxelize_fp / voxelize_bp
+ *                               (src/pointgroup_ops.cpp:18,25; voxelize.cu:10-53)
+ * point_recover_fp / _bp        replace PG_OP.point_recover_fp / _bp (pointgroup_ops.cpp:30,35;
+ *                               voxelize.cpp:182-202): the same two kernels with average = 0.
+ * fp: out[v][c] = sum_i fl(mult * feats[r_i][c]) left to right from 0, mult = fl(1/cnt) if average.
+ * bp: d_feats[r_i][c] += fl(mult * d_out[v][c]).
+ * ---------------------------------------------------------------------------------------------- */
+int pg_voxelize_fp(const float *feats, float *out, const int32_t *rules, int32_t M, int32_t maxActive,
+                   int32_t C, int average, void *stream);
+int pg_voxelize_bp(const float *d_out, float *d_feats, const int32_t *rules, int32_t M,
+                   int32_t maxActive, int32_t C, int average, void *stream);
+int pg_point_recover_fp(const float *feats, float *out, const int32_t *rules, int32_t M,
+                        int32_t maxActive, int32_t C, void *stream);
+int pg_point_recover_bp(const float *d_out, float *d_feats, const int32_t *rules, int32_t M,
+                        int32_t maxActive, int32_t C, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ballquery_batch_p     replaces PG_OP.ballquery_batch_p (bfs_cluster.h:15, bfs_cluster.cu:15-90)
+ * Per point i: every k of the same scene with fma(dz,dz,fma(dx,dx,dy*dy)) < fl(r*r), ascending k,
+ * at most the first PG_BALLQUERY_CAP.  phase 1 writes start_len int32 [n,2] = (start, cnt) with
+ * segments laid out in point order (deterministic; the reference's atomicAdd placement is not) and
+ * host_total = sum cnt; phase 2 writes idx int32 [total].
+ * ---------------------------------------------------------------------------------------------- */
+size_t pg_ballquery_workspace_bytes(int64_t n);
+int pg_ballquery_count(const float *xyz, const int32_t *batch_idxs, const int32_t *batch_offsets,
+                       int32_t n, int32_t B, float radius, int32_t *start_len, void *ws, size_t ws_bytes,
+                       int64_t *host_total, void *stream);
+int pg_ballquery_fill(const float *xyz, int32_t n, float radius, const int32_t *start_len, int32_t *idx,
+                      int64_t idx_capacity, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * bfs_cluster     replaces PG_OP.bfs_cluster (bfs_cluster.h:18, bfs_cluster.cpp:28-112)
+ * Connected components of the neighbour graph restricted to equal semantic labels; components with
+ * >= threshold points are kept and numbered by ascending smallest member (= the reference's seed
+ * order).  Members are emitted in ascending point order (the reference emits BFS order; membership
+ * and cluster order are identical).  nActive = length of ball_query_idxs.  phase 1 stores
+ * host_sizes = {nCluster, sumNPoint, 1 if the generic path ran}; phase 2
+ * writes cluster_idxs int32 [sumNPoint,2] = (cluster_id, point) and cluster_offsets int32 [nCluster+1].
+ * `generic` != 0 forces the any-digraph propagation path; 0 picks it automatically
+ * when the neighbour lists are not a truncated symmetric relation.
+ * ---------------------------------------------------------------------------------------------- */
+size_t pg_bfs_cluster_workspace_bytes(int64_t N);
+int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t *ball_query_idxs,
+                         const int32_t *start_len, int32_t N, int64_t nActive, int32_t threshold, int generic,
+                         void *ws, size_t ws_bytes, int32_t *host_sizes, void *stream);
+int pg_bfs_cluster_fill(int32_t N, int32_t nCluster, int32_t sumNPoint, void *ws, size_t ws_bytes,
+                        int32_t *cluster_idxs, int32_t *cluster_offsets, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * roipool_fp / roipool_bp     replace PG_OP.roipool_fp / roipool_bp (roipool.h:15,21; roipool.cu:12-57)
+ * fp: per proposal and channel, max over rows [offsets[p], offsets[p+1]) with the LOWEST row on ties,
+ * -inf / argmax -1 when nothing compares greater than -inf (empty proposal, NaN, -inf).
+ * nRows = rows of feats (bounds the tiling; rows outside [offsets[0], offsets[nProposal]) are ignored).
+ * ws: nProposal * C * 8 bytes.
+ * bp: d_feats[maxidx[p][c]][c] += d_out[p][c] (entries with maxidx < 0 are skipped; the reference
+ * writes out of bounds there, roipool.cu:45-46).
+ * ---------------------------------------------------------------------------------------------- */
+size_t pg_roipool_workspace_bytes(int32_t nProposal, int32_t C);
+int pg_roipool_fp(const float *feats, const int32_t *offsets, float *out, int32_t *maxidx, int32_t nRows,
+                  int32_t nProposal, int32_t C, void *ws, size_t ws_bytes, void *stream);
+int pg_roipool_bp(float *d_feats, const int32_t *offsets, const int32_t *maxidx, const float *d_out,
+                  int32_t nProposal, int32_t C, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * sec_mean / sec_min / sec_max     replace PG_OP.sec_mean / sec_min / sec_max
+ *                                  (sec_mean.h:14,17,20; sec_mean.cu:12-86)
+ * mean = sum_i fl(x_i / (float)len) accumulated left to right (bit-exact with the reference's order);
+ * min / max from +inf / -inf with strict compares.
+ * ---------------------------------------------------------------------------------------------- */
+int pg_sec_mean(const float *inp, const int32_t *offsets, float *out, int32_t nRows, int32_t nProposal,
+                int32_t C, void *stream);
+int pg_sec_min(const float *inp, const int32_t *offsets, float *out, int32_t nRows, int32_t nProposal,
+               int32_t C, void *stream);
+int pg_sec_max(const float *inp, const int32_t *offsets, float *out, int32_t nRows, int32_t nProposal,
+               int32_t C, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * get_iou     replaces PG_OP.get_iou (get_iou.h:16, get_iou.cu:12-38)
+ * iou[p][g] = (float)((double)(float)inter / ((double)(float)(|P| + pointnum[g] - inter) + 1e-5)).
+ * ---------------------------------------------------------------------------------------------- */
+int pg_get_iou(const int32_t *proposals_idx, const int32_t *proposals_offset,
+               const int64_t *instance_labels, const int32_t *instance_pointnum, float *proposals_iou,
+               int32_t nInstance, int32_t nProposal, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PG_B200_H_ */
