@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- scenes/sec of the PointGroup proposal hot path (voxelize + cluster + roipool + IoU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+A "step" is one pass of d3net_b200.chain.proposal_chain over one collated batch of 8 synthetic
+150k-point ScanNet-shaped scenes per GPU (BASELINE.json configs[1]; configs[2] under torchrun: each
+rank owns its own 8 scenes -- weak scaling, scene-per-GPU -- and the packed per-scene proposal
+tensors are all-gathered over NCCL every step).  One JSON line is printed by rank 0.
+
+  value      scenes/sec over all ranks, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same through the public API with HOST (pinned) inputs: H2D of the step's inputs and
+             D2H of its results inside the timed region
+  roofline   the dominant kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json
+  cpu_baseline  the CPU restatement of the same chain (oracle/, with the reference's own compiled
+             voxelize_idx / bfs_cluster when oracle/_ref exists) on a bounded sample, rank 0, N=1
+  --impl reference  times only that CPU path (the reference has no GPU implementation of
+             voxelize_idx / bfs_cluster and no multi-GPU path of its own)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from d3net_b200 import chain, scenes  # noqa: E402
+
+METRIC = "scenes/sec (voxelize+cluster+roipool)"
+UNIT = "scenes/s"
+SCENES_PER_GPU = 8
+POINTS = 150_000
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# algorithmic bytes per op (restated in DESIGN.md)
+# ----------------------------------------------------------------------------------------------------
+def algorithmic_bytes(batch, out):
+    N = batch["locs"].shape[0]
+    C = batch["feats"].shape[1]
+    M, W = out["voxel_feats"].shape[0], None
+    n = out["n_object_points"]
+    S = out["proposals_idx"].shape[0]
+    nP = out["proposals_offset"].numel() - 1
+    nI = batch["instance_pointnum"].numel()
+    b = {}
+    b["voxelization(scene)"] = 4 * N * C + 4 * M * C + 4 * M * 2          # + the map (>= 2 ints per row)
+    b["ballquery(shift).fill"] = 16 * n + 8 * n + 4 * out["nActive_shift"]
+    b["ballquery(raw).fill"] = 16 * n + 8 * n + 4 * out["nActive_raw"]
+    b["bfs_cluster(shift)"] = 4 * n + 4 * out["nActive_shift"] + 8 * n + 8 * S // 2
+    b["bfs_cluster(raw)"] = 4 * n + 4 * out["nActive_raw"] + 8 * n + 8 * S // 2
+    b["roipool"] = 4 * S * 16 + 4 * (nP + 1) + 8 * nP * 16
+    b["get_iou"] = 4 * S + 8 * S + 4 * nI + 4 * (nP + 1) + 4 * nP * nI
+    return b
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU leg (oracle / reference-compiled ops) -- the only place bench.py touches oracle/
+# ----------------------------------------------------------------------------------------------------
+def cpu_chain_rate(budget_s, steps, warmup):
+    """Times the CPU restatement of the chain on a bounded sample.  Returns (scene-equivalents/s,
+    ms per step, description, cores, kind)."""
+    from oracle.ops_adapter import OracleOps
+    from oracle import pg_oracle
+    cores = os.cpu_count() or 1
+    pg_oracle.set_threads(cores)
+    torch.set_num_threads(cores)
+    ops = OracleOps(use_ref=True)
+    kind = "port"
+    # calibrate on a 15k-point scene, then pick the sample size that fits the budget
+    cal = chain.batch_to_device(scenes.make_batch(1, 15000, config_id=2, geometry_points=15000), None)
+    t0 = time.perf_counter()
+    chain.proposal_chain(ops, cal)
+    per_point = (time.perf_counter() - t0) / 15000
+    n_steps = steps + warmup
+    pts = int(min(POINTS, max(5000, budget_s / max(n_steps, 1) / per_point)))
+    nb = scenes.make_batch(1, pts, config_id=2, geometry_points=pts)
+    b = chain.batch_to_device(nb, None)
+    for _ in range(warmup):
+        chain.proposal_chain(ops, b)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        chain.proposal_chain(ops, b)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    rate = (pts / POINTS) / dt
+    desc = ("1 synthetic scene of %d points (=%.3f of a 150k-point scene) per step through the CPU chain: "
+            "voxelize_idx + bfs_cluster via %s, CUDA-only ops via oracle/pg_oracle.c (OpenMP)"
+            % (pts, pts / POINTS, "oracle/_ref (reference sources compiled)" if ops.ref is not None
+               else "oracle/pg_oracle.c"))
+    return rate, dt * 1e3, desc, cores, kind
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    rate, ms, desc, cores, kind = cpu_chain_rate(150.0, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1]: full pointgroup_ops chain on synthetic 150k-point scenes (CPU sample)",
+                   "points_per_scene": POINTS},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------
+# GPU leg
+# ----------------------------------------------------------------------------------------------------
+def count_pg_kernels(fn):
+    """Kernels of this library (namespace pg) launched by one call of fn, counted with CUPTI."""
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if "pg::" in e.key]
+        return sum(r[1] for r in rows), sorted(rows, key=lambda r: -r[2])
+    except Exception as e:  # CUPTI can be unavailable under another profiler
+        return None, [("profiler unavailable: %r" % (e,), 0, 0)]
+
+
+def run_b200(args, rank, world, local):
+    import torch.distributed as dist
+    from d3net_b200 import pointgroup_ops as ops, dist as pgdist, _native
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    _native.lib()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_scenes = args.scenes
+    first_scene = rank * n_scenes                      # scene-per-GPU sharding: each rank its own scenes
+    nb = scenes.make_batch(n_scenes, args.points, config_id=2, first_scene=first_scene, with_feats=False)
+    host = chain.batch_to_device(nb, None, pt_feat_seed=rank, pin=True)
+    batch = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+    rand6 = torch.full((6,), 0.5, device=dev)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+
+    def step_device(timer=None):
+        out = chain.proposal_chain(ops, batch, rand6, timer)
+        packed = pgdist.pack_proposals(out, batch, args.max_proposals)
+        gathered = pgdist.all_gather_proposals(packed)
+        return out, gathered
+
+    d2h_keep = {}
+
+    def step_e2e():
+        b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+        out = chain.proposal_chain(ops, b, rand6)
+        packed = pgdist.pack_proposals(out, b, args.max_proposals)
+        gathered = pgdist.all_gather_proposals(packed)
+        res = [gathered, out["ious"], out["proposals_offset"]]
+        hostres = [r.to("cpu", non_blocking=False) for r in res]     # the device->host read of the step's result
+        d2h_keep["bytes"] = sum(r.numel() * r.element_size() for r in res)
+        return hostres
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    if args.profile_mode:
+        for _ in range(args.warmup + args.steps):
+            step_device()
+        torch.cuda.synchronize()
+        return
+    # warm-up (also sizes the caching allocator)
+    for _ in range(max(args.warmup, 3)):
+        out, _ = step_device()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # timed region 1: device-resident inputs, with the per-op event timers live
+    timer = chain.SectionTimer(True)
+    ops._section_timer = timer
+    ms_total = timed(lambda: step_device(timer), args.steps)
+    ops._section_timer = None
+    # timed region 2: end to end from pinned host memory
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    total_scenes = n_scenes * world
+    value = total_scenes * args.steps / (ms_total / 1e3)
+    e2e_value = total_scenes * args.steps / (ms_e2e / 1e3)
+
+    if rank == 0:
+        sec_ms = {k: v / args.steps for k, v in timer.totals_ms().items()}
+        algo = algorithmic_bytes(batch, out)
+        peak, peak_kind = peaks()
+        single_kernel = {k: v for k, v in sec_ms.items() if k in algo}
+        dom = max(single_kernel, key=single_kernel.get)
+        achieved = algo[dom] / (sec_ms[dom] / 1e3) / 1e9
+        per_op = {k: {"ms": round(v, 4), "GBps": (round(algo[k] / (v / 1e3) / 1e9, 1) if k in algo else None)}
+                  for k, v in sorted(sec_ms.items(), key=lambda kv: -kv[1])}
+        n_launch, top = (None, [])
+        if world == 1:
+            n_launch, top = count_pg_kernels(lambda: step_device())
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rate, ms, desc, cores, kind = cpu_chain_rate(20.0, 1, 1)
+            cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "points_per_sec": value * args.points,
+            "config": {"workload": "configs[1]: full pointgroup_ops chain (voxelization_idx, voxelization C=134, "
+                                   "ballquery+bfs_cluster on shifted and raw coords, sec_mean/min/max, cluster "
+                                   "re-voxelisation C=16, roipool, get_iou) on %d synthetic %dk-point scenes per GPU"
+                                   % (n_scenes, args.points // 1000),
+                       "scenes_per_gpu": n_scenes, "points_per_scene": args.points, "parallelism": "scene-per-GPU x%d" % world,
+                       "cluster_radius": scenes.CLUSTER_RADIUS, "npoint_thre": scenes.CLUSTER_NPOINT_THRE,
+                       "l2": "inputs larger than L2 (%.0f MB of point features per step)" % (batch["feats"].numel() * 4 / 1e6),
+                       "collective": "all_gather of [scenes, %d, 46] fp32 proposal block" % args.max_proposals if world > 1 else "none (N=1)",
+                       "n_points": int(batch["locs"].shape[0]), "n_object_points": int(out["n_object_points"]),
+                       "nActive_shift": int(out["nActive_shift"]), "nActive_raw": int(out["nActive_raw"]),
+                       "n_proposals": int(out["proposals_offset"].numel() - 1), "sumNPoint": int(out["proposals_idx"].shape[0])},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_keep.get("bytes", 0))},
+            "gpu_launches": (n_launch * args.steps) if n_launch is not None else None,
+            "gpu_launches_per_step": n_launch,
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                         "algorithmic_bytes_per_launch": int(algo[dom]), "ms_per_launch": sec_ms[dom]},
+            "per_op": per_op,
+            "top_kernels": [{"name": k[:80], "calls": c, "us": round(t, 1)} for k, c, t in top[:8]],
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scenes", type=int, default=SCENES_PER_GPU, help="scenes per GPU per step")
+    ap.add_argument("--points", type=int, default=POINTS)
+    ap.add_argument("--max-proposals", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-mode", action="store_true",
+                    help="only W warm-up + K device-resident steps, no JSON line (for runs under ncu)")
+    args = ap.parse_args()
+    rank, world, local = dist_env()
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()

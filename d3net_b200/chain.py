@@ -1,0 +1,253 @@
+"""The proposal hot path as the detector runs it, restated around the ops of this package.
+
+This is the caller side of the path BASELINE.json names -- input voxelisation, dual-set clustering,
+cluster re-voxelisation, proposal pooling, proposal/instance IoU -- following
+model/pointgroup.py:266-370 (forward), :125-178 (clusters_voxelization), :445 (get_iou in the loss)
+and lib/dataset/pipeline.py:992 (collate-side voxelization_idx) line by line, with two differences:
+
+  * the MinkowskiEngine backbone and score U-Net are out of scope, so the three tensors they would
+    produce (per-point features [N, m], semantic_preds, pt_offsets; per-voxel score features) are
+    inputs / pass-throughs here;
+  * every tensor stays on the device: the reference moves the neighbour lists to the CPU for its BFS
+    (model/pointgroup.py:297,305) and the cluster coordinates to the CPU for voxelization_idx (:167);
+    with GPU clustering and GPU voxelisation neither round trip is needed.  Python-side loops of the
+    reference (get_batch_offsets :112-122) are replaced by their vectorised equivalents.
+
+``ops`` is any module exposing the reference's operator API (d3net_b200.pointgroup_ops in the
+product; the tests also trace this function to replay each op's inputs through the oracle).
+"""
+import torch
+
+from . import scenes
+
+
+class SectionTimer:
+    """CUDA-event timing of named sections on the current stream (bench.py's per-op breakdown)."""
+
+    def __init__(self, enabled=True):
+        self.enabled = enabled
+        self.events = {}
+        self.current = ""
+
+    def start(self, name):
+        if not self.enabled:
+            return None
+        self.current = name
+        return self._begin(name)
+
+    def start_sub(self, name):
+        """A phase inside the current section (used by pointgroup_ops for its two-phase ops)."""
+        if not self.enabled:
+            return None
+        return self._begin(self.current + "." + name)
+
+    def _begin(self, name):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        self.events.setdefault(name, []).append((a, b))
+        return b
+
+    def stop(self, tok):
+        if tok is not None:
+            tok.record()
+
+    def totals_ms(self):
+        return {k: sum(a.elapsed_time(b) for a, b in v) for k, v in self.events.items()}
+
+    def counts(self):
+        return {k: len(v) for k, v in self.events.items()}
+
+
+class _NoTimer(SectionTimer):
+    def __init__(self):
+        super().__init__(False)
+
+
+def get_batch_offsets(batch_idxs, batch_size):
+    """model/pointgroup.py:112-122 without the Python loop."""
+    counts = torch.bincount(batch_idxs.long(), minlength=batch_size)[:batch_size]
+    out = torch.zeros(batch_size + 1, dtype=torch.int32, device=batch_idxs.device)
+    out[1:] = torch.cumsum(counts, 0).int()
+    return out
+
+
+def clusters_voxelization(ops, clusters_idx, clusters_offset, feats, coords, fullscale, scale, mode, rand6,
+                          timer=None, trace=None):
+    """model/pointgroup.py:125-178.  ``rand6`` replaces the two torch.rand(3) draws (:161) so runs are
+    reproducible.  Returns (voxel_feats [M,C], voxel_coords int64 [M,4], p2v_map, v2p_map, (center, size))."""
+    timer = timer or _NoTimer()
+    c_idxs = clusters_idx[:, 1].long()
+    clusters_feats = feats[c_idxs]
+    clusters_coords = coords[c_idxs]
+    cid = clusters_idx[:, 0].long()
+
+    t = timer.start("sec_mean")
+    clusters_coords_mean = ops.sec_mean(clusters_coords, clusters_offset)                # (nCluster, 3)
+    timer.stop(t)
+    if trace is not None:
+        trace["sec_mean"] = (clusters_coords.clone(), clusters_offset, clusters_coords_mean)
+    clusters_coords = clusters_coords - torch.index_select(clusters_coords_mean, 0, cid)
+
+    t = timer.start("sec_minmax")
+    clusters_coords_min = ops.sec_min(clusters_coords, clusters_offset)
+    clusters_coords_max = ops.sec_max(clusters_coords, clusters_offset)
+    timer.stop(t)
+    if trace is not None:
+        trace["sec_minmax"] = (clusters_coords.clone(), clusters_offset, clusters_coords_min, clusters_coords_max)
+
+    clusters_size = clusters_coords_max - clusters_coords_min
+    clusters_center = (clusters_coords_max + clusters_coords_min) / 2 + clusters_coords_mean
+
+    clusters_scale = 1 / ((clusters_coords_max - clusters_coords_min) / fullscale).max(1)[0] - 0.01
+    clusters_scale = torch.clamp(clusters_scale, min=None, max=scale)
+    min_xyz = clusters_coords_min * clusters_scale.unsqueeze(-1)
+    max_xyz = clusters_coords_max * clusters_scale.unsqueeze(-1)
+    clusters_scale = torch.index_select(clusters_scale, 0, cid)
+    clusters_coords = clusters_coords * clusters_scale.unsqueeze(-1)
+    rng_ = max_xyz - min_xyz
+    offset = -min_xyz + torch.clamp(fullscale - rng_ - 0.001, min=0) * rand6[:3] \
+        + torch.clamp(fullscale - rng_ + 0.001, max=0) * rand6[3:]
+    clusters_coords = clusters_coords + torch.index_select(offset, 0, cid)
+    clusters_coords = clusters_coords.long()
+    clusters_coords = torch.cat([cid.view(-1, 1), clusters_coords], 1).contiguous()       # (sumNPoint, 1 + 3)
+
+    n_clusters = clusters_offset.numel() - 1
+    t = timer.start("voxelization_idx(clusters)")
+    voxel_coords, p2v_map, v2p_map = ops.voxelization_idx(clusters_coords, n_clusters, mode)
+    timer.stop(t)
+    if trace is not None:
+        trace["voxelization_idx(clusters)"] = (clusters_coords, n_clusters, voxel_coords, p2v_map, v2p_map)
+    t = timer.start("voxelization(clusters)")
+    voxel_feats = ops.voxelization(clusters_feats, v2p_map, mode)                         # (M, C)
+    timer.stop(t)
+    if trace is not None:
+        trace["voxelization(clusters)"] = (clusters_feats, v2p_map, voxel_feats)
+    return voxel_feats, voxel_coords, p2v_map, v2p_map, (clusters_center, clusters_size)
+
+
+def proposal_chain(ops, batch, rand6=None, timer=None, trace=None):
+    """One pass of the hot path over one collated batch (all tensors on one CUDA device).
+
+    batch: locs fp32 [N,3], locs_scaled int64 [N,4], feats fp32 [N,134], pt_feats fp32 [N,16],
+    semantic_preds int64 [N], pt_offsets fp32 [N,3], instance_ids int64 [N], instance_pointnum int32
+    [nInst], n_scenes.  Returns a dict of the tensors the rest of the detector consumes."""
+    timer = timer or _NoTimer()
+    dev = batch["locs"].device
+    B = int(batch["n_scenes"])
+    if rand6 is None:
+        rand6 = torch.full((6,), 0.5, device=dev)
+    out = {}
+
+    # ---- collate-side voxelisation of the input cloud (pipeline.py:992, pointgroup.py:472)
+    t = timer.start("voxelization_idx(scene)")
+    voxel_locs, p2v_map, v2p_map = ops.voxelization_idx(batch["locs_scaled"], B, scenes.SCORE_MODE)
+    timer.stop(t)
+    if trace is not None:
+        trace["voxelization_idx(scene)"] = (batch["locs_scaled"], B, voxel_locs, p2v_map, v2p_map)
+    t = timer.start("voxelization(scene)")
+    voxel_feats = ops.voxelization(batch["feats"], v2p_map, scenes.SCORE_MODE)
+    timer.stop(t)
+    if trace is not None:
+        trace["voxelization(scene)"] = (batch["feats"], v2p_map, voxel_feats)
+    out["voxel_locs"], out["voxel_feats"], out["p2v_map"] = voxel_locs, voxel_feats, p2v_map
+
+    # ---- clustering on the predicted-object points (pointgroup.py:284-316)
+    semantic_preds = batch["semantic_preds"]
+    batch_idxs = batch["locs_scaled"][:, 0].int()
+    object_idxs = torch.nonzero(semantic_preds > 0, as_tuple=False).view(-1)
+    batch_idxs_ = batch_idxs[object_idxs].contiguous()
+    batch_offsets_ = get_batch_offsets(batch_idxs_, B)
+    coords_ = batch["locs"][object_idxs].contiguous()
+    pt_offsets_ = batch["pt_offsets"][object_idxs]
+    sem_ = semantic_preds[object_idxs].int().contiguous()
+
+    shifted = (coords_ + pt_offsets_).contiguous()
+    t = timer.start("ballquery(shift)")
+    idx_shift, start_len_shift = ops.ballquery_batch_p(shifted, batch_idxs_, batch_offsets_, scenes.CLUSTER_RADIUS,
+                                                       scenes.CLUSTER_SHIFT_MEANACTIVE)
+    timer.stop(t)
+    t = timer.start("bfs_cluster(shift)")
+    proposals_idx_shift, proposals_offset_shift = ops.bfs_cluster(sem_, idx_shift, start_len_shift,
+                                                                  scenes.CLUSTER_NPOINT_THRE)
+    timer.stop(t)
+    if trace is not None:
+        trace["ballquery(shift)"] = (shifted, batch_idxs_, batch_offsets_, idx_shift, start_len_shift)
+        trace["bfs_cluster(shift)"] = (sem_, idx_shift, start_len_shift, proposals_idx_shift.clone(),
+                                       proposals_offset_shift.clone())
+    out["nActive_shift"] = idx_shift.numel()
+    proposals_idx_shift[:, 1] = object_idxs[proposals_idx_shift[:, 1].long()].int()
+
+    t = timer.start("ballquery(raw)")
+    idx, start_len = ops.ballquery_batch_p(coords_, batch_idxs_, batch_offsets_, scenes.CLUSTER_RADIUS,
+                                           scenes.CLUSTER_MEANACTIVE)
+    timer.stop(t)
+    t = timer.start("bfs_cluster(raw)")
+    proposals_idx, proposals_offset = ops.bfs_cluster(sem_, idx, start_len, scenes.CLUSTER_NPOINT_THRE)
+    timer.stop(t)
+    if trace is not None:
+        trace["ballquery(raw)"] = (coords_, batch_idxs_, batch_offsets_, idx, start_len)
+        trace["bfs_cluster(raw)"] = (sem_, idx, start_len, proposals_idx.clone(), proposals_offset.clone())
+    out["nActive_raw"] = idx.numel()
+    proposals_idx[:, 1] = object_idxs[proposals_idx[:, 1].long()].int()
+
+    proposals_idx_shift[:, 0] += (proposals_offset.size(0) - 1)
+    proposals_offset_shift = proposals_offset_shift + proposals_offset[-1]
+    proposals_idx = torch.cat((proposals_idx, proposals_idx_shift), dim=0).contiguous()
+    proposals_offset = torch.cat((proposals_offset, proposals_offset_shift[1:])).contiguous()
+    out["proposals_idx"], out["proposals_offset"] = proposals_idx, proposals_offset
+    out["n_object_points"] = object_idxs.numel()
+
+    # ---- proposal re-voxelisation (pointgroup.py:326 -> :125-178)
+    (prop_voxel_feats, prop_voxel_coords, prop_p2v_map, _v2p,
+     (proposals_center, proposals_size)) = clusters_voxelization(
+        ops, proposals_idx, proposals_offset, batch["pt_feats"], batch["locs"], scenes.SCORE_FULLSCALE,
+        scenes.SCORE_SCALE, scenes.SCORE_MODE, rand6, timer, trace)
+    out["proposals_center"], out["proposals_size"] = proposals_center, proposals_size
+    out["proposals_voxel_feats"], out["proposals_voxel_coords"] = prop_voxel_feats, prop_voxel_coords
+
+    # ---- score features per point and proposal pooling (pointgroup.py:332-334; the score U-Net is
+    #      out of scope, its per-voxel output is stood in for by its input)
+    pt_score_feats = prop_voxel_feats[prop_p2v_map.long()].contiguous()
+    t = timer.start("roipool")
+    proposals_score_feats = ops.roipool(pt_score_feats, proposals_offset)
+    timer.stop(t)
+    if trace is not None:
+        trace["roipool"] = (pt_score_feats, proposals_offset, proposals_score_feats)
+    out["proposals_score_feats"] = proposals_score_feats
+
+    # ---- proposal / ground-truth IoU (pointgroup.py:445)
+    t = timer.start("get_iou")
+    ious = ops.get_iou(proposals_idx[:, 1].contiguous(), proposals_offset, batch["instance_ids"],
+                       batch["instance_pointnum"])
+    timer.stop(t)
+    if trace is not None:
+        trace["get_iou"] = (proposals_idx[:, 1].contiguous(), proposals_offset, batch["instance_ids"],
+                            batch["instance_pointnum"], ious)
+    out["ious"] = ious
+    return out
+
+
+def batch_to_device(np_batch, device, pt_feat_seed=0, pin=False):
+    """numpy batch from scenes.make_batch -> the tensor dict proposal_chain expects."""
+    import numpy as np
+    g = torch.Generator().manual_seed(1234 + pt_feat_seed)
+    n = np_batch["locs"].shape[0]
+    host = {
+        "locs": torch.from_numpy(np_batch["locs"]),
+        "locs_scaled": torch.from_numpy(np_batch["locs_scaled"]),
+        "feats": torch.from_numpy(np_batch["feats"]) if "feats" in np_batch
+        else torch.randn((n, scenes.IN_CHANNELS), generator=g),
+        "pt_feats": torch.randn((n, scenes.M_CHANNELS), generator=g),
+        "semantic_preds": torch.from_numpy(np_batch["semantic_preds"]),
+        "pt_offsets": torch.from_numpy(np_batch["pt_offsets"]),
+        "instance_ids": torch.from_numpy(np_batch["instance_ids"]),
+        "instance_pointnum": torch.from_numpy(np.ascontiguousarray(np_batch["instance_pointnum"], dtype=np.int32)),
+    }
+    if pin:
+        host = {k: v.contiguous().pin_memory() for k, v in host.items()}
+    if device is None:
+        host["n_scenes"] = np_batch["n_scenes"]
+        return host
+    dev = {k: v.to(device, non_blocking=pin).contiguous() for k, v in host.items()}
+    dev["n_scenes"] = np_batch["n_scenes"]
+    return dev

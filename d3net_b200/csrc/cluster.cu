@@ -23,7 +23,8 @@ constexpr int kCapC = PG_BALLQUERY_CAP;
 
 struct ClWs {
     int2 *info;          // per point: (label, last index that still has a reverse edge)
-    int32_t *parent;     // union-find forest (fast path) / identity (generic)
+    int32_t *parent;     // union-find forest (fast path only)
+    int32_t *root;       // flattened component root per point (identity on the generic path)
     int32_t *lab;        // min-ancestor label forest over roots
     int32_t *size;       // points per final label
     int32_t *cid;        // cluster id per kept label (exclusive scan of keep flags)
@@ -42,6 +43,7 @@ static ClWs cl_layout(void *ws, size_t ws_bytes, int64_t N_) {
     const size_t n = (size_t)(N_ > 0 ? N_ : 1);
     w.info = a.take<int2>(n);
     w.parent = a.take<int32_t>(n);
+    w.root = a.take<int32_t>(n);
     w.lab = a.take<int32_t>(n);
     w.size = a.take<int32_t>(n + 1);
     w.cid = a.take<int32_t>(n + 1);
@@ -133,14 +135,16 @@ __global__ void __launch_bounds__(256) k_cl_union(const int32_t *__restrict__ id
     if (residual) scalars[2] = 1;
 }
 
-__global__ void k_cl_flatten(int32_t *parent, int32_t N) {
+// Roots go to their own array: writing them back into `parent` would race with the path-halving
+// stores of other threads' finds, which may re-install an intermediate ancestor after the root.
+__global__ void k_cl_flatten(int32_t *parent, int32_t *__restrict__ root, int32_t N) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < N) parent[v] = uf_find(parent, v);
+    if (v < N) root[v] = uf_find(parent, v);
 }
 
-__global__ void k_cl_reset(int32_t *parent, int32_t *lab, int32_t N) {
+__global__ void k_cl_reset(int32_t *__restrict__ root, int32_t *__restrict__ lab, int32_t N) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < N) { parent[v] = v; lab[v] = v; }
+    if (v < N) { root[v] = v; lab[v] = v; }
 }
 
 // resolve() on the label forest.  Unlike uf_find, its shortcut writes must be atomicMin: lab[x] is
@@ -266,7 +270,7 @@ extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t
     if (!use_generic) {
         if (wide) k_cl_union<32><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.info, N, w.parent, w.scalars);
         else k_cl_union<8><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.info, N, w.parent, w.scalars);
-        k_cl_flatten<<<nb, 256, 0, st>>>(w.parent, N);
+        k_cl_flatten<<<nb, 256, 0, st>>>(w.parent, w.root, N);
         PG_LAUNCH_CHECK();
         PG_CUDA(cudaMemcpyAsync(h, w.scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
@@ -279,16 +283,16 @@ extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t
         set_error("pg_bfs_cluster_count: start_len has a row outside ball_query_idxs[0..%lld)", (long long)nActive);
         return PG_EINVAL;
     }
-    if (use_generic) k_cl_reset<<<nb, 256, 0, st>>>(w.parent, w.lab, N);
+    if (use_generic) k_cl_reset<<<nb, 256, 0, st>>>(w.root, w.lab, N);
     if (use_generic || h[2] != 0) {
         for (int it = 0; it < 100000; it++) {
             PG_CUDA(cudaMemsetAsync(w.scalars + 3, 0, sizeof(unsigned long long), st));
             if (use_generic) {
-                if (wide) k_cl_propagate<32, true><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.info, N, w.parent, w.lab, w.scalars);
-                else k_cl_propagate<8, true><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.info, N, w.parent, w.lab, w.scalars);
+                if (wide) k_cl_propagate<32, true><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.info, N, w.root, w.lab, w.scalars);
+                else k_cl_propagate<8, true><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.info, N, w.root, w.lab, w.scalars);
             } else {
-                if (wide) k_cl_propagate<32, false><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.info, N, w.parent, w.lab, w.scalars);
-                else k_cl_propagate<8, false><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.info, N, w.parent, w.lab, w.scalars);
+                if (wide) k_cl_propagate<32, false><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.info, N, w.root, w.lab, w.scalars);
+                else k_cl_propagate<8, false><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.info, N, w.root, w.lab, w.scalars);
             }
             PG_LAUNCH_CHECK();
             unsigned long long changed = 0;
@@ -297,7 +301,7 @@ extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t
             if (!changed) break;
         }
     }
-    k_cl_label<<<nb, 256, 0, st>>>(w.parent, w.lab, N, w.size, w.key0);
+    k_cl_label<<<nb, 256, 0, st>>>(w.root, w.lab, N, w.size, w.key0);
     k_cl_keep<<<nb, 256, 0, st>>>(w.key0, w.size, N, threshold, w.cid);
     PG_CUDA(cudaMemsetAsync(w.cid + N, 0, sizeof(int32_t), st));
     PG_TRY(scan_exclusive_i32(w.cid, w.cid, (int64_t)N + 1, (int64_t *)(w.scalars + 4), w.scan_tmp, st));

@@ -1,0 +1,64 @@
+"""Scene-per-GPU sharding of the proposal path and the one collective it needs.
+
+Scenes are independent units of work: every op is confined to one scene, so a
+batch is cut into contiguous blocks of scenes, each rank runs the whole chain on its block with no
+exchange step, and only the per-scene proposal tensors that the captioning / grounding heads consume
+(model/pointgroup.py:223-263, convert_stack_to_batch) are all-gathered -- as ONE packed fp32 buffer of
+fixed shape [scenes_per_rank, P, 46], a few MB, i.e. a single latency-bound NCCL all-gather over
+NVLink/NVSwitch.  No reduction is involved, so there is nothing to fuse a kernel with.
+"""
+import torch
+import torch.distributed as dist
+
+PACK_WIDTH = 46   # feats 16 | bbox corners 8x3 | center 3 | sem_cls | score | mask
+
+
+def scene_shard(n_scenes, rank, world_size):
+    """Contiguous block [lo, hi) of scene indices owned by `rank` (uneven remainders go to low ranks)."""
+    base, rem = divmod(n_scenes, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_proposals(out, batch, max_num_proposal=256):
+    """Device-side, loop-free restatement of convert_stack_to_batch's padding (without its randperm):
+    per scene the first `max_num_proposal` proposals -> [B, P, 46] fp32."""
+    B = int(batch["n_scenes"])
+    P = max_num_proposal
+    dev = out["proposals_score_feats"].device
+    offs = out["proposals_offset"].long()
+    n_prop = offs.numel() - 1
+    packed = torch.zeros((B, P, PACK_WIDTH), dtype=torch.float32, device=dev)
+    if n_prop == 0:
+        return packed
+    first_pt = out["proposals_idx"][offs[:-1], 1].long()
+    scene = batch["locs_scaled"][first_pt, 0]                                  # proposals_batchId (:349)
+    order = torch.argsort(scene, stable=True)
+    scene_sorted = scene[order]
+    start = torch.searchsorted(scene_sorted, torch.arange(B, device=dev))
+    slot = torch.arange(n_prop, device=dev) - start[scene_sorted]
+    keep = slot < P
+    src = order[keep]
+    b, s = scene_sorted[keep], slot[keep]
+    center, size = out["proposals_center"][src], out["proposals_size"][src]
+    signs = torch.tensor([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)],
+                         dtype=torch.float32, device=dev)
+    corners = center[:, None, :] + 0.5 * size[:, None, :] * signs[None]       # axis-aligned 8 corners
+    feats = out["proposals_score_feats"][src]
+    row = torch.cat([feats[:, :16], corners.reshape(-1, 24), center,
+                     batch["semantic_preds"][first_pt[src]].float()[:, None],   # sem_cls (:359)
+                     torch.sigmoid(feats[:, :1]),                               # stand-in objectness score
+                     torch.ones((src.numel(), 1), device=dev)], 1)
+    packed[b, s] = row
+    return packed
+
+
+def all_gather_proposals(packed, group=None):
+    """[b, P, 46] per rank -> [world * b, P, 46] on every rank with one all_gather_into_tensor."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return packed
+    world = dist.get_world_size(group)
+    gathered = torch.empty((world * packed.size(0),) + tuple(packed.shape[1:]), dtype=packed.dtype,
+                           device=packed.device)
+    dist.all_gather_into_tensor(gathered, packed.contiguous(), group=group)
+    return gathered

@@ -20,6 +20,19 @@ from torch.autograd import Function
 from . import PG_OP
 
 
+# bench.py sets this to a chain.SectionTimer to get CUDA-event timings of the phases of the two-phase ops
+_section_timer = None
+
+
+def _sub(name):
+    return _section_timer.start_sub(name) if _section_timer is not None else None
+
+
+def _end(tok):
+    if tok is not None:
+        tok.record()
+
+
 def _cuda_of(t):
     return t if t.is_cuda else t.to(PG_OP._compute_device(t))
 
@@ -129,9 +142,13 @@ class BallQueryBatchP(Function):
         assert coords.is_contiguous() and coords.is_cuda
         assert batch_idxs.is_contiguous() and batch_idxs.is_cuda
         assert batch_offsets.is_contiguous() and batch_offsets.is_cuda
+        t = _sub("count")
         start_len, nActive, ws = PG_OP.ballquery_count_impl(coords, batch_idxs, batch_offsets, radius)
+        _end(t)
         idx = torch.empty(nActive, dtype=torch.int32, device=coords.device)
+        t = _sub("fill")
         PG_OP.ballquery_fill_impl(coords, radius, start_len, idx, ws)
+        _end(t)
         ctx.mark_non_differentiable(idx, start_len)
         return idx, start_len
 

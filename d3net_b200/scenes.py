@@ -144,10 +144,11 @@ def make_scene(n_points=150_000, seed=0, geometry_points=_GEOM_N):
     }
 
 
-def make_batch(n_scenes, n_points=150_000, config_id=2, first_scene=0, with_feats=False, feat_seed=None):
+def make_batch(n_scenes, n_points=150_000, config_id=2, first_scene=0, with_feats=False, feat_seed=None,
+               geometry_points=_GEOM_N):
     """Collate ``n_scenes`` scenes the way sparse_collate_fn does (lib/dataset/pipeline.py:937-992):
     stacked points, batch index column, batch-global instance ids."""
-    scenes = [make_scene(n_points, 1000 * config_id + first_scene + i) for i in range(n_scenes)]
+    scenes = [make_scene(n_points, 1000 * config_id + first_scene + i, geometry_points) for i in range(n_scenes)]
     locs = np.concatenate([s["locs"] for s in scenes])
     batch_idx = np.concatenate([np.full(len(s["locs"]), i, np.int64) for i, s in enumerate(scenes)])
     inst, off = [], 0

@@ -186,7 +186,7 @@ ORC_API int64_t orc_ballquery(const float *xyz, const int32_t *batch_idxs, const
         }
     } else {
         /* per-scene uniform grid with cell edge slightly above r; candidates = 27 surrounding cells */
-        const double cell0 = (double)radius * 1.001;
+        const double cell0 = fabs((double)radius) * 1.001;   /* r enters the predicate only as r*r */
         for (int b = 0; b < B && r2 > 0.f; b++) {
             int s = batch_offsets[b], e = batch_offsets[b + 1];
             if (e <= s) continue;

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from util import cu, npy, object_subset, small_batch, random_segments
+from util import cu, npy, object_subset, small_batch, random_segments, assert_same_floats
 
 pytestmark = pytest.mark.gpu
 
@@ -109,7 +109,7 @@ def test_voxelize_fp_signed_zero_and_specials(ops, oracle):
     feats = np.array([[-0.0, np.inf, 1e-45], [-0.0, -np.inf, 1e-45], [-0.0, np.nan, -1e38]], np.float32)
     out = npy(ops.voxelization(cu(feats), cu(om), 4))
     ref = oracle.voxelization(feats, om, 4)
-    assert out.tobytes() == ref.tobytes()
+    assert_same_floats(out, ref)
 
 
 def test_point_recover(ops, oracle):
@@ -360,10 +360,10 @@ def test_roipool_specials(ops, oracle):
     arg = torch.empty((4, 4), dtype=torch.int32, device="cuda")
     PG_OP.roipool_fp(cu(x), cu(off), out, arg, 4, 4)
     ref, refidx = oracle.roipool(x, off)
-    assert npy(out).tobytes() == ref.tobytes()
+    assert_same_floats(npy(out), ref)
     np.testing.assert_array_equal(npy(arg), refidx)
     for fn, rf in ((ops.sec_max, oracle.sec_max), (ops.sec_min, oracle.sec_min), (ops.sec_mean, oracle.sec_mean)):
-        assert npy(fn(cu(x), cu(off))).tobytes() == rf(x, off).tobytes()
+        assert_same_floats(npy(fn(cu(x), cu(off))), rf(x, off))
 
 
 def test_sec_mean_on_cluster_coords(ops, oracle):
@@ -390,3 +390,35 @@ def test_get_iou(ops, oracle, nI):
     iou = ops.get_iou(cu(pidx), cu(off), cu(labels), cu(pointnum))
     ref = oracle.get_iou(pidx, off, labels, pointnum)
     assert npy(iou).tobytes() == ref.tobytes()
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole chain, traced and replayed op by op
+# ------------------------------------------------------------------------------------------------
+def test_chain_trace_replay(ops):
+    from d3net_b200 import chain
+    from oracle import replay
+    nb = small_batch(3, 20000, config_id=5)
+    batch = chain.batch_to_device(nb, torch.device("cuda"))
+    trace = {}
+    out = chain.proposal_chain(ops, batch, trace=trace)
+    checked = replay.check_trace(trace)
+    assert len(checked) == 12
+    assert out["proposals_offset"].numel() - 1 >= 10
+
+
+def test_pack_proposals(ops):
+    from d3net_b200 import chain, dist as pgdist
+    nb = small_batch(3, 12000, config_id=6)
+    batch = chain.batch_to_device(nb, torch.device("cuda"))
+    out = chain.proposal_chain(ops, batch)
+    packed = pgdist.pack_proposals(out, batch, 64)
+    assert tuple(packed.shape) == (3, 64, pgdist.PACK_WIDTH)
+    offs = out["proposals_offset"].long()
+    scene = batch["locs_scaled"][out["proposals_idx"][offs[:-1], 1].long(), 0]
+    for b in range(3):
+        k = min(int((scene == b).sum()), 64)
+        assert int(packed[b, :, 45].sum()) == k
+        first = torch.nonzero(scene == b).view(-1)[0]
+        assert torch.equal(packed[b, 0, :16], out["proposals_score_feats"][first])
+    assert torch.equal(pgdist.all_gather_proposals(packed), packed)      # world size 1: identity

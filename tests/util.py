@@ -36,7 +36,8 @@ def object_subset(batch):
 
 
 def small_batch(n_scenes=2, n_points=12000, config_id=9):
-    return scenes.make_batch(n_scenes, n_points, config_id=config_id)
+    # geometry scaled with the point count: the 2 cm pitch (hence connectivity at r = 0.03) is kept
+    return scenes.make_batch(n_scenes, n_points, config_id=config_id, geometry_points=n_points)
 
 
 def random_segments(rng, n_seg, max_len, empty_frac=0.1, big=None):
@@ -45,3 +46,14 @@ def random_segments(rng, n_seg, max_len, empty_frac=0.1, big=None):
     if big is not None and n_seg > 2:
         lens[n_seg // 2] = big
     return np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+
+
+def assert_same_floats(a, b):
+    """Bitwise equality, except that any NaN equals any NaN: x86 and the GPU generate different
+    quiet-NaN bit patterns for inf - inf (0xFFC00000 vs 0x7FFFFFFF); signed zeros still have to match."""
+    a = np.asarray(a, np.float32)
+    b = np.asarray(b, np.float32)
+    assert a.shape == b.shape
+    na, nb = np.isnan(a), np.isnan(b)
+    np.testing.assert_array_equal(na, nb)
+    np.testing.assert_array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])
