@@ -120,31 +120,143 @@ __device__ __forceinline__ int lower_bound_u32(const uint32_t *__restrict__ a, i
     return lo;
 }
 
-// one thread per (sorted position q, neighbour slot j): place point k = sorted_pt[q] into the
-// candidate array of the j-th neighbour cell of its own cell
-__global__ void __launch_bounds__(256) k_bq_merge(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
-                                                  const int32_t *__restrict__ cell, const int32_t *__restrict__ cstart,
-                                                  const int32_t *__restrict__ ccnt, const int32_t *__restrict__ nbr,
-                                                  const int32_t *__restrict__ cand_start, int32_t n,
-                                                  float4 *__restrict__ cand) {
-    const int64_t total = (int64_t)n * 27;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int q = (int)(t / 27), j = (int)(t - (int64_t)q * 27);
-        const uint32_t k = sorted_pt[q];
-        const int s = cell[k];
-        const int target = nbr[(int64_t)s * 27 + j];
-        if (target < 0) continue;
-        const int32_t *tn = nbr + (int64_t)target * 27;
-        int pos = 0;
-#pragma unroll 1
-        for (int jj = 0; jj < 27; jj++) {
-            const int src = __ldg(tn + jj);
-            if (src < 0) continue;
-            if (src == s) pos += q - cstart[s];
-            else pos += lower_bound_u32(sorted_pt + cstart[src], ccnt[src], k);
+// ---- merge: one candidate array per cell = its <= 27 neighbour lists merged by ascending index ----
+// A work item is (cell, tile): cells with <= 32 candidates are one tile; larger cells are cut into
+// ~24-element tiles by splitting the cell's index range evenly (point indices are a random shuffle
+// with respect to space, so even splits balance).  For a tile [a, b) lane l binary-searches both
+// bounds in neighbour list l: the sum of the lower bounds over the lists IS the tile's offset in the
+// merged array, so tiles need no scan between them.  The <= 32 keys of a tile are gathered through
+// shared memory, sorted with a warp bitonic network and written out with their coordinates.  A tile
+// that turns out larger than 32 is halved on a small stack.
+constexpr int kMergeTile = 24;
+
+__global__ void k_bq_tiles(const int32_t *__restrict__ kc, const int64_t *__restrict__ nCells, int32_t n,
+                           int32_t *__restrict__ tiles) {
+    const int64_t nc = *nCells;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
+        const int K = c < nc ? kc[c] : 0;
+        tiles[c] = K <= 32 ? (K > 0) : (K + kMergeTile - 1) / kMergeTile;
+    }
+}
+
+__device__ __forceinline__ uint32_t warp_bitonic_sort(uint32_t key, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, key, j);
+            const bool up = ((lane & k) == 0);          // ascending block
+            const bool lower = ((lane & j) == 0);       // this lane keeps the smaller of the pair
+            const uint32_t mn = min(key, other), mx = max(key, other);
+            key = (up == lower) ? mn : mx;
         }
-        const float *p = xyz + 3 * (int64_t)k;
-        cand[(int64_t)cand_start[target] + pos] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __int_as_float((int)k));
+    }
+    return key;
+}
+
+__global__ void __launch_bounds__(256) k_bq_merge(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
+                                                  const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
+                                                  const int32_t *__restrict__ nbr, const int32_t *__restrict__ kc,
+                                                  const int32_t *__restrict__ cand_start,
+                                                  const int32_t *__restrict__ tile_start, const int64_t *__restrict__ scalars,
+                                                  float4 *__restrict__ cand) {
+    __shared__ uint32_t scratch_all[8][32];
+    uint32_t *scratch = scratch_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = lanemask_lt();
+    const int64_t nCells = scalars[0], nItems = scalars[5];
+    // every warp takes a contiguous run of work items: one binary search for the first cell, then it
+    // walks forward (every cell has at least one tile, so the walk never skips)
+    const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    const int64_t per = (nItems + nWarps - 1) / nWarps;
+    const int64_t w0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * per;
+    const int64_t w1 = w0 + per < nItems ? w0 + per : nItems;
+    int c = 0, t = 0;
+    if (w0 < w1) {
+        int64_t lo_c = 0, hi_c = nCells;
+        while (hi_c - lo_c > 1) {
+            const int64_t mid = (lo_c + hi_c) >> 1;
+            if (__ldg(tile_start + mid) <= w0) lo_c = mid; else hi_c = mid;
+        }
+        c = (int)lo_c;
+        t = (int)(w0 - __ldg(tile_start + c));
+    }
+    for (int64_t w = w0; w < w1; w++, t++) {
+        int K = __ldg(kc + c);
+        int T = K <= 32 ? 1 : (K + kMergeTile - 1) / kMergeTile;
+        if (t >= T) {
+            ++c; t = 0;
+            K = __ldg(kc + c);
+            T = K <= 32 ? 1 : (K + kMergeTile - 1) / kMergeTile;
+        }
+        // lane l < 27 owns neighbour list l
+        int len = 0;
+        const uint32_t *L = sorted_pt;
+        if (lane < 27) {
+            const int src = __ldg(nbr + (int64_t)c * 27 + lane);
+            if (src >= 0) { len = __ldg(ccnt + src); L = sorted_pt + __ldg(cstart + src); }
+        }
+        float4 *dst = cand + __ldg(cand_start + c);
+        uint32_t sa[30], sb[30];      // interval stack (warp-uniform)
+        int sp = 0;
+        if (T == 1) {
+            sa[0] = 0u; sb[0] = 0xffffffffu; sp = 1;
+        } else {
+            uint32_t head = len ? L[0] : 0xffffffffu, tail = len ? L[len - 1] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                head = min(head, __shfl_xor_sync(0xffffffffu, head, o));
+                tail = max(tail, __shfl_xor_sync(0xffffffffu, tail, o));
+            }
+            const uint32_t span = tail - head + 1u;
+            const uint32_t width = (span + (uint32_t)T - 1u) / (uint32_t)T;
+            const uint64_t a64 = (uint64_t)head + (uint64_t)t * width;
+            if (a64 <= tail) {
+                const uint64_t b64 = a64 + width;
+                sa[0] = (uint32_t)a64;
+                sb[0] = b64 > (uint64_t)tail ? tail + 1u : (uint32_t)b64;      // indices < 2^26: no overflow
+                sp = 1;
+            }
+        }
+        while (sp > 0) {
+            --sp;
+            const uint32_t a = sa[sp], b = sb[sp];
+            int lbA = 0, lbB = len;
+            if (a != 0u) lbA = lower_bound_u32(L, len, a);
+            if (b != 0xffffffffu) lbB = lower_bound_u32(L, len, b);
+            const int cnt = lbB - lbA;
+            int s = cnt, off = lbA;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s += __shfl_xor_sync(0xffffffffu, s, o);
+                off += __shfl_xor_sync(0xffffffffu, off, o);
+            }
+            if (s == 0) continue;
+            if (s > 32) {     // uneven tile: halve its index interval (indices are unique, so this ends)
+                const uint32_t mid = a + ((b - a) >> 1);
+                sa[sp] = mid; sb[sp] = b; ++sp;
+                sa[sp] = a; sb[sp] = mid; ++sp;
+                continue;
+            }
+            // exclusive prefix of cnt over lanes -> slot of each list's run inside the tile
+            int pre = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, pre, o);
+                if (lane >= o) pre += v;
+            }
+            pre -= cnt;
+            for (int i = 0; i < cnt; i++) scratch[pre + i] = L[lbA + i];
+            __syncwarp();
+            uint32_t key = lane < s ? scratch[lane] : 0xffffffffu;
+            __syncwarp();
+            key = warp_bitonic_sort(key, lane);
+            if (lane < s) {
+                const float *p = xyz + 3 * (int64_t)key;
+                dst[off + lane] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __int_as_float((int)key));
+            }
+        }
+        (void)lt;
     }
 }
 
@@ -161,39 +273,17 @@ __global__ void k_bq_clear_tail(int32_t *kc, const int64_t *__restrict__ nCells,
     for (int64_t c = nc + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n1; c += (int64_t)gridDim.x * blockDim.x) kc[c] = 0;
 }
 
-// chunks of <= 32 queries per cell
-__global__ void k_bq_chunks(const int32_t *__restrict__ ccnt, const int64_t *__restrict__ nCells, int32_t n,
-                            int32_t *__restrict__ chunks) {
-    const int64_t nc = *nCells;
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x)
-        chunks[c] = c < nc ? (ccnt[c] + 31) >> 5 : 0;
-}
-
+// count: one thread per query, taken in cell-sorted order so that the lanes of a warp mostly share a
+// cell: their loads of the cell's candidate array are then the same address (one broadcast
+// transaction), and in sparse regions each lane simply walks its own short list.
 __global__ void __launch_bounds__(256) k_bq_count(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
-                                                  const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
-                                                  const int32_t *__restrict__ chunk_start, const int64_t *__restrict__ scalars,
-                                                  const int32_t *__restrict__ cand_start, const int32_t *__restrict__ kc,
-                                                  const float4 *__restrict__ cand, float r2, int32_t *__restrict__ counts) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nCells = scalars[0], nItems = scalars[4];
-    const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nItems; w += nWarps) {
-        // cell owning work item w: largest c with chunk_start[c] <= w
-        int64_t lo = 0, hi = nCells;
-        while (hi - lo > 1) {
-            int64_t mid = (lo + hi) >> 1;
-            if (__ldg(chunk_start + mid) <= w) lo = mid; else hi = mid;
-        }
-        const int c = (int)lo;
-        const int first = (int)(w - __ldg(chunk_start + c)) * 32;
-        const int nq = min(32, __ldg(ccnt + c) - first);
-        const bool on = lane < nq;
-        uint32_t k = 0;
-        float ox = 0.f, oy = 0.f, oz = 0.f;
-        if (on) {
-            k = sorted_pt[__ldg(cstart + c) + first + lane];
-            ox = __ldg(xyz + 3 * (int64_t)k); oy = __ldg(xyz + 3 * (int64_t)k + 1); oz = __ldg(xyz + 3 * (int64_t)k + 2);
-        }
+                                                  const int32_t *__restrict__ cell, const int32_t *__restrict__ cand_start,
+                                                  const int32_t *__restrict__ kc, const float4 *__restrict__ cand,
+                                                  float r2, int32_t n, int32_t *__restrict__ counts) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = sorted_pt[q];
+        const int c = __ldg(cell + k);
+        const float ox = __ldg(xyz + 3 * (int64_t)k), oy = __ldg(xyz + 3 * (int64_t)k + 1), oz = __ldg(xyz + 3 * (int64_t)k + 2);
         const float4 *cl = cand + __ldg(cand_start + c);
         const int K = __ldg(kc + c);
         int cnt = 0;
@@ -203,7 +293,7 @@ __global__ void __launch_bounds__(256) k_bq_count(const float *__restrict__ xyz,
             cnt += bq_hit(ox, oy, oz, c0, r2) + bq_hit(ox, oy, oz, c1, r2) + bq_hit(ox, oy, oz, c2, r2) + bq_hit(ox, oy, oz, c3, r2);
         }
         for (; e < K; e++) cnt += bq_hit(ox, oy, oz, __ldg(cl + e), r2);
-        if (on) counts[k] = min(cnt, kCap);
+        counts[k] = min(cnt, kCap);
     }
 }
 
@@ -281,7 +371,8 @@ extern "C" int pg_ballquery_count(const float *xyz, const int32_t *batch_idxs, c
     PG_TRY(radix_sort_pairs(reinterpret_cast<const uint32_t *>(w.cell), nullptr, w.kA, w.vA, w.kB, w.vB, n, bits,
                             w.hist, w.scan_tmp, st, &res));
     const uint32_t *sorted_pt = res == 0 ? w.vA : w.vB;
-    uint32_t *spare = res == 0 ? w.kB : w.kA;   // a free n-sized int array (chunk starts)
+    // after the sort both key buffers are free n-sized int arrays
+    uint32_t *spare2 = res == 0 ? w.kA : w.kB;  // merge tile starts
     const int64_t flag = res;
     PG_CUDA(cudaMemcpyAsync(w.scalars + 3, &flag, sizeof(int64_t), cudaMemcpyHostToDevice, st));
     PG_CUDA(cudaMemsetAsync(w.ccnt + n, 0, sizeof(int32_t), st));
@@ -290,11 +381,11 @@ extern "C" int pg_ballquery_count(const float *xyz, const int32_t *batch_idxs, c
     k_bq_neighbours<<<gsm, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc);
     k_bq_clear_tail<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n + 1);   // kc beyond nCells must scan as 0
     PG_TRY(scan_exclusive_i32(w.kc, w.cand_start, (int64_t)n + 1, w.scalars + 1, w.scan_tmp, st));
-    k_bq_merge<<<kNumSM * 16, 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cstart, w.ccnt, w.nbr, w.cand_start, n, w.cand);
-    k_bq_chunks<<<gsm, 256, 0, st>>>(w.ccnt, w.scalars, n, (int32_t *)spare);
-    PG_TRY(scan_exclusive_i32((int32_t *)spare, (int32_t *)spare, n, w.scalars + 4, w.scan_tmp, st));
-    k_bq_count<<<kNumSM * 8, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, (int32_t *)spare, w.scalars, w.cand_start,
-                                           w.kc, w.cand, r2, w.counts);
+    k_bq_tiles<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n, (int32_t *)spare2);
+    PG_TRY(scan_exclusive_i32((int32_t *)spare2, (int32_t *)spare2, n, w.scalars + 5, w.scan_tmp, st));
+    k_bq_merge<<<kNumSM * 8, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, (int32_t *)spare2,
+                                           w.scalars, w.cand);
+    k_bq_count<<<(unsigned)div_up(n, 256), 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cand_start, w.kc, w.cand, r2, n, w.counts);
     // starts (reuse pslot) and the interleaved (start, len) rows
     PG_TRY(scan_exclusive_i32(w.counts, w.pslot, n, w.scalars + 2, w.scan_tmp, st));
     k_bq_start_len<<<(unsigned)div_up(n, 256), 256, 0, st>>>(w.counts, w.pslot, n, (int2 *)start_len);
