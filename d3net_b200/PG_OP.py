@@ -274,3 +274,22 @@ def sec_min(inp, offsets, out, nProposal, C):
 def sec_max(inp, offsets, out, nProposal, C):
     """sec_mean.h:20 / sec_mean.cu:64-86."""
     _seg(_L().pg_sec_max, inp, offsets, out, nProposal, C)
+
+
+# -------------------------------------------------------------------------------------------------
+# additions (not in the reference's PG_OP)
+# -------------------------------------------------------------------------------------------------
+def gather_rows(src, idx, out=None):
+    """out[i] = src[idx[i]] for fp32 [N, C] rows and an int32 / int64 index vector, all CUDA."""
+    _need(src, "src", torch.float32)
+    if idx.dtype not in (torch.int32, torch.int64) or not idx.is_cuda or not idx.is_contiguous():
+        raise TypeError("idx must be a contiguous CUDA int32 / int64 tensor")
+    if src.dim() != 2:
+        raise ValueError("src must be [N, C]")
+    n, C = idx.numel(), src.size(1)
+    if out is None:
+        out = torch.empty((n, C), dtype=torch.float32, device=src.device)
+    with torch.cuda.device(src.device):
+        check(_L().pg_gather_rows(_p(src), _p(idx), int(idx.dtype == torch.int64), _p(out), n, C, _stream()),
+              "gather_rows")
+    return out

@@ -89,6 +89,7 @@ SIGNATURES = {
     "pg_sec_min": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pg_sec_max": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pg_get_iou": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
+    "pg_gather_rows": (_int, [_vp, _vp, _int, _vp, _i64, _i32, _vp]),
 }
 
 

@@ -63,6 +63,12 @@ class _NoTimer(SectionTimer):
         super().__init__(False)
 
 
+def _gather_rows(ops, feats, idx):
+    """feats[idx]; through the package's coalesced gather kernel when `ops` offers one."""
+    fn = getattr(ops, "gather_rows", None)
+    return fn(feats, idx) if fn is not None and feats.is_cuda else feats[idx]
+
+
 def get_batch_offsets(batch_idxs, batch_size):
     """model/pointgroup.py:112-122 without the Python loop."""
     counts = torch.bincount(batch_idxs.long(), minlength=batch_size)[:batch_size]
@@ -77,7 +83,7 @@ def clusters_voxelization(ops, clusters_idx, clusters_offset, feats, coords, ful
     reproducible.  Returns (voxel_feats [M,C], voxel_coords int64 [M,4], p2v_map, v2p_map, (center, size))."""
     timer = timer or _NoTimer()
     c_idxs = clusters_idx[:, 1].long()
-    clusters_feats = feats[c_idxs]
+    clusters_feats = _gather_rows(ops, feats, c_idxs)
     clusters_coords = coords[c_idxs]
     cid = clusters_idx[:, 0].long()
 
@@ -207,7 +213,7 @@ def proposal_chain(ops, batch, rand6=None, timer=None, trace=None):
 
     # ---- score features per point and proposal pooling (pointgroup.py:332-334; the score U-Net is
     #      out of scope, its per-voxel output is stood in for by its input)
-    pt_score_feats = prop_voxel_feats[prop_p2v_map.long()].contiguous()
+    pt_score_feats = _gather_rows(ops, prop_voxel_feats, prop_p2v_map)
     t = timer.start("roipool")
     proposals_score_feats = ops.roipool(pt_score_feats, proposals_offset)
     timer.stop(t)

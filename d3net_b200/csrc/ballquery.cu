@@ -84,30 +84,35 @@ __global__ void k_bq_keys(const float *__restrict__ xyz, const int32_t *__restri
     keys[i] = make_int4(__ldg(batch_idxs + i), cell_coord(x, inv_s), cell_coord(y, inv_s), cell_coord(z, inv_s));
 }
 
-// one thread per cell: 27 neighbour ids (-1 when absent; slot 13 is the cell itself) + candidate count
-__global__ void k_bq_neighbours(const int4 *__restrict__ keys, GroupTable tab, const uint32_t *__restrict__ sorted_pt,
-                                const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
-                                const int64_t *__restrict__ nCells, int32_t *__restrict__ nbr, int32_t *__restrict__ kc) {
+// one warp per cell: lane j < 27 looks up neighbour j (-1 when absent; slot 13 is the cell itself),
+// the warp sums the candidate count
+__global__ void __launch_bounds__(256) k_bq_neighbours(const int4 *__restrict__ keys, GroupTable tab,
+                                                       const uint32_t *__restrict__ sorted_pt,
+                                                       const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
+                                                       const int64_t *__restrict__ nCells, int32_t *__restrict__ nbr,
+                                                       int32_t *__restrict__ kc) {
     const int64_t nc = *nCells;
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nc; c += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nc; c += nWarps) {
         const int4 k = keys[sorted_pt[cstart[c]]];
-        int total = 0;
-        int j = 0;
-        for (int dz = -1; dz <= 1; dz++)
-            for (int dy = -1; dy <= 1; dy++)
-                for (int dx = -1; dx <= 1; dx++, j++) {
-                    int id;
-                    if (j == 13) id = (int)c;
-                    else {
-                        // wrapping adds: far-coordinate cells may sit at the int32 limits
-                        const int4 q = make_int4(k.x, (int)((unsigned)k.y + (unsigned)dx), (int)((unsigned)k.z + (unsigned)dy),
-                                                 (int)((unsigned)k.w + (unsigned)dz));
-                        id = group_lookup(keys, tab, q);
-                    }
-                    nbr[c * 27 + j] = id;
-                    if (id >= 0) total += ccnt[id];
-                }
-        kc[c] = total;
+        int cnt = 0;
+        if (lane < 27) {
+            const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+            int id;
+            if (lane == 13) id = (int)c;
+            else {
+                // wrapping adds: far-coordinate cells may sit at the int32 limits
+                const int4 q = make_int4(k.x, (int)((unsigned)k.y + (unsigned)dx), (int)((unsigned)k.z + (unsigned)dy),
+                                         (int)((unsigned)k.w + (unsigned)dz));
+                id = group_lookup(keys, tab, q);
+            }
+            nbr[c * 27 + lane] = id;
+            if (id >= 0) cnt = ccnt[id];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if (lane == 0) kc[c] = cnt;
     }
 }
 
@@ -303,6 +308,35 @@ __global__ void k_bq_start_len(const int32_t *__restrict__ counts, const int32_t
     if (i < n) start_len[i] = make_int2(starts[i], counts[i]);
 }
 
+// fill: a warp streams a cell's candidate array lane-per-candidate (coalesced 512-byte loads), ballots
+// the hits and writes them compacted -- ascending by construction -- until the query's count is
+// reached.  Four queries that share a cell (the common case wherever it matters: dense cells hold
+// hundreds of queries) ride on the same candidate loads.
+constexpr int kFillQ = 4;
+
+__device__ __forceinline__ void bq_fill_one(const float *__restrict__ xyz, uint32_t k, const float4 *__restrict__ cl, int K,
+                                            const int2 *__restrict__ start_len, float r2, int32_t *__restrict__ idx,
+                                            int lane, unsigned lt) {
+    const int2 sl = __ldg(start_len + k);
+    if (sl.y == 0) return;
+    const float ox = __ldg(xyz + 3 * (int64_t)k), oy = __ldg(xyz + 3 * (int64_t)k + 1), oz = __ldg(xyz + 3 * (int64_t)k + 2);
+    int32_t *out = idx + sl.x;
+    int written = 0;
+    for (int base = 0; base < K && written < sl.y; base += 32) {
+        const int e = base + lane;
+        bool hit = false;
+        float4 cd = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (e < K) {
+            cd = __ldg(cl + e);
+            hit = bq_hit(ox, oy, oz, cd, r2);
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const int pos = written + __popc(m & lt);
+        if (hit && pos < sl.y) out[pos] = __float_as_int(cd.w);
+        written += __popc(m);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_bq_fill(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
                                                  const int32_t *__restrict__ cell, const int32_t *__restrict__ cand_start,
                                                  const int32_t *__restrict__ kc, const float4 *__restrict__ cand,
@@ -311,28 +345,49 @@ __global__ void __launch_bounds__(256) k_bq_fill(const float *__restrict__ xyz, 
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n; q += nWarps) {
-        const uint32_t k = sorted_pt[q];
-        const int len = __ldg(&start_len[k].y);
-        if (len == 0) continue;
-        const int c = __ldg(cell + k);
-        const float ox = __ldg(xyz + 3 * (int64_t)k), oy = __ldg(xyz + 3 * (int64_t)k + 1), oz = __ldg(xyz + 3 * (int64_t)k + 2);
-        const float4 *cl = cand + __ldg(cand_start + c);
-        const int K = __ldg(kc + c);
-        int32_t *out = idx + __ldg(&start_len[k].x);
-        int written = 0;
-        for (int base = 0; base < K && written < len; base += 32) {
+    for (int64_t q0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kFillQ; q0 < n; q0 += nWarps * kFillQ) {
+        const int nq = (int)((n - q0) < kFillQ ? (n - q0) : kFillQ);
+        uint32_t k[kFillQ];
+        int c[kFillQ];
+        bool same = nq == kFillQ;
+#pragma unroll
+        for (int u = 0; u < kFillQ; u++) {
+            k[u] = u < nq ? sorted_pt[q0 + u] : 0u;
+            c[u] = u < nq ? __ldg(cell + k[u]) : -1;
+            same = same && c[u] == c[0];
+        }
+        if (!same) {
+            for (int u = 0; u < nq; u++)
+                bq_fill_one(xyz, k[u], cand + __ldg(cand_start + c[u]), __ldg(kc + c[u]), start_len, r2, idx, lane, lt);
+            continue;
+        }
+        const float4 *cl = cand + __ldg(cand_start + c[0]);
+        const int K = __ldg(kc + c[0]);
+        float ox[kFillQ], oy[kFillQ], oz[kFillQ];
+        int len[kFillQ], written[kFillQ];
+        int32_t *out[kFillQ];
+        int todo = 0;
+#pragma unroll
+        for (int u = 0; u < kFillQ; u++) {
+            const int2 sl = __ldg(start_len + k[u]);
+            ox[u] = __ldg(xyz + 3 * (int64_t)k[u]); oy[u] = __ldg(xyz + 3 * (int64_t)k[u] + 1); oz[u] = __ldg(xyz + 3 * (int64_t)k[u] + 2);
+            len[u] = sl.y; out[u] = idx + sl.x; written[u] = 0;
+            todo += sl.y > 0;
+        }
+        for (int base = 0; base < K && todo > 0; base += 32) {
             const int e = base + lane;
-            bool hit = false;
-            float4 cd = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (e < K) {
-                cd = __ldg(cl + e);
-                hit = bq_hit(ox, oy, oz, cd, r2);
+            const bool in = e < K;
+            const float4 cd = in ? __ldg(cl + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            todo = 0;
+#pragma unroll
+            for (int u = 0; u < kFillQ; u++) {
+                const bool hit = in && bq_hit(ox[u], oy[u], oz[u], cd, r2);
+                const unsigned m = __ballot_sync(0xffffffffu, hit);
+                const int pos = written[u] + __popc(m & lt);
+                if (hit && pos < len[u]) out[u][pos] = __float_as_int(cd.w);
+                written[u] += __popc(m);
+                todo += written[u] < len[u];
             }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            const int pos = written + __popc(m & lt);
-            if (hit && pos < len) out[pos] = __float_as_int(cd.w);
-            written += __popc(m);
         }
     }
 }
@@ -378,7 +433,7 @@ extern "C" int pg_ballquery_count(const float *xyz, const int32_t *batch_idxs, c
     PG_CUDA(cudaMemsetAsync(w.ccnt + n, 0, sizeof(int32_t), st));
     PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
     const unsigned gsm = kNumSM * 8;
-    k_bq_neighbours<<<gsm, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc);
+    k_bq_neighbours<<<kNumSM * 16, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc);
     k_bq_clear_tail<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n + 1);   // kc beyond nCells must scan as 0
     PG_TRY(scan_exclusive_i32(w.kc, w.cand_start, (int64_t)n + 1, w.scalars + 1, w.scan_tmp, st));
     k_bq_tiles<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n, (int32_t *)spare2);

@@ -306,3 +306,25 @@ class SecMax(Function):
 
 
 sec_max = SecMax.apply
+
+
+class GatherRows(Function):
+    """ADDITION (not in the reference API): feats[idx] for fp32 [N, C] rows as one coalesced kernel.
+    torch's own row gather is launch-rate bound on this shape (one tiny block per row); the
+    reference's caller does this gather between the ops (model/pointgroup.py:133-134,333)."""
+
+    @staticmethod
+    def forward(ctx, feats, idx):
+        ctx.save_for_backward(idx)
+        ctx.n_rows = feats.size(0)
+        return PG_OP.gather_rows(feats.contiguous(), idx.contiguous())
+
+    @staticmethod
+    def backward(ctx, d_out):
+        (idx,) = ctx.saved_tensors
+        d_feats = torch.zeros((ctx.n_rows, d_out.size(1)), dtype=d_out.dtype, device=d_out.device)
+        d_feats.index_add_(0, idx.long(), d_out)
+        return d_feats, None
+
+
+gather_rows = GatherRows.apply

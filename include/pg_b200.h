@@ -146,6 +146,14 @@ int pg_get_iou(const int32_t *proposals_idx, const int32_t *proposals_offset,
                const int64_t *instance_labels, const int32_t *instance_pointnum, float *proposals_iou,
                int32_t nInstance, int32_t nProposal, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * gather_rows     an ADDITION, not a PG_OP function: dst[i][:] = src[idx[i]][:], the row gather the
+ * reference's caller performs in torch between the ops (clusters_feats = feats[c_idxs],
+ * model/pointgroup.py:133-134; score_feats.features[p2v_map], :333).  idx is int32 or int64.
+ * ---------------------------------------------------------------------------------------------- */
+int pg_gather_rows(const float *src, const void *idx, int idx_is_int64, float *dst, int64_t nIdx, int32_t C,
+                   void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -422,3 +422,16 @@ def test_pack_proposals(ops):
         first = torch.nonzero(scene == b).view(-1)[0]
         assert torch.equal(packed[b, 0, :16], out["proposals_score_feats"][first])
     assert torch.equal(pgdist.all_gather_proposals(packed), packed)      # world size 1: identity
+
+
+def test_gather_rows(ops):
+    rng = np.random.default_rng(77)
+    for C in (1, 3, 16, 134):
+        src = rng.standard_normal((5000, C)).astype(np.float32)
+        for dt in (torch.int32, torch.int64):
+            idx = rng.integers(0, 5000, 12345)
+            s = cu(src).requires_grad_(True)
+            out = ops.gather_rows(s, cu(idx, dt))
+            np.testing.assert_array_equal(npy(out), src[idx])
+            out.sum().backward()
+            np.testing.assert_array_equal(npy(s.grad)[:, 0], np.bincount(idx, minlength=5000).astype(np.float32))
