@@ -122,11 +122,6 @@ __device__ __forceinline__ void vred(float *p, float v) { atomicAdd(p, v); }
 __device__ __forceinline__ void vred(float2 *p, float2 v) { atomicAdd(p, v); }
 __device__ __forceinline__ void vred(float4 *p, float4 v) { atomicAdd(p, v); }
 
-// Four (row, column) items per thread per trip, software-pipelined: all four row headers, then all
-// four first indices, then all four first gathers are in flight before anything is consumed -- the
-// three dependent loads of an item would otherwise leave most of the bytes-in-flight budget idle.
-constexpr int kVoxIlp = 4;
-
 template <int V>
 __global__ void __launch_bounds__(256) k_voxelize_fp(const float *__restrict__ feats, float *__restrict__ out,
                                                      const int32_t *__restrict__ rules, int32_t M, int32_t W,
@@ -135,44 +130,26 @@ __global__ void __launch_bounds__(256) k_voxelize_fp(const float *__restrict__ f
     const T *__restrict__ f = reinterpret_cast<const T *>(feats);
     T *__restrict__ o = reinterpret_cast<T *>(out);
     const int64_t total = (int64_t)M * Cv;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += stride * kVoxIlp) {
-        const int32_t *r[kVoxIlp];
-        int c[kVoxIlp], n[kVoxIlp], r1[kVoxIlp];
-        T x1[kVoxIlp];
-#pragma unroll
-        for (int u = 0; u < kVoxIlp; u++) {
-            const int64_t t = t0 + u * stride;
-            const int v = t < total ? (int)(t / Cv) : 0;
-            c[u] = t < total ? (int)(t - (int64_t)v * Cv) : 0;
-            r[u] = rules + (int64_t)v * W;
-            n[u] = t < total ? __ldg(r[u]) : 0;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+         t += (int64_t)gridDim.x * blockDim.x) {
+        const int v = (int)(t / Cv), c = (int)(t - (int64_t)v * Cv);
+        const int32_t *r = rules + (int64_t)v * W;
+        const int n = __ldg(r);
+        const float mult = (average && n > 0) ? __fdiv_rn(1.0f, (float)n) : 1.0f;
+        T acc;
+        vzero<V>(acc);
+        int i = 1;
+        for (; i + 3 <= n; i += 4) {   // four independent gathers in flight, then the ordered adds
+            const int r0 = __ldg(r + i), r1 = __ldg(r + i + 1), r2 = __ldg(r + i + 2), r3 = __ldg(r + i + 3);
+            const T x0 = __ldg(f + (int64_t)r0 * Cv + c), x1 = __ldg(f + (int64_t)r1 * Cv + c);
+            const T x2 = __ldg(f + (int64_t)r2 * Cv + c), x3 = __ldg(f + (int64_t)r3 * Cv + c);
+            vmuladd(acc, mult, x0); vmuladd(acc, mult, x1); vmuladd(acc, mult, x2); vmuladd(acc, mult, x3);
         }
-#pragma unroll
-        for (int u = 0; u < kVoxIlp; u++) r1[u] = n[u] > 0 ? __ldg(r[u] + 1) : 0;
-#pragma unroll
-        for (int u = 0; u < kVoxIlp; u++) {
-            vzero<V>(x1[u]);
-            if (n[u] > 0) x1[u] = __ldg(f + (int64_t)r1[u] * Cv + c[u]);
+        for (; i <= n; i++) {
+            const int r0 = __ldg(r + i);
+            vmuladd(acc, mult, __ldg(f + (int64_t)r0 * Cv + c));
         }
-#pragma unroll
-        for (int u = 0; u < kVoxIlp; u++) {
-            const int64_t t = t0 + u * stride;
-            if (t >= total) continue;
-            const float mult = (average && n[u] > 0) ? __fdiv_rn(1.0f, (float)n[u]) : 1.0f;
-            T acc;
-            vzero<V>(acc);
-            if (n[u] > 0) vmuladd(acc, mult, x1[u]);
-            int i = 2;
-            for (; i + 3 <= n[u]; i += 4) {   // four independent gathers in flight, then the ordered adds
-                const int q0 = __ldg(r[u] + i), q1 = __ldg(r[u] + i + 1), q2 = __ldg(r[u] + i + 2), q3 = __ldg(r[u] + i + 3);
-                const T y0 = __ldg(f + (int64_t)q0 * Cv + c[u]), y1 = __ldg(f + (int64_t)q1 * Cv + c[u]);
-                const T y2 = __ldg(f + (int64_t)q2 * Cv + c[u]), y3 = __ldg(f + (int64_t)q3 * Cv + c[u]);
-                vmuladd(acc, mult, y0); vmuladd(acc, mult, y1); vmuladd(acc, mult, y2); vmuladd(acc, mult, y3);
-            }
-            for (; i <= n[u]; i++) vmuladd(acc, mult, __ldg(f + (int64_t)__ldg(r[u] + i) * Cv + c[u]));
-            __stcs(o + t, acc);
-        }
+        __stcs(o + t, acc);
     }
 }
 

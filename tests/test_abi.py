@@ -1,0 +1,91 @@
+"""The C-ABI library loads on a machine without a GPU and exports exactly what include/pg_b200.h
+declares; host-only entry points (workspace sizing, argument validation, N = 0 early-outs) behave."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "pg_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pg_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from d3net_b200 import _native
+    _native.build()
+    return _native.lib()
+
+
+def test_every_declared_symbol_is_exported_and_bound(lib):
+    from d3net_b200 import _native
+    names = _declared()
+    assert len(names) == 23
+    for n in names:
+        assert hasattr(lib, n), "libpg_b200.so does not export " + n
+        assert n in _native.SIGNATURES, "no ctypes signature for " + n
+    assert sorted(_native.SIGNATURES) == names      # nothing bound that the header does not declare
+    assert lib.pg_abi_version() == 1
+
+
+def test_header_cites_the_reference_interface():
+    src = open(os.path.join(ROOT, "include", "pg_b200.h")).read()
+    for ref in ("pointgroup_ops_api.cpp", "voxelize.cpp", "bfs_cluster.h:15", "bfs_cluster.h:18", "roipool.h:15",
+                "sec_mean.h:14", "get_iou.h:16"):
+        assert ref in src
+
+
+def test_workspace_sizes_scale(lib):
+    for fn in (lib.pg_voxelize_idx_workspace_bytes, lib.pg_ballquery_workspace_bytes, lib.pg_bfs_cluster_workspace_bytes):
+        a, b, z = fn(1000), fn(1000000), fn(0)
+        assert 0 < z <= a < b
+        assert b < 1000000 * 1024          # under 1 KB per point
+    assert lib.pg_roipool_workspace_bytes(10, 16) >= 10 * 16 * 8
+
+
+def test_argument_validation_without_a_gpu(lib):
+    """Every path below returns before any CUDA call."""
+    sizes = (ctypes.c_int32 * 3)()
+    total = ctypes.c_int64(-1)
+    assert lib.pg_voxelize_idx_map(None, 0, 4, None, None, 0, sizes, None) == 0 and list(sizes)[:2] == [0, 1]
+    assert lib.pg_voxelize_idx_map(None, 0, 9, None, None, 0, sizes, None) == -1           # bad mode
+    assert b"mode" in lib.pg_last_error()
+    assert lib.pg_voxelize_idx_map(None, 5, 4, None, None, 0, sizes, None) == -1           # null pointers
+    assert lib.pg_ballquery_count(None, None, None, 0, 1, 0.03, None, None, 0, ctypes.byref(total), None) == 0
+    assert total.value == 0
+    assert lib.pg_ballquery_count(None, None, None, -1, 1, 0.03, None, None, 0, ctypes.byref(total), None) == -1
+    assert lib.pg_bfs_cluster_count(None, None, None, 0, 0, 50, 0, None, 0, sizes, None) == 0
+    assert lib.pg_voxelize_fp(None, None, None, 0, 1, 16, 1, None) == 0
+    assert lib.pg_voxelize_fp(None, None, None, 5, 1, 16, 1, None) == -1
+    assert lib.pg_sec_mean(None, None, None, 0, 0, 3, None) == 0
+    assert lib.pg_get_iou(None, None, None, None, None, 0, 0, None) == 0
+    assert lib.pg_roipool_bp(None, None, None, None, 0, 16, None) == 0
+    assert lib.pg_gather_rows(None, None, 0, None, 0, 16, None) == 0
+
+
+def test_product_never_touches_the_oracle():
+    """The oracle is test infrastructure: nothing under d3net_b200/ may import or open it."""
+    pkg = os.path.join(ROOT, "d3net_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("the oracle", "").replace("The oracle", "") or f == "chain.py", f
+    chain = open(os.path.join(pkg, "chain.py")).read()
+    assert "import oracle" not in chain and "from oracle" not in chain
+
+
+def test_ops_fail_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from d3net_b200 import pointgroup_ops as ops
+    with pytest.raises(RuntimeError):
+        ops.voxelization_idx(torch.zeros((4, 4), dtype=torch.int64), 1, 4)
+    with pytest.raises((AssertionError, RuntimeError, ValueError)):
+        ops.sec_mean(torch.zeros((4, 3)), torch.tensor([0, 4], dtype=torch.int32))
