@@ -222,8 +222,31 @@ def run_b200(args, rank, world, local):
 
     d2h_keep = {}
 
+    # End to end: every step's inputs start in pinned HOST memory.  The upload of step k+1 runs on a copy
+    # stream while step k computes (what a serving loop does); every byte of every upload is inside the
+    # timed region, and each step ends with the device->host read of its results.
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def upload():
+        with torch.cuda.stream(copy_stream):
+            b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        return b, ev
+
+    e2e_state = {"next": None, "left": 0}
+
     def step_e2e():
-        b = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+        if e2e_state["next"] is None:
+            e2e_state["next"] = upload()
+        b, ev = e2e_state["next"]
+        e2e_state["left"] -= 1
+        e2e_state["next"] = upload() if e2e_state["left"] > 0 else None
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        for v in b.values():
+            if torch.is_tensor(v):
+                v.record_stream(cur)
         out = chain.proposal_chain(ops, b, rand6)
         packed = pgdist.pack_proposals(out, b, args.max_proposals)
         gathered = pgdist.all_gather_proposals(packed)
@@ -271,8 +294,10 @@ def run_b200(args, rank, world, local):
     ms_total = timed(lambda: step_device(timer), args.steps)
     ops._section_timer = None
     # timed region 2: end to end from pinned host memory
+    e2e_state["left"] = 2
     for _ in range(2):
         step_e2e()
+    e2e_state["left"] = args.steps
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -284,7 +309,9 @@ def run_b200(args, rank, world, local):
         sec_ms = {k: v / args.steps for k, v in timer.totals_ms().items()}
         algo = algorithmic_bytes(batch, out)
         peak, peak_kind = peaks()
-        single_kernel = {k: v for k, v in sec_ms.items() if k in algo}
+        # the roofline is quoted for a SINGLE kernel: sections that bracket exactly one launch
+        one_launch = ("voxelization(scene)", "ballquery(shift).fill", "ballquery(raw).fill")
+        single_kernel = {k: v for k, v in sec_ms.items() if k in algo and k in one_launch}
         dom = max(single_kernel, key=single_kernel.get)
         achieved = algo[dom] / (sec_ms[dom] / 1e3) / 1e9
         per_op = {k: {"ms": round(v, 4), "GBps": (round(algo[k] / (v / 1e3) / 1e9, 1) if k in algo else None)}
@@ -313,6 +340,7 @@ def run_b200(args, rank, world, local):
                        "nActive_shift": int(out["nActive_shift"]), "nActive_raw": int(out["nActive_raw"]),
                        "n_proposals": int(out["proposals_offset"].numel() - 1), "sumNPoint": int(out["proposals_idx"].shape[0])},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "pipeline": "H2D of step k+1 on a copy stream overlaps step k; all uploads inside the timed region",
                     "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_keep.get("bytes", 0))},
             "gpu_launches": (n_launch * args.steps) if n_launch is not None else None,
             "gpu_launches_per_step": n_launch,
