@@ -301,6 +301,10 @@ def run_b200(args, rank, world, local):
     ms_e2e = timed(step_e2e, args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
+    # kernels of this library launched per step (CUPTI count of one untimed step; every rank takes part
+    # because the step contains the collective)
+    n_launch, top = count_pg_kernels(lambda: step_device())
+
     total_scenes = n_scenes * world
     value = total_scenes * args.steps / (ms_total / 1e3)
     e2e_value = total_scenes * args.steps / (ms_e2e / 1e3)
@@ -316,9 +320,6 @@ def run_b200(args, rank, world, local):
         achieved = algo[dom] / (sec_ms[dom] / 1e3) / 1e9
         per_op = {k: {"ms": round(v, 4), "GBps": (round(algo[k] / (v / 1e3) / 1e9, 1) if k in algo else None)}
                   for k, v in sorted(sec_ms.items(), key=lambda kv: -kv[1])}
-        n_launch, top = (None, [])
-        if world == 1:
-            n_launch, top = count_pg_kernels(lambda: step_device())
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             rate, ms, desc, cores, kind = cpu_chain_rate(20.0, 1, 1)

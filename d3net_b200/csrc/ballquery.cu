@@ -278,27 +278,53 @@ __global__ void k_bq_clear_tail(int32_t *kc, const int64_t *__restrict__ nCells,
     for (int64_t c = nc + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n1; c += (int64_t)gridDim.x * blockDim.x) kc[c] = 0;
 }
 
-// count: one thread per query, taken in cell-sorted order so that the lanes of a warp mostly share a
-// cell: their loads of the cell's candidate array are then the same address (one broadcast
-// transaction), and in sparse regions each lane simply walks its own short list.
+// count: one thread per query, taken in cell-sorted order.  When all 32 lanes of a warp sit in the
+// same cell (every dense cell), the warp stages the cell's candidate array through shared memory 32
+// records at a time -- one coalesced 512-byte load, prefetched one tile ahead -- and every lane reads
+// the records back as LDS.128 broadcasts: the loop runs at shared-memory latency instead of waiting
+// on a 16-byte global load per candidate.  Mixed warps (sparse regions) walk their own short lists.
 __global__ void __launch_bounds__(256) k_bq_count(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
                                                   const int32_t *__restrict__ cell, const int32_t *__restrict__ cand_start,
                                                   const int32_t *__restrict__ kc, const float4 *__restrict__ cand,
                                                   float r2, int32_t n, int32_t *__restrict__ counts) {
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t k = sorted_pt[q];
-        const int c = __ldg(cell + k);
-        const float ox = __ldg(xyz + 3 * (int64_t)k), oy = __ldg(xyz + 3 * (int64_t)k + 1), oz = __ldg(xyz + 3 * (int64_t)k + 2);
-        const float4 *cl = cand + __ldg(cand_start + c);
-        const int K = __ldg(kc + c);
+    __shared__ float4 tile_all[8][32];
+    float4 *tile = tile_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int64_t n_up = ((int64_t)n + 31) / 32 * 32;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_up; q += (int64_t)gridDim.x * blockDim.x) {
+        const bool live = q < n;
+        const uint32_t k = live ? sorted_pt[q] : 0u;
+        const int c = live ? __ldg(cell + k) : -1;
+        const bool uni = __all_sync(0xffffffffu, c == __shfl_sync(0xffffffffu, c, 0));
+        if (!live && !uni) continue;
+        float ox = 0.f, oy = 0.f, oz = 0.f;
+        if (live) { ox = __ldg(xyz + 3 * (int64_t)k); oy = __ldg(xyz + 3 * (int64_t)k + 1); oz = __ldg(xyz + 3 * (int64_t)k + 2); }
         int cnt = 0;
-        int e = 0;
-        for (; e + 4 <= K; e += 4) {
-            const float4 c0 = __ldg(cl + e), c1 = __ldg(cl + e + 1), c2 = __ldg(cl + e + 2), c3 = __ldg(cl + e + 3);
-            cnt += bq_hit(ox, oy, oz, c0, r2) + bq_hit(ox, oy, oz, c1, r2) + bq_hit(ox, oy, oz, c2, r2) + bq_hit(ox, oy, oz, c3, r2);
+        if (uni) {
+            if (c < 0) continue;                     // a whole warp past the end
+            const float4 *cl = cand + __ldg(cand_start + c);
+            const int K = __ldg(kc + c);
+            const float4 pad = make_float4(INFINITY, INFINITY, INFINITY, 0.f);   // never within any radius
+            float4 nx = lane < K ? __ldg(cl + lane) : pad;
+            for (int base = 0; base < K; base += 32) {
+                tile[lane] = nx;
+                __syncwarp();
+                nx = (base + 32 + lane < K) ? __ldg(cl + base + 32 + lane) : pad;
+#pragma unroll
+                for (int u = 0; u < 32; u++) cnt += bq_hit(ox, oy, oz, tile[u], r2);
+                __syncwarp();
+            }
+        } else {
+            const float4 *cl = cand + __ldg(cand_start + c);
+            const int K = __ldg(kc + c);
+            int e = 0;
+            for (; e + 4 <= K; e += 4) {
+                const float4 c0 = __ldg(cl + e), c1 = __ldg(cl + e + 1), c2 = __ldg(cl + e + 2), c3 = __ldg(cl + e + 3);
+                cnt += bq_hit(ox, oy, oz, c0, r2) + bq_hit(ox, oy, oz, c1, r2) + bq_hit(ox, oy, oz, c2, r2) + bq_hit(ox, oy, oz, c3, r2);
+            }
+            for (; e < K; e++) cnt += bq_hit(ox, oy, oz, __ldg(cl + e), r2);
         }
-        for (; e < K; e++) cnt += bq_hit(ox, oy, oz, __ldg(cl + e), r2);
-        counts[k] = min(cnt, kCap);
+        if (live) counts[k] = min(cnt, kCap);
     }
 }
 
@@ -374,10 +400,12 @@ __global__ void __launch_bounds__(256) k_bq_fill(const float *__restrict__ xyz, 
             len[u] = sl.y; out[u] = idx + sl.x; written[u] = 0;
             todo += sl.y > 0;
         }
+        float4 nx = lane < K ? __ldg(cl + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
         for (int base = 0; base < K && todo > 0; base += 32) {
             const int e = base + lane;
             const bool in = e < K;
-            const float4 cd = in ? __ldg(cl + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 cd = nx;
+            nx = (e + 32 < K) ? __ldg(cl + e + 32) : make_float4(0.f, 0.f, 0.f, 0.f);   // next tile in flight
             todo = 0;
 #pragma unroll
             for (int u = 0; u < kFillQ; u++) {

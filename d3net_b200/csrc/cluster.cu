@@ -69,10 +69,13 @@ static ClWs cl_layout(void *ws, size_t ws_bytes, int64_t N_) {
     return w;
 }
 
+// 64-bit tag of an ordered pair (hi, lo): the product of two independently scrambled 32-bit words.
+// Cheap (three integer multiplies); it only has to make accidental cancellation of unmatched edges
+// in the checksum a 2^-64-class event, not resist an adversary.
 __device__ __forceinline__ unsigned long long mix64(unsigned a, unsigned b) {
-    unsigned long long x = ((unsigned long long)a << 32) | b;
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
-    return x;
+    const unsigned x = (a ^ 0x5bd1e995u) * 0x9E3779B1u;
+    const unsigned y = (b + 0x7f4a7c15u) * 0x85EBCA77u;
+    return (unsigned long long)(x ^ (x >> 15)) * (unsigned long long)((y ^ (y >> 13)) | 1u) + a;
 }
 
 // one thread per point, launched over ceil(N / 32) * 32 threads so every bitmap word has a full warp
@@ -142,38 +145,61 @@ __global__ void __launch_bounds__(256) k_cl_union(const int32_t *__restrict__ id
         if (!live) continue;
         const int2 sl = start_len[i];
         const unsigned li = pl[i].y;
-        for (int e = sub; e < sl.y; e += G) {
-            const int j = __ldg(idx + sl.x + e);
-            if ((unsigned)j >= (unsigned)N) { bad = true; continue; }
-            if (e > 0 && __ldg(idx + sl.x + e - 1) >= j) bad = true;   // lists must ascend for the O(1) two-way test
-            if (j == i) continue;
-            const bool jfull = (__ldg(trunc + (j >> 5)) >> (j & 31)) & 1u;
-            const bool twoway = !jfull || i <= __ldg(last + j);
-            if (twoway) {
-                // each two-way pair {a > b} is seen as a -> b and as b -> a: the two terms cancel
-                if (j < i) chk += mix64((unsigned)i, (unsigned)j); else { chk -= mix64((unsigned)j, (unsigned)i); continue; }
+        // software pipeline, kU edges per lane per trip: all index loads first, then all bitmap words,
+        // then all (parent, label) records -- three dependent round trips per trip instead of per edge
+        constexpr int kU = 4;
+        for (int e0 = sub; e0 < sl.y; e0 += kU * G) {
+            int jj[kU], pv[kU];
+            unsigned tw[kU];
+            uint2 w[kU];
+            bool use[kU], twoway[kU];
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int e = e0 + u * G;
+                jj[u] = e < sl.y ? __ldg(idx + sl.x + e) : -1;
+                pv[u] = (e < sl.y && e > 0) ? __ldg(idx + sl.x + e - 1) : -1;      // same lines as a neighbour lane's jj
             }
-            // two-way edges are taken from their higher endpoint; one-way edges as they come
-            const uint2 w = __ldcg(pl + j);
-            if (w.y != li) continue;
-            const int p = (int)w.x;
-            if (p == ri) continue;                 // already under the same root
-            // climb from j's parent to its root, stopping early at ri (spares the hot root line)
-            int r = p;
-            while (r != ri) {
-                const int g = (int)__ldcg(&pl[r].x);
-                if (g == r) break;
-                r = g;
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                use[u] = jj[u] >= 0 && jj[u] < N && jj[u] != i;
+                if (e0 + u * G < sl.y && (jj[u] < 0 || jj[u] >= N)) bad = true;
+                if (pv[u] >= jj[u] && e0 + u * G < sl.y && e0 + u * G > 0) bad = true;   // lists must ascend
+                tw[u] = use[u] ? __ldg(trunc + (jj[u] >> 5)) : 0u;
             }
-            if (r != p) pl[j].x = (unsigned)r;     // compress j straight onto the ancestor found
-            if (r == ri) continue;
-            if (twoway) {
-                ri = uf_union_roots(pl, ri, r);
-            } else {
-                // one-way edge i -> j whose ends are not (yet) connected: park it
-                if (uf_find(pl, ri) == uf_find(pl, r)) continue;
-                const unsigned long long slot = atomicAdd(&scalars[2], 1ULL);
-                if (slot < pend_cap) pend[slot] = make_int2(i, j);
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const bool jfull = (tw[u] >> (jj[u] & 31)) & 1u;
+                twoway[u] = !jfull || i <= __ldg(last + jj[u]);
+                if (use[u] && twoway[u]) {
+                    // each two-way pair {a > b} is seen as a -> b and as b -> a: the two terms cancel
+                    if (jj[u] < i) chk += mix64((unsigned)i, (unsigned)jj[u]);
+                    else { chk -= mix64((unsigned)jj[u], (unsigned)i); use[u] = false; }   // taken from the higher endpoint
+                }
+                w[u] = use[u] ? __ldcg(pl + jj[u]) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                if (!use[u] || w[u].y != li) continue;
+                const int j = jj[u];
+                const int p = (int)w[u].x;
+                if (p == ri) continue;                 // already under the same root
+                // climb from j's parent to its root, stopping early at ri (spares the hot root line)
+                int r = p;
+                while (r != ri) {
+                    const int g = (int)__ldcg(&pl[r].x);
+                    if (g == r) break;
+                    r = g;
+                }
+                if (r != p) pl[j].x = (unsigned)r;     // compress j straight onto the ancestor found
+                if (r == ri) continue;
+                if (twoway[u]) {
+                    ri = uf_union_roots(pl, ri, r);
+                } else {
+                    // one-way edge i -> j whose ends are not (yet) connected: park it
+                    if (uf_find(pl, ri) == uf_find(pl, r)) continue;
+                    const unsigned long long slot = atomicAdd(&scalars[2], 1ULL);
+                    if (slot < pend_cap) pend[slot] = make_int2(i, j);
+                }
             }
         }
     }
