@@ -86,8 +86,13 @@ def voxelize_idx_impl(coords, mode):
     return output_coords, input_map, output_map
 
 
-def ballquery_count_impl(xyz, batch_idxs, batch_offsets, radius):
-    """Phase 1: returns (start_len int32 [n,2], total, workspace)."""
+# hit masks are used while they stay under this many bytes (they cost 1 bit per tested pair)
+BALLQUERY_MASK_BUDGET_BYTES = 4 << 30
+
+
+def ballquery_count_impl(xyz, batch_idxs, batch_offsets, radius, use_masks=True):
+    """Phases 1+2: returns (start_len int32 [n,2], total, state) where state carries the workspace and the
+    optional hit-mask buffer to ballquery_fill_impl."""
     _need(xyz, "coords", torch.float32)
     _need(batch_idxs, "batch_idxs", torch.int32)
     _need(batch_offsets, "batch_offsets", torch.int32)
@@ -99,18 +104,26 @@ def ballquery_count_impl(xyz, batch_idxs, batch_offsets, radius):
         L = _L()
         nws = L.pg_ballquery_workspace_bytes(n)
         ws = _ws(nws, dev)
+        words = ctypes.c_int64(0)
+        check(L.pg_ballquery_prepare(_p(xyz), _p(batch_idxs), _p(batch_offsets), n, batch_offsets.numel() - 1,
+                                     float(radius), _p(ws), nws, ctypes.byref(words), _stream()),
+              "ballquery_batch_p(prepare)")
+        masks = None
+        if use_masks and 0 < words.value and words.value * 4 <= BALLQUERY_MASK_BUDGET_BYTES:
+            masks = torch.empty(words.value, dtype=torch.int32, device=dev)
         start_len = torch.empty((n, 2), dtype=torch.int32, device=dev)
         total = ctypes.c_int64(0)
-        check(L.pg_ballquery_count(_p(xyz), _p(batch_idxs), _p(batch_offsets), n, batch_offsets.numel() - 1,
-                                   float(radius), _p(start_len), _p(ws), nws, ctypes.byref(total), _stream()),
-              "ballquery_batch_p(count)")
-    return start_len, int(total.value), ws
+        check(L.pg_ballquery_count(_p(xyz), n, float(radius), _p(start_len), _p(masks),
+                                   masks.numel() if masks is not None else 0, _p(ws), nws, ctypes.byref(total),
+                                   _stream()), "ballquery_batch_p(count)")
+    return start_len, int(total.value), (ws, masks)
 
 
-def ballquery_fill_impl(xyz, radius, start_len, idx, ws):
+def ballquery_fill_impl(xyz, radius, start_len, idx, state):
+    ws, masks = state
     with torch.cuda.device(xyz.device):
-        check(_L().pg_ballquery_fill(_p(xyz), xyz.size(0), float(radius), _p(start_len), _p(idx), idx.numel(),
-                                     _p(ws), ws.numel(), _stream()), "ballquery_batch_p(fill)")
+        check(_L().pg_ballquery_fill(_p(xyz), xyz.size(0), float(radius), _p(start_len), _p(masks), _p(idx),
+                                     idx.numel(), _p(ws), ws.numel(), _stream()), "ballquery_batch_p(fill)")
 
 
 def bfs_cluster_impl(semantic_label, ball_query_idxs, start_len, threshold, generic=0):

@@ -27,11 +27,12 @@ constexpr int kCap = PG_BALLQUERY_CAP;
 struct BqWs {
     int4 *keys;
     GroupTable tab;
-    int32_t *pslot, *cell, *ccnt, *cstart, *kc, *cand_start, *counts, *nbr;
+    int32_t *pslot, *cell, *ccnt, *cstart, *kc, *cand_start, *counts, *nbr, *mbase;
+    uint32_t *cand_idx;
     uint32_t *kA, *vA, *kB, *vB;
     int32_t *hist;
     int64_t *scan_tmp;
-    int64_t *scalars;   // [0] nCells, [1] total candidates, [2] total neighbours, [3] sorted-buffer id
+    int64_t *scalars;   // [0] nCells [1] total candidates [2] total neighbours [5] merge tiles [6] mask words
     float4 *cand;
     bool ok;
     size_t used;
@@ -61,6 +62,8 @@ static BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
     w.scan_tmp = a.take<int64_t>(scan_tmp_count((int64_t)(n + radix_tmp_count(n_))));
     w.scalars = a.take<int64_t>(8);
     w.cand = a.take<float4>(n * 27);
+    w.cand_idx = a.take<uint32_t>(n * 27);
+    w.mbase = a.take<int32_t>(n + 1);
     w.ok = a.ok;
     w.used = a.used;
     return w;
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(256) k_bq_merge(const float *__restrict__ xyz,
                                                   const int32_t *__restrict__ nbr, const int32_t *__restrict__ kc,
                                                   const int32_t *__restrict__ cand_start,
                                                   const int32_t *__restrict__ tile_start, const int64_t *__restrict__ scalars,
-                                                  float4 *__restrict__ cand) {
+                                                  float4 *__restrict__ cand, uint32_t *__restrict__ cand_idx) {
     __shared__ uint32_t scratch_all[8][32];
     uint32_t *scratch = scratch_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -201,7 +204,9 @@ __global__ void __launch_bounds__(256) k_bq_merge(const float *__restrict__ xyz,
             const int src = __ldg(nbr + (int64_t)c * 27 + lane);
             if (src >= 0) { len = __ldg(ccnt + src); L = sorted_pt + __ldg(cstart + src); }
         }
-        float4 *dst = cand + __ldg(cand_start + c);
+        const int cbase = __ldg(cand_start + c);
+        float4 *dst = cand + cbase;
+        uint32_t *dst_idx = cand_idx + cbase;
         uint32_t sa[30], sb[30];      // interval stack (warp-uniform)
         int sp = 0;
         if (T == 1) {
@@ -259,6 +264,7 @@ __global__ void __launch_bounds__(256) k_bq_merge(const float *__restrict__ xyz,
             if (lane < s) {
                 const float *p = xyz + 3 * (int64_t)key;
                 dst[off + lane] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __int_as_float((int)key));
+                dst_idx[off + lane] = key;
             }
         }
         (void)lt;
@@ -278,14 +284,29 @@ __global__ void k_bq_clear_tail(int32_t *kc, const int64_t *__restrict__ nCells,
     for (int64_t c = nc + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n1; c += (int64_t)gridDim.x * blockDim.x) kc[c] = 0;
 }
 
+// Hit masks: the count pass already evaluates every (query, candidate) predicate, so it records the
+// outcome -- one bit per pair, 32 candidates per word, laid out per cell as [block of 32 candidates]
+// [query of the cell] -- and the fill pass turns bits into indices without touching a coordinate.
+__global__ void k_bq_mask_sizes(const int32_t *__restrict__ ccnt, const int32_t *__restrict__ kc,
+                                const int64_t *__restrict__ nCells, int32_t n1, int32_t *__restrict__ words) {
+    const int64_t nc = *nCells;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n1; c += (int64_t)gridDim.x * blockDim.x) {
+        long long w = c < nc ? (long long)ccnt[c] * ((kc[c] + 31) >> 5) : 0;
+        words[c] = w > 0x7fffffffLL ? 0x7fffffff : (int32_t)w;     // saturates: the int64 total then exceeds the cap
+    }
+}
+
 // count: one thread per query, taken in cell-sorted order.  When all 32 lanes of a warp sit in the
 // same cell (every dense cell), the warp stages the cell's candidate array through shared memory 32
 // records at a time -- one coalesced 512-byte load, prefetched one tile ahead -- and every lane reads
 // the records back as LDS.128 broadcasts: the loop runs at shared-memory latency instead of waiting
 // on a 16-byte global load per candidate.  Mixed warps (sparse regions) walk their own short lists.
+template <bool MASK>
 __global__ void __launch_bounds__(256) k_bq_count(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
-                                                  const int32_t *__restrict__ cell, const int32_t *__restrict__ cand_start,
+                                                  const int32_t *__restrict__ cell, const int32_t *__restrict__ cstart,
+                                                  const int32_t *__restrict__ ccnt, const int32_t *__restrict__ cand_start,
                                                   const int32_t *__restrict__ kc, const float4 *__restrict__ cand,
+                                                  const int32_t *__restrict__ mbase, uint32_t *__restrict__ masks,
                                                   float r2, int32_t n, int32_t *__restrict__ counts) {
     __shared__ float4 tile_all[8][32];
     float4 *tile = tile_all[threadIdx.x >> 5];
@@ -297,32 +318,36 @@ __global__ void __launch_bounds__(256) k_bq_count(const float *__restrict__ xyz,
         const int c = live ? __ldg(cell + k) : -1;
         const bool uni = __all_sync(0xffffffffu, c == __shfl_sync(0xffffffffu, c, 0));
         if (!live && !uni) continue;
+        if (c < 0) continue;                         // a whole warp past the end
         float ox = 0.f, oy = 0.f, oz = 0.f;
         if (live) { ox = __ldg(xyz + 3 * (int64_t)k); oy = __ldg(xyz + 3 * (int64_t)k + 1); oz = __ldg(xyz + 3 * (int64_t)k + 2); }
+        const float4 *cl = cand + __ldg(cand_start + c);
+        const int K = __ldg(kc + c);
+        const int nq = MASK ? __ldg(ccnt + c) : 0;
+        uint32_t *mrow = MASK ? masks + __ldg(mbase + c) + (int)(q - __ldg(cstart + c)) : nullptr;
         int cnt = 0;
         if (uni) {
-            if (c < 0) continue;                     // a whole warp past the end
-            const float4 *cl = cand + __ldg(cand_start + c);
-            const int K = __ldg(kc + c);
             const float4 pad = make_float4(INFINITY, INFINITY, INFINITY, 0.f);   // never within any radius
             float4 nx = lane < K ? __ldg(cl + lane) : pad;
             for (int base = 0; base < K; base += 32) {
                 tile[lane] = nx;
                 __syncwarp();
                 nx = (base + 32 + lane < K) ? __ldg(cl + base + 32 + lane) : pad;
+                unsigned m = 0;
 #pragma unroll
-                for (int u = 0; u < 32; u++) cnt += bq_hit(ox, oy, oz, tile[u], r2);
+                for (int u = 0; u < 32; u++) m |= (unsigned)bq_hit(ox, oy, oz, tile[u], r2) << u;
+                cnt += __popc(m);
+                if (MASK) mrow[(int64_t)(base >> 5) * nq] = m;
                 __syncwarp();
             }
         } else {
-            const float4 *cl = cand + __ldg(cand_start + c);
-            const int K = __ldg(kc + c);
-            int e = 0;
-            for (; e + 4 <= K; e += 4) {
-                const float4 c0 = __ldg(cl + e), c1 = __ldg(cl + e + 1), c2 = __ldg(cl + e + 2), c3 = __ldg(cl + e + 3);
-                cnt += bq_hit(ox, oy, oz, c0, r2) + bq_hit(ox, oy, oz, c1, r2) + bq_hit(ox, oy, oz, c2, r2) + bq_hit(ox, oy, oz, c3, r2);
+            for (int base = 0; base < K; base += 32) {
+                const int lim = min(32, K - base);
+                unsigned m = 0;
+                for (int u = 0; u < lim; u++) m |= (unsigned)bq_hit(ox, oy, oz, __ldg(cl + base + u), r2) << u;
+                cnt += __popc(m);
+                if (MASK) mrow[(int64_t)(base >> 5) * nq] = m;
             }
-            for (; e < K; e++) cnt += bq_hit(ox, oy, oz, __ldg(cl + e), r2);
         }
         if (live) counts[k] = min(cnt, kCap);
     }
@@ -420,6 +445,90 @@ __global__ void __launch_bounds__(256) k_bq_fill(const float *__restrict__ xyz, 
     }
 }
 
+// fill from hit masks: no coordinates, no predicate -- a word of 32 outcomes per (query, block); the
+// lane whose bit is set writes its candidate's index at (hits so far) + (set bits below it).
+__device__ __forceinline__ void bq_fill_mask_one(uint32_t k, const uint32_t *__restrict__ ci, int K,
+                                                 const uint32_t *__restrict__ mrow, int nq,
+                                                 const int2 *__restrict__ start_len, int32_t *__restrict__ idx, int lane,
+                                                 unsigned lt) {
+    const int2 sl = __ldg(start_len + k);
+    int32_t *out = idx + sl.x;
+    int written = 0;
+    for (int base = 0; base < K && written < sl.y; base += 32) {
+        const unsigned m = __ldg(mrow + (int64_t)(base >> 5) * nq);
+        if (m == 0u) continue;
+        const int pos = written + __popc(m & lt);
+        if (((m >> lane) & 1u) && pos < sl.y) out[pos] = (int)__ldg(ci + base + lane);
+        written += __popc(m);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bq_fill_mask(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cell,
+                                                      const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
+                                                      const int32_t *__restrict__ cand_start, const int32_t *__restrict__ kc,
+                                                      const uint32_t *__restrict__ cand_idx, const int32_t *__restrict__ mbase,
+                                                      const uint32_t *__restrict__ masks, const int2 *__restrict__ start_len,
+                                                      int32_t n, int32_t *__restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = lanemask_lt();
+    const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t q0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kFillQ; q0 < n; q0 += nWarps * kFillQ) {
+        const int nqr = (int)((n - q0) < kFillQ ? (n - q0) : kFillQ);
+        uint32_t k[kFillQ];
+        int c[kFillQ];
+        bool same = nqr == kFillQ;
+#pragma unroll
+        for (int u = 0; u < kFillQ; u++) {
+            k[u] = u < nqr ? sorted_pt[q0 + u] : 0u;
+            c[u] = u < nqr ? __ldg(cell + k[u]) : -1;
+            same = same && c[u] == c[0];
+        }
+        if (!same) {
+            for (int u = 0; u < nqr; u++) {
+                const int cc = c[u];
+                bq_fill_mask_one(k[u], cand_idx + __ldg(cand_start + cc), __ldg(kc + cc),
+                                 masks + __ldg(mbase + cc) + (int)(q0 + u - __ldg(cstart + cc)), __ldg(ccnt + cc), start_len,
+                                 idx, lane, lt);
+            }
+            continue;
+        }
+        const int cc = c[0];
+        const uint32_t *ci = cand_idx + __ldg(cand_start + cc);
+        const int K = __ldg(kc + cc);
+        const int nq = __ldg(ccnt + cc);
+        const uint32_t *mrow = masks + __ldg(mbase + cc) + (int)(q0 - __ldg(cstart + cc));   // the 4 queries' words are adjacent
+        int len[kFillQ], written[kFillQ];
+        int32_t *out[kFillQ];
+        int todo = 0;
+#pragma unroll
+        for (int u = 0; u < kFillQ; u++) {
+            const int2 sl = __ldg(start_len + k[u]);
+            len[u] = sl.y; out[u] = idx + sl.x; written[u] = 0;
+            todo += sl.y > 0;
+        }
+        // lanes 0..3 fetch the four mask words of a block, everyone the candidate index; both one block ahead
+        unsigned mw = (lane < kFillQ && K > 0) ? __ldg(mrow + lane) : 0u;
+        uint32_t cnx = lane < K ? __ldg(ci + lane) : 0u;
+        for (int base = 0; base < K && todo > 0; base += 32) {
+            const unsigned mcur = mw;
+            const uint32_t cid = cnx;
+            if (base + 32 < K) {
+                if (lane < kFillQ) mw = __ldg(mrow + (int64_t)((base >> 5) + 1) * nq + lane);
+                cnx = (base + 32 + lane < K) ? __ldg(ci + base + 32 + lane) : 0u;
+            }
+            todo = 0;
+#pragma unroll
+            for (int u = 0; u < kFillQ; u++) {
+                const unsigned m = __shfl_sync(0xffffffffu, mcur, u);
+                const int pos = written[u] + __popc(m & lt);
+                if (((m >> lane) & 1u) && pos < len[u]) out[u][pos] = (int)cid;
+                written[u] += __popc(m);
+                todo += written[u] < len[u];
+            }
+        }
+    }
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -429,20 +538,27 @@ extern "C" size_t pg_ballquery_workspace_bytes(int64_t n) {
     return bq_layout(nullptr, 0, n).used + 256;
 }
 
-extern "C" int pg_ballquery_count(const float *xyz, const int32_t *batch_idxs, const int32_t *batch_offsets, int32_t n,
-                                  int32_t B, float radius, int32_t *start_len, void *ws, size_t ws_bytes,
-                                  int64_t *host_total, void *stream) {
+// ping-pong parity of the radix sort (prepare / count / fill must agree on where sorted_pt landed)
+static const uint32_t *bq_sorted(const BqWs &w, int32_t n) {
+    int bits = 0;
+    while ((1ll << bits) < (long long)n) bits++;
+    const int passes = (bits + 7) / 8 < 1 ? 1 : (bits + 7) / 8;
+    return (passes & 1) ? w.vA : w.vB;
+}
+
+extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs, const int32_t *batch_offsets, int32_t n,
+                                    int32_t B, float radius, void *ws, size_t ws_bytes, int64_t *host_mask_words,
+                                    void *stream) {
     (void)batch_offsets; (void)B;   // scene membership comes from batch_idxs
     cudaStream_t st = (cudaStream_t)stream;
-    PG_CHECK_ARG(host_total, "null host_total");
-    *host_total = 0;
+    PG_CHECK_ARG(host_mask_words, "null host_mask_words");
+    *host_mask_words = 0;
     PG_CHECK_ARG(n >= 0 && n <= (1 << 26), "n out of range (0 .. 2^26)");
     if (n == 0) return PG_OK;
-    PG_CHECK_ARG(xyz && batch_idxs && start_len && ws, "null pointer");
+    PG_CHECK_ARG(xyz && batch_idxs && ws, "null pointer");
     BqWs w = bq_layout(ws, ws_bytes, n);
-    if (!w.ok) { set_error("pg_ballquery_count: workspace too small (%zu < %zu)", ws_bytes, w.used); return PG_EWORKSPACE; }
+    if (!w.ok) { set_error("pg_ballquery_prepare: workspace too small (%zu < %zu)", ws_bytes, w.used); return PG_EWORKSPACE; }
 
-    const float r2 = radius * radius;
     const double s = fabs((double)radius) * 1.0001;
     const double inv_s = (s > 0.0 && isfinite(s)) ? 1.0 / s : 0.0;   // r = 0 / inf / NaN: one cell per scene
     PG_CUDA(cudaMemsetAsync(w.scalars, 0, 8 * sizeof(int64_t), st));
@@ -454,10 +570,7 @@ extern "C" int pg_ballquery_count(const float *xyz, const int32_t *batch_idxs, c
     PG_TRY(radix_sort_pairs(reinterpret_cast<const uint32_t *>(w.cell), nullptr, w.kA, w.vA, w.kB, w.vB, n, bits,
                             w.hist, w.scan_tmp, st, &res));
     const uint32_t *sorted_pt = res == 0 ? w.vA : w.vB;
-    // after the sort both key buffers are free n-sized int arrays
-    uint32_t *spare2 = res == 0 ? w.kA : w.kB;  // merge tile starts
-    const int64_t flag = res;
-    PG_CUDA(cudaMemcpyAsync(w.scalars + 3, &flag, sizeof(int64_t), cudaMemcpyHostToDevice, st));
+    uint32_t *spare2 = res == 0 ? w.kA : w.kB;  // after the sort the key buffers are free: merge tile starts
     PG_CUDA(cudaMemsetAsync(w.ccnt + n, 0, sizeof(int32_t), st));
     PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
     const unsigned gsm = kNumSM * 8;
@@ -467,8 +580,33 @@ extern "C" int pg_ballquery_count(const float *xyz, const int32_t *batch_idxs, c
     k_bq_tiles<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n, (int32_t *)spare2);
     PG_TRY(scan_exclusive_i32((int32_t *)spare2, (int32_t *)spare2, n, w.scalars + 5, w.scan_tmp, st));
     k_bq_merge<<<kNumSM * 8, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, (int32_t *)spare2,
-                                           w.scalars, w.cand);
-    k_bq_count<<<(unsigned)div_up(n, 256), 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cand_start, w.kc, w.cand, r2, n, w.counts);
+                                           w.scalars, w.cand, w.cand_idx);
+    k_bq_mask_sizes<<<gsm, 256, 0, st>>>(w.ccnt, w.kc, w.scalars, n + 1, w.mbase);
+    PG_TRY(scan_exclusive_i32(w.mbase, w.mbase, (int64_t)n + 1, w.scalars + 6, w.scan_tmp, st));
+    PG_LAUNCH_CHECK();
+    int64_t words = 0;
+    PG_CUDA(cudaMemcpyAsync(&words, w.scalars + 6, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaStreamSynchronize(st));
+    *host_mask_words = words >= 0x7fffffffLL ? -1 : words;   // -1: too many for int32 bases, run without masks
+    return PG_OK;
+}
+
+extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int32_t *start_len, uint32_t *masks,
+                                  int64_t mask_words, void *ws, size_t ws_bytes, int64_t *host_total, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PG_CHECK_ARG(host_total, "null host_total");
+    *host_total = 0;
+    PG_CHECK_ARG(n >= 0 && n <= (1 << 26), "n out of range (0 .. 2^26)");
+    if (n == 0) return PG_OK;
+    PG_CHECK_ARG(xyz && start_len && ws, "null pointer");
+    PG_CHECK_ARG(masks == nullptr || mask_words >= 0, "negative mask_words");
+    BqWs w = bq_layout(ws, ws_bytes, n);
+    if (!w.ok) { set_error("pg_ballquery_count: workspace too small (%zu < %zu)", ws_bytes, w.used); return PG_EWORKSPACE; }
+    const uint32_t *sorted_pt = bq_sorted(w, n);
+    const float r2 = radius * radius;
+    const unsigned grid = (unsigned)div_up(n, 256);
+    if (masks) k_bq_count<true><<<grid, 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kc, w.cand, w.mbase, masks, r2, n, w.counts);
+    else k_bq_count<false><<<grid, 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kc, w.cand, w.mbase, nullptr, r2, n, w.counts);
     // starts (reuse pslot) and the interleaved (start, len) rows
     PG_TRY(scan_exclusive_i32(w.counts, w.pslot, n, w.scalars + 2, w.scan_tmp, st));
     k_bq_start_len<<<(unsigned)div_up(n, 256), 256, 0, st>>>(w.counts, w.pslot, n, (int2 *)start_len);
@@ -484,20 +622,22 @@ extern "C" int pg_ballquery_count(const float *xyz, const int32_t *batch_idxs, c
     return PG_OK;
 }
 
-extern "C" int pg_ballquery_fill(const float *xyz, int32_t n, float radius, const int32_t *start_len, int32_t *idx,
-                                 int64_t idx_capacity, void *ws, size_t ws_bytes, void *stream) {
+extern "C" int pg_ballquery_fill(const float *xyz, int32_t n, float radius, const int32_t *start_len,
+                                 const uint32_t *masks, int32_t *idx, int64_t idx_capacity, void *ws, size_t ws_bytes,
+                                 void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     PG_CHECK_ARG(n >= 0 && idx_capacity >= 0, "negative size");
     if (n == 0 || idx_capacity == 0) return PG_OK;
     PG_CHECK_ARG(xyz && start_len && idx && ws, "null pointer");
     BqWs w = bq_layout(ws, ws_bytes, n);
     if (!w.ok) { set_error("pg_ballquery_fill: workspace too small"); return PG_EWORKSPACE; }
-    int bits = 0;
-    while ((1ll << bits) < (long long)n) bits++;
-    const int passes = (bits + 7) / 8 < 1 ? 1 : (bits + 7) / 8;
-    const uint32_t *sorted_pt = (passes & 1) ? w.vA : w.vB;   // same ping-pong parity as the count phase
+    const uint32_t *sorted_pt = bq_sorted(w, n);
     const float r2 = radius * radius;
-    k_bq_fill<<<kNumSM * 8, 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cand_start, w.kc, w.cand, (const int2 *)start_len, r2, n, idx);
+    if (masks)
+        k_bq_fill_mask<<<kNumSM * 8, 256, 0, st>>>(sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kc, w.cand_idx, w.mbase,
+                                                   masks, (const int2 *)start_len, n, idx);
+    else
+        k_bq_fill<<<kNumSM * 8, 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cand_start, w.kc, w.cand, (const int2 *)start_len, r2, n, idx);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

@@ -81,16 +81,22 @@ int pg_point_recover_bp(const float *d_out, float *d_feats, const int32_t *rules
 /* ------------------------------------------------------------------------------------------------
  * ballquery_batch_p     replaces PG_OP.ballquery_batch_p (bfs_cluster.h:15, bfs_cluster.cu:15-90)
  * Per point i: every k of the same scene with fma(dz,dz,fma(dx,dx,dy*dy)) < fl(r*r), ascending k,
- * at most the first PG_BALLQUERY_CAP.  phase 1 writes start_len int32 [n,2] = (start, cnt) with
- * segments laid out in point order (deterministic; the reference's atomicAdd placement is not) and
- * host_total = sum cnt; phase 2 writes idx int32 [total].
+ * at most the first PG_BALLQUERY_CAP.  Three phases over one workspace:
+ *   prepare  builds the uniform grid and the per-cell candidate arrays; host_mask_words = number of
+ *            uint32 words an optional hit-mask buffer needs (-1: too many, run without);
+ *   count    writes start_len int32 [n,2] = (start, cnt), segments laid out in point order
+ *            (deterministic; the reference's atomicAdd placement is not), host_total = sum cnt; when
+ *            `masks` (device, mask_words uint32) is given it also records every predicate outcome;
+ *   fill     writes idx int32 [total]; with `masks` it only turns recorded bits into indices, without
+ *            it the predicates are evaluated again.  Pass the same masks pointer (or NULL) to both.
  * ---------------------------------------------------------------------------------------------- */
 size_t pg_ballquery_workspace_bytes(int64_t n);
-int pg_ballquery_count(const float *xyz, const int32_t *batch_idxs, const int32_t *batch_offsets,
-                       int32_t n, int32_t B, float radius, int32_t *start_len, void *ws, size_t ws_bytes,
-                       int64_t *host_total, void *stream);
-int pg_ballquery_fill(const float *xyz, int32_t n, float radius, const int32_t *start_len, int32_t *idx,
-                      int64_t idx_capacity, void *ws, size_t ws_bytes, void *stream);
+int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs, const int32_t *batch_offsets, int32_t n,
+                         int32_t B, float radius, void *ws, size_t ws_bytes, int64_t *host_mask_words, void *stream);
+int pg_ballquery_count(const float *xyz, int32_t n, float radius, int32_t *start_len, uint32_t *masks,
+                       int64_t mask_words, void *ws, size_t ws_bytes, int64_t *host_total, void *stream);
+int pg_ballquery_fill(const float *xyz, int32_t n, float radius, const int32_t *start_len, const uint32_t *masks,
+                      int32_t *idx, int64_t idx_capacity, void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * bfs_cluster     replaces PG_OP.bfs_cluster (bfs_cluster.h:18, bfs_cluster.cpp:28-112)

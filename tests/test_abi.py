@@ -25,7 +25,7 @@ def lib():
 def test_every_declared_symbol_is_exported_and_bound(lib):
     from d3net_b200 import _native
     names = _declared()
-    assert len(names) == 23
+    assert len(names) == 24
     for n in names:
         assert hasattr(lib, n), "libpg_b200.so does not export " + n
         assert n in _native.SIGNATURES, "no ctypes signature for " + n
@@ -56,9 +56,11 @@ def test_argument_validation_without_a_gpu(lib):
     assert lib.pg_voxelize_idx_map(None, 0, 9, None, None, 0, sizes, None) == -1           # bad mode
     assert b"mode" in lib.pg_last_error()
     assert lib.pg_voxelize_idx_map(None, 5, 4, None, None, 0, sizes, None) == -1           # null pointers
-    assert lib.pg_ballquery_count(None, None, None, 0, 1, 0.03, None, None, 0, ctypes.byref(total), None) == 0
+    assert lib.pg_ballquery_prepare(None, None, None, 0, 1, 0.03, None, 0, ctypes.byref(total), None) == 0
     assert total.value == 0
-    assert lib.pg_ballquery_count(None, None, None, -1, 1, 0.03, None, None, 0, ctypes.byref(total), None) == -1
+    assert lib.pg_ballquery_prepare(None, None, None, -1, 1, 0.03, None, 0, ctypes.byref(total), None) == -1
+    assert lib.pg_ballquery_count(None, 0, 0.03, None, None, 0, None, 0, ctypes.byref(total), None) == 0
+    assert lib.pg_ballquery_fill(None, 0, 0.03, None, None, None, 0, None, 0, None) == 0
     assert lib.pg_bfs_cluster_count(None, None, None, 0, 0, 50, 0, None, 0, sizes, None) == 0
     assert lib.pg_voxelize_fp(None, None, None, 0, 1, 16, 1, None) == 0
     assert lib.pg_voxelize_fp(None, None, None, 5, 1, 16, 1, None) == -1

@@ -435,3 +435,19 @@ def test_gather_rows(ops):
             np.testing.assert_array_equal(npy(out), src[idx])
             out.sum().backward()
             np.testing.assert_array_equal(npy(s.grad)[:, 0], np.bincount(idx, minlength=5000).astype(np.float32))
+
+
+def test_ballquery_mask_and_recompute_paths_agree(ops):
+    """The fill phase either decodes hit masks recorded by the count phase or re-evaluates the predicates;
+    both must give the same lists (the oracle comparison above runs the mask path)."""
+    from d3net_b200 import PG_OP
+    s = object_subset(small_batch(2, 15000))
+    xyz, bi, bo = cu(s["shifted"]), cu(s["batch_idxs"]), cu(s["batch_offsets"])
+    res = []
+    for use_masks in (True, False):
+        sl, total, state = PG_OP.ballquery_count_impl(xyz, bi, bo, 0.03, use_masks=use_masks)
+        assert (state[1] is not None) == use_masks
+        idx = torch.empty(total, dtype=torch.int32, device="cuda")
+        PG_OP.ballquery_fill_impl(xyz, 0.03, sl, idx, state)
+        res.append((sl, idx))
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
