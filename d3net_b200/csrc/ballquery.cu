@@ -412,35 +412,31 @@ __global__ void __launch_bounds__(256) k_bq_fill(const float *__restrict__ xyz, 
                 bq_fill_one(xyz, k[u], cand + __ldg(cand_start + c[u]), __ldg(kc + c[u]), start_len, r2, idx, lane, lt);
             continue;
         }
-        const float4 *cl = cand + __ldg(cand_start + c[0]);
         const int K = __ldg(kc + c[0]);
+        const float4 *cp = cand + __ldg(cand_start + c[0]) + lane;
         float ox[kFillQ], oy[kFillQ], oz[kFillQ];
-        int len[kFillQ], written[kFillQ];
-        int32_t *out[kFillQ];
-        int todo = 0;
+        int wpos[kFillQ], wend[kFillQ];
 #pragma unroll
         for (int u = 0; u < kFillQ; u++) {
             const int2 sl = __ldg(start_len + k[u]);
             ox[u] = __ldg(xyz + 3 * (int64_t)k[u]); oy[u] = __ldg(xyz + 3 * (int64_t)k[u] + 1); oz[u] = __ldg(xyz + 3 * (int64_t)k[u] + 2);
-            len[u] = sl.y; out[u] = idx + sl.x; written[u] = 0;
-            todo += sl.y > 0;
+            wpos[u] = sl.x; wend[u] = sl.x + sl.y;
         }
-        float4 nx = lane < K ? __ldg(cl + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int base = 0; base < K && todo > 0; base += 32) {
-            const int e = base + lane;
-            const bool in = e < K;
+        const float4 pad = make_float4(INFINITY, INFINITY, INFINITY, 0.f);   // never within any radius
+        float4 nx = lane < K ? __ldg(cp) : pad;
+        for (int base = 0; base < K; base += 32) {
             const float4 cd = nx;
-            nx = (e + 32 < K) ? __ldg(cl + e + 32) : make_float4(0.f, 0.f, 0.f, 0.f);   // next tile in flight
-            todo = 0;
+            cp += 32;
+            nx = (base + 32 + lane < K) ? __ldg(cp) : pad;                   // next tile in flight
 #pragma unroll
             for (int u = 0; u < kFillQ; u++) {
-                const bool hit = in && bq_hit(ox[u], oy[u], oz[u], cd, r2);
+                const bool hit = bq_hit(ox[u], oy[u], oz[u], cd, r2);
                 const unsigned m = __ballot_sync(0xffffffffu, hit);
-                const int pos = written[u] + __popc(m & lt);
-                if (hit && pos < len[u]) out[u][pos] = __float_as_int(cd.w);
-                written[u] += __popc(m);
-                todo += written[u] < len[u];
+                const int pos = wpos[u] + __popc(m & lt);
+                if (hit && pos < wend[u]) idx[pos] = __float_as_int(cd.w);
+                wpos[u] += __popc(m);
             }
+            if (wpos[0] >= wend[0] && wpos[1] >= wend[1] && wpos[2] >= wend[2] && wpos[3] >= wend[3]) break;
         }
     }
 }
@@ -493,38 +489,38 @@ __global__ void __launch_bounds__(256) k_bq_fill_mask(const uint32_t *__restrict
             continue;
         }
         const int cc = c[0];
-        const uint32_t *ci = cand_idx + __ldg(cand_start + cc);
         const int K = __ldg(kc + cc);
         const int nq = __ldg(ccnt + cc);
-        const uint32_t *mrow = masks + __ldg(mbase + cc) + (int)(q0 - __ldg(cstart + cc));   // the 4 queries' words are adjacent
-        int len[kFillQ], written[kFillQ];
-        int32_t *out[kFillQ];
-        int todo = 0;
+        // running pointers, 32-bit output positions: the loop body is ~10 instructions per (query, block)
+        const uint32_t *cp = cand_idx + __ldg(cand_start + cc) + lane;
+        int wpos[kFillQ], wend[kFillQ];
 #pragma unroll
         for (int u = 0; u < kFillQ; u++) {
             const int2 sl = __ldg(start_len + k[u]);
-            len[u] = sl.y; out[u] = idx + sl.x; written[u] = 0;
-            todo += sl.y > 0;
+            wpos[u] = sl.x; wend[u] = sl.x + sl.y;
         }
-        // lanes 0..3 fetch the four mask words of a block, everyone the candidate index; both one block ahead
-        unsigned mw = (lane < kFillQ && K > 0) ? __ldg(mrow + lane) : 0u;
-        uint32_t cnx = lane < K ? __ldg(ci + lane) : 0u;
-        for (int base = 0; base < K && todo > 0; base += 32) {
-            const unsigned mcur = mw;
-            const uint32_t cid = cnx;
-            if (base + 32 < K) {
-                if (lane < kFillQ) mw = __ldg(mrow + (int64_t)((base >> 5) + 1) * nq + lane);
-                cnx = (base + 32 + lane < K) ? __ldg(ci + base + 32 + lane) : 0u;
-            }
-            todo = 0;
+        // Eight blocks per trip: ONE load brings the 8 x 4 mask words (lane = block * 4 + query) and eight
+        // independent loads the 256 candidate indices, so nine loads per lane are in flight together
+        // and their latency is paid once per eight blocks.
+        const int nb = (K + 31) >> 5;
+        const uint32_t *mp8 = masks + __ldg(mbase + cc) + (int)(q0 - __ldg(cstart + cc)) + (int64_t)(lane >> 2) * nq + (lane & 3);
+        bool done = false;
+        for (int b0 = 0; b0 < nb && !done; b0 += 8) {
+            const unsigned mw = (b0 + (lane >> 2) < nb) ? __ldg(mp8 + (int64_t)b0 * nq) : 0u;
+            int cidr[8];
 #pragma unroll
-            for (int u = 0; u < kFillQ; u++) {
-                const unsigned m = __shfl_sync(0xffffffffu, mcur, u);
-                const int pos = written[u] + __popc(m & lt);
-                if (((m >> lane) & 1u) && pos < len[u]) out[u][pos] = (int)cid;
-                written[u] += __popc(m);
-                todo += written[u] < len[u];
+            for (int j = 0; j < 8; j++) cidr[j] = ((b0 + j) * 32 + lane < K) ? (int)__ldg(cp + (b0 + j) * 32) : 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+#pragma unroll
+                for (int u = 0; u < kFillQ; u++) {
+                    const unsigned m = __shfl_sync(0xffffffffu, mw, j * 4 + u);
+                    const int pos = wpos[u] + __popc(m & lt);
+                    if (((m >> lane) & 1u) && pos < wend[u]) idx[pos] = cidr[j];
+                    wpos[u] += __popc(m);
+                }
             }
+            done = wpos[0] >= wend[0] && wpos[1] >= wend[1] && wpos[2] >= wend[2] && wpos[3] >= wend[3];
         }
     }
 }
