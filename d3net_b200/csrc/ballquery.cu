@@ -2,20 +2,26 @@
 // "first 1000 neighbours by ascending index" rule.  Reference behaviour:
 // lib/pointgroup_ops/src/bfs_cluster/bfs_cluster.cu:15-90 (brute-force scan of the whole scene).
 //
-// Pipeline (all on `stream`, no host round trip until the total is read):
-//   1. cell key per point: (scene, floor(x/s), floor(y/s), floor(z/s)), s = 1.0001 * |r| in fp64, so
-//      every pair that can pass the predicate sits in adjacent cells;
-//   2. hash-group the keys -> dense cell ids, stable radix sort of (cell, point) -> every cell's
-//      point list in ASCENDING original index;
-//   3. per cell: the ids of its 27 neighbour cells (hash lookups) and the size of its candidate set;
-//   4. merge: every cell gets ONE candidate array -- the union of its 27 neighbour lists, in
-//      ascending original index, as float4 (x, y, z, index) -- built by rank-merging (a point's slot
-//      is the sum of its lower-bound ranks in the 27 sorted lists);
-//   5. count: a warp takes up to 32 query points of one cell (lane = query), streams the cell's
-//      candidate array (warp-uniform 16-byte loads) and counts hits, capped at 1000;
-//   6. exclusive scan of the counts -> start_len, total;
-//   7. fill: a warp per query streams the same candidate array lane-per-candidate (coalesced 512-byte
-//      loads), ballots the hits and writes them compacted -- ascending by construction -- until 1000.
+// Pipeline (all on `stream`; the host only reads two sizes):
+//   prepare
+//     1. cell key per point: (scene, floor(x/s), floor(y/s), floor(z/s)), s = 1.0001 * |r| in fp64, so
+//        every pair that can pass the predicate sits in adjacent cells;
+//     2. hash-group the keys -> dense cell ids; stable radix sort of (cell, point) -> every cell's
+//        point list in ASCENDING original index; the sorted order is also the QUERY order;
+//     3. per cell: its 27 neighbour cells (hash lookups), K = size of its candidate set, and the
+//        cell's class: K <= kSmallK "sparse" (one warp), otherwise "dense" (one block);
+//   count -- one pass over the cells, each cell builds its candidate set ONCE, merged in ascending
+//     original index, and tests all of its queries against it:
+//       sparse cell: the <= 128 candidate indices are sorted in registers (warp bitonic network);
+//       dense cell:  rank-select through a shared-memory bitmap over the index range (set one bit per
+//                    candidate, prefix-count the words, walk the bits in order), 1024 candidates at a
+//                    time into a shared-memory tile of (x, y, z); queries are lanes, candidates are
+//                    LDS.128 broadcasts; tiles stop as soon as every query of the cell holds 1000 hits;
+//     every predicate outcome is recorded as one bit (32 candidates per word) and the sorted candidate
+//     indices are kept (4 bytes each), so
+//   fill turns bits into indices without touching a coordinate.
+//   Segments of `idx` are laid out in query (= cell) order: deterministic, and neighbouring points own
+//   neighbouring segments, which is what makes the consumer (bfs_cluster) cache-friendly.
 #include <math.h>
 
 #include "common.cuh"
@@ -23,17 +29,24 @@
 namespace pg {
 
 constexpr int kCap = PG_BALLQUERY_CAP;
+constexpr int kSmallK = 128;             // sparse/dense class boundary (candidates per cell)
+constexpr int kTile = 1024;              // candidates per shared-memory tile (dense cells)
+constexpr int kWinBits = 1 << 18;        // index window covered by the rank bitmap
+constexpr int kWinWords = kWinBits / 32;
+constexpr int kQMax = 1024;              // queries of one dense cell handled per pass
+constexpr int kDenseThreads = 256;
+constexpr int kChunkBlocks = 4;          // 32-candidate blocks per (query group, chunk) work item
 
 struct BqWs {
     int4 *keys;
     GroupTable tab;
-    int32_t *pslot, *cell, *ccnt, *cstart, *kc, *cand_start, *counts, *nbr, *mbase;
+    int32_t *pslot, *cell, *ccnt, *cstart, *kc, *kb, *cand_start, *counts, *nbr, *mbase, *dense;
     uint32_t *cand_idx;
     uint32_t *kA, *vA, *kB, *vB;
     int32_t *hist;
     int64_t *scan_tmp;
-    int64_t *scalars;   // [0] nCells [1] total candidates [2] total neighbours [5] merge tiles [6] mask words
-    float4 *cand;
+    // [0] nCells [1] total candidates [2] total neighbours [3] nDense [4] dense work counter [6] mask words
+    int64_t *scalars;
     bool ok;
     size_t used;
 };
@@ -51,9 +64,11 @@ static BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
     w.ccnt = a.take<int32_t>(n + 1);
     w.cstart = a.take<int32_t>(n + 1);
     w.kc = a.take<int32_t>(n + 1);
+    w.kb = a.take<int32_t>(n + 1);
     w.cand_start = a.take<int32_t>(n + 1);
     w.counts = a.take<int32_t>(n + 1);
     w.nbr = a.take<int32_t>(n * 27);
+    w.dense = a.take<int32_t>(n);
     w.kA = a.take<uint32_t>(n);
     w.vA = a.take<uint32_t>(n);
     w.kB = a.take<uint32_t>(n);
@@ -61,7 +76,6 @@ static BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
     w.hist = a.take<int32_t>(radix_tmp_count(n_));
     w.scan_tmp = a.take<int64_t>(scan_tmp_count((int64_t)(n + radix_tmp_count(n_))));
     w.scalars = a.take<int64_t>(8);
-    w.cand = a.take<float4>(n * 27);
     w.cand_idx = a.take<uint32_t>(n * 27);
     w.mbase = a.take<int32_t>(n + 1);
     w.ok = a.ok;
@@ -88,13 +102,13 @@ __global__ void k_bq_keys(const float *__restrict__ xyz, const int32_t *__restri
 }
 
 // one warp per cell: lane j < 27 looks up neighbour j (-1 when absent; slot 13 is the cell itself),
-// the warp sums the candidate count
+// the warp sums the candidate count and files dense cells in the (unordered) dense list
 __global__ void __launch_bounds__(256) k_bq_neighbours(const int4 *__restrict__ keys, GroupTable tab,
                                                        const uint32_t *__restrict__ sorted_pt,
                                                        const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
-                                                       const int64_t *__restrict__ nCells, int32_t *__restrict__ nbr,
-                                                       int32_t *__restrict__ kc) {
-    const int64_t nc = *nCells;
+                                                       int64_t *scalars, int32_t *__restrict__ nbr,
+                                                       int32_t *__restrict__ kc, int32_t *__restrict__ dense) {
+    const int64_t nc = scalars[0];
     const int lane = threadIdx.x & 31;
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nc; c += nWarps) {
@@ -115,7 +129,10 @@ __global__ void __launch_bounds__(256) k_bq_neighbours(const int4 *__restrict__ 
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        if (lane == 0) kc[c] = cnt;
+        if (lane == 0) {
+            kc[c] = cnt;
+            if (cnt > kSmallK) dense[atomicAdd((unsigned long long *)&scalars[3], 1ULL)] = (int32_t)c;
+        }
     }
 }
 
@@ -126,149 +143,6 @@ __device__ __forceinline__ int lower_bound_u32(const uint32_t *__restrict__ a, i
         if (a[mid] < v) lo = mid + 1; else hi = mid;
     }
     return lo;
-}
-
-// ---- merge: one candidate array per cell = its <= 27 neighbour lists merged by ascending index ----
-// A work item is (cell, tile): cells with <= 32 candidates are one tile; larger cells are cut into
-// ~24-element tiles by splitting the cell's index range evenly (point indices are a random shuffle
-// with respect to space, so even splits balance).  For a tile [a, b) lane l binary-searches both
-// bounds in neighbour list l: the sum of the lower bounds over the lists IS the tile's offset in the
-// merged array, so tiles need no scan between them.  The <= 32 keys of a tile are gathered through
-// shared memory, sorted with a warp bitonic network and written out with their coordinates.  A tile
-// that turns out larger than 32 is halved on a small stack.
-constexpr int kMergeTile = 24;
-
-__global__ void k_bq_tiles(const int32_t *__restrict__ kc, const int64_t *__restrict__ nCells, int32_t n,
-                           int32_t *__restrict__ tiles) {
-    const int64_t nc = *nCells;
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (int64_t)gridDim.x * blockDim.x) {
-        const int K = c < nc ? kc[c] : 0;
-        tiles[c] = K <= 32 ? (K > 0) : (K + kMergeTile - 1) / kMergeTile;
-    }
-}
-
-__device__ __forceinline__ uint32_t warp_bitonic_sort(uint32_t key, int lane) {
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const uint32_t other = __shfl_xor_sync(0xffffffffu, key, j);
-            const bool up = ((lane & k) == 0);          // ascending block
-            const bool lower = ((lane & j) == 0);       // this lane keeps the smaller of the pair
-            const uint32_t mn = min(key, other), mx = max(key, other);
-            key = (up == lower) ? mn : mx;
-        }
-    }
-    return key;
-}
-
-__global__ void __launch_bounds__(256) k_bq_merge(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
-                                                  const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
-                                                  const int32_t *__restrict__ nbr, const int32_t *__restrict__ kc,
-                                                  const int32_t *__restrict__ cand_start,
-                                                  const int32_t *__restrict__ tile_start, const int64_t *__restrict__ scalars,
-                                                  float4 *__restrict__ cand, uint32_t *__restrict__ cand_idx) {
-    __shared__ uint32_t scratch_all[8][32];
-    uint32_t *scratch = scratch_all[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const unsigned lt = lanemask_lt();
-    const int64_t nCells = scalars[0], nItems = scalars[5];
-    // every warp takes a contiguous run of work items: one binary search for the first cell, then it
-    // walks forward (every cell has at least one tile, so the walk never skips)
-    const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int64_t per = (nItems + nWarps - 1) / nWarps;
-    const int64_t w0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * per;
-    const int64_t w1 = w0 + per < nItems ? w0 + per : nItems;
-    int c = 0, t = 0;
-    if (w0 < w1) {
-        int64_t lo_c = 0, hi_c = nCells;
-        while (hi_c - lo_c > 1) {
-            const int64_t mid = (lo_c + hi_c) >> 1;
-            if (__ldg(tile_start + mid) <= w0) lo_c = mid; else hi_c = mid;
-        }
-        c = (int)lo_c;
-        t = (int)(w0 - __ldg(tile_start + c));
-    }
-    for (int64_t w = w0; w < w1; w++, t++) {
-        int K = __ldg(kc + c);
-        int T = K <= 32 ? 1 : (K + kMergeTile - 1) / kMergeTile;
-        if (t >= T) {
-            ++c; t = 0;
-            K = __ldg(kc + c);
-            T = K <= 32 ? 1 : (K + kMergeTile - 1) / kMergeTile;
-        }
-        // lane l < 27 owns neighbour list l
-        int len = 0;
-        const uint32_t *L = sorted_pt;
-        if (lane < 27) {
-            const int src = __ldg(nbr + (int64_t)c * 27 + lane);
-            if (src >= 0) { len = __ldg(ccnt + src); L = sorted_pt + __ldg(cstart + src); }
-        }
-        const int cbase = __ldg(cand_start + c);
-        float4 *dst = cand + cbase;
-        uint32_t *dst_idx = cand_idx + cbase;
-        uint32_t sa[30], sb[30];      // interval stack (warp-uniform)
-        int sp = 0;
-        if (T == 1) {
-            sa[0] = 0u; sb[0] = 0xffffffffu; sp = 1;
-        } else {
-            uint32_t head = len ? L[0] : 0xffffffffu, tail = len ? L[len - 1] : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                head = min(head, __shfl_xor_sync(0xffffffffu, head, o));
-                tail = max(tail, __shfl_xor_sync(0xffffffffu, tail, o));
-            }
-            const uint32_t span = tail - head + 1u;
-            const uint32_t width = (span + (uint32_t)T - 1u) / (uint32_t)T;
-            const uint64_t a64 = (uint64_t)head + (uint64_t)t * width;
-            if (a64 <= tail) {
-                const uint64_t b64 = a64 + width;
-                sa[0] = (uint32_t)a64;
-                sb[0] = b64 > (uint64_t)tail ? tail + 1u : (uint32_t)b64;      // indices < 2^26: no overflow
-                sp = 1;
-            }
-        }
-        while (sp > 0) {
-            --sp;
-            const uint32_t a = sa[sp], b = sb[sp];
-            int lbA = 0, lbB = len;
-            if (a != 0u) lbA = lower_bound_u32(L, len, a);
-            if (b != 0xffffffffu) lbB = lower_bound_u32(L, len, b);
-            const int cnt = lbB - lbA;
-            int s = cnt, off = lbA;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                s += __shfl_xor_sync(0xffffffffu, s, o);
-                off += __shfl_xor_sync(0xffffffffu, off, o);
-            }
-            if (s == 0) continue;
-            if (s > 32) {     // uneven tile: halve its index interval (indices are unique, so this ends)
-                const uint32_t mid = a + ((b - a) >> 1);
-                sa[sp] = mid; sb[sp] = b; ++sp;
-                sa[sp] = a; sb[sp] = mid; ++sp;
-                continue;
-            }
-            // exclusive prefix of cnt over lanes -> slot of each list's run inside the tile
-            int pre = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, pre, o);
-                if (lane >= o) pre += v;
-            }
-            pre -= cnt;
-            for (int i = 0; i < cnt; i++) scratch[pre + i] = L[lbA + i];
-            __syncwarp();
-            uint32_t key = lane < s ? scratch[lane] : 0xffffffffu;
-            __syncwarp();
-            key = warp_bitonic_sort(key, lane);
-            if (lane < s) {
-                const float *p = xyz + 3 * (int64_t)key;
-                dst[off + lane] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __int_as_float((int)key));
-                dst_idx[off + lane] = key;
-            }
-        }
-        (void)lt;
-    }
 }
 
 // bfs_cluster.cu:36 as nvcc compiles it (-fmad=true): d2 = fma(dz, dz, fma(dx, dx, dy * dy)), with
@@ -284,9 +158,8 @@ __global__ void k_bq_clear_tail(int32_t *kc, const int64_t *__restrict__ nCells,
     for (int64_t c = nc + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n1; c += (int64_t)gridDim.x * blockDim.x) kc[c] = 0;
 }
 
-// Hit masks: the count pass already evaluates every (query, candidate) predicate, so it records the
-// outcome -- one bit per pair, 32 candidates per word, laid out per cell as [block of 32 candidates]
-// [query of the cell] -- and the fill pass turns bits into indices without touching a coordinate.
+// Hit masks: one bit per (query, candidate) pair, 32 candidates per word, laid out per cell as
+// [block of 32 candidates][query of the cell].
 __global__ void k_bq_mask_sizes(const int32_t *__restrict__ ccnt, const int32_t *__restrict__ kc,
                                 const int64_t *__restrict__ nCells, int32_t n1, int32_t *__restrict__ words) {
     const int64_t nc = *nCells;
@@ -296,147 +169,371 @@ __global__ void k_bq_mask_sizes(const int32_t *__restrict__ ccnt, const int32_t 
     }
 }
 
-// count: one thread per query, taken in cell-sorted order.  When all 32 lanes of a warp sit in the
-// same cell (every dense cell), the warp stages the cell's candidate array through shared memory 32
-// records at a time -- one coalesced 512-byte load, prefetched one tile ahead -- and every lane reads
-// the records back as LDS.128 broadcasts: the loop runs at shared-memory latency instead of waiting
-// on a 16-byte global load per candidate.  Mixed warps (sparse regions) walk their own short lists.
-template <bool MASK>
-__global__ void __launch_bounds__(256) k_bq_count(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
-                                                  const int32_t *__restrict__ cell, const int32_t *__restrict__ cstart,
-                                                  const int32_t *__restrict__ ccnt, const int32_t *__restrict__ cand_start,
-                                                  const int32_t *__restrict__ kc, const float4 *__restrict__ cand,
-                                                  const int32_t *__restrict__ mbase, uint32_t *__restrict__ masks,
-                                                  float r2, int32_t n, int32_t *__restrict__ counts) {
-    __shared__ float4 tile_all[8][32];
-    float4 *tile = tile_all[threadIdx.x >> 5];
-    const int lane = threadIdx.x & 31;
-    const int64_t n_up = ((int64_t)n + 31) / 32 * 32;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_up; q += (int64_t)gridDim.x * blockDim.x) {
-        const bool live = q < n;
-        const uint32_t k = live ? sorted_pt[q] : 0u;
-        const int c = live ? __ldg(cell + k) : -1;
-        const bool uni = __all_sync(0xffffffffu, c == __shfl_sync(0xffffffffu, c, 0));
-        if (!live && !uni) continue;
-        if (c < 0) continue;                         // a whole warp past the end
-        float ox = 0.f, oy = 0.f, oz = 0.f;
-        if (live) { ox = __ldg(xyz + 3 * (int64_t)k); oy = __ldg(xyz + 3 * (int64_t)k + 1); oz = __ldg(xyz + 3 * (int64_t)k + 2); }
-        const float4 *cl = cand + __ldg(cand_start + c);
-        const int K = __ldg(kc + c);
-        const int nq = MASK ? __ldg(ccnt + c) : 0;
-        uint32_t *mrow = MASK ? masks + __ldg(mbase + c) + (int)(q - __ldg(cstart + c)) : nullptr;
-        int cnt = 0;
-        if (uni) {
-            const float4 pad = make_float4(INFINITY, INFINITY, INFINITY, 0.f);   // never within any radius
-            float4 nx = lane < K ? __ldg(cl + lane) : pad;
-            for (int base = 0; base < K; base += 32) {
-                tile[lane] = nx;
-                __syncwarp();
-                nx = (base + 32 + lane < K) ? __ldg(cl + base + 32 + lane) : pad;
-                unsigned m = 0;
+// ---- sparse cells: one warp per cell, candidates sorted in registers ------------------------------
+// Striped layout: register r of lane l holds position r * 32 + l, so after the sort register r IS
+// 32-candidate block r and a ballot over it IS the mask word.
+template <int KP>
+__device__ __forceinline__ void warp_sort_striped(uint32_t (&key)[KP], int lane) {
+    constexpr int N = 32 * KP;
 #pragma unroll
-                for (int u = 0; u < 32; u++) m |= (unsigned)bq_hit(ox, oy, oz, tile[u], r2) << u;
-                cnt += __popc(m);
-                if (MASK) mrow[(int64_t)(base >> 5) * nq] = m;
-                __syncwarp();
-            }
-        } else {
-            for (int base = 0; base < K; base += 32) {
-                const int lim = min(32, K - base);
-                unsigned m = 0;
-                for (int u = 0; u < lim; u++) m |= (unsigned)bq_hit(ox, oy, oz, __ldg(cl + base + u), r2) << u;
-                cnt += __popc(m);
-                if (MASK) mrow[(int64_t)(base >> 5) * nq] = m;
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            if (j >= 32) {
+                const int jr = j >> 5;
+#pragma unroll
+                for (int r = 0; r < KP; r++) {
+                    if ((r & jr) == 0) {
+                        const int r2 = r | jr;
+                        const bool up = (((r << 5) | lane) & k) == 0;
+                        const uint32_t a = key[r], b = key[r2];
+                        const uint32_t mn = min(a, b), mx = max(a, b);
+                        key[r] = up ? mn : mx;
+                        key[r2] = up ? mx : mn;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < KP; r++) {
+                    const uint32_t other = __shfl_xor_sync(0xffffffffu, key[r], j);
+                    const bool up = (((r << 5) | lane) & k) == 0;
+                    const bool lower = (lane & j) == 0;
+                    const uint32_t mn = min(key[r], other), mx = max(key[r], other);
+                    key[r] = (up == lower) ? mn : mx;
+                }
             }
         }
-        if (live) counts[k] = min(cnt, kCap);
     }
 }
 
-__global__ void k_bq_start_len(const int32_t *__restrict__ counts, const int32_t *__restrict__ starts, int32_t n,
-                               int2 *__restrict__ start_len) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) start_len[i] = make_int2(starts[i], counts[i]);
+template <int KP>
+__device__ __forceinline__ void bq_small_cell(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
+                                              const uint32_t *scratch, int K, int nq, int qs, int cbase, int mb,
+                                              uint32_t *__restrict__ masks, uint32_t *__restrict__ cand_idx,
+                                              int32_t *__restrict__ counts, float r2, int lane) {
+    uint32_t key[KP];
+    float cx[KP], cy[KP], cz[KP];
+#pragma unroll
+    for (int r = 0; r < KP; r++) key[r] = (r * 32 + lane < K) ? scratch[r * 32 + lane] : 0xffffffffu;
+    warp_sort_striped<KP>(key, lane);
+#pragma unroll
+    for (int r = 0; r < KP; r++) {
+        const bool valid = r * 32 + lane < K;
+        cx[r] = cy[r] = cz[r] = INFINITY;                        // padding never passes the predicate
+        if (valid) {
+            const float *p = xyz + 3 * (int64_t)key[r];
+            cx[r] = __ldg(p); cy[r] = __ldg(p + 1); cz[r] = __ldg(p + 2);
+            cand_idx[cbase + r * 32 + lane] = key[r];
+        }
+    }
+    const int nblk = (K + 31) >> 5;
+    for (int qi = 0; qi < nq; qi++) {
+        const uint32_t k = __ldg(sorted_pt + qs + qi);            // warp-uniform
+        const float ox = __ldg(xyz + 3 * (int64_t)k), oy = __ldg(xyz + 3 * (int64_t)k + 1), oz = __ldg(xyz + 3 * (int64_t)k + 2);
+        int cnt = 0;
+        unsigned mine = 0;
+#pragma unroll
+        for (int r = 0; r < KP; r++) {
+            const unsigned m = __ballot_sync(0xffffffffu, bq_hit(ox, oy, oz, make_float4(cx[r], cy[r], cz[r], 0.f), r2));
+            cnt += __popc(m);
+            if (lane == r) mine = m;
+        }
+        if (masks && lane < nblk) masks[mb + lane * nq + qi] = mine;
+        if (lane == 0) counts[qs + qi] = cnt;                     // <= kSmallK < kCap
+    }
 }
 
-// fill: a warp streams a cell's candidate array lane-per-candidate (coalesced 512-byte loads), ballots
-// the hits and writes them compacted -- ascending by construction -- until the query's count is
-// reached.  Four queries that share a cell (the common case wherever it matters: dense cells hold
-// hundreds of queries) ride on the same candidate loads.
+__global__ void __launch_bounds__(256) k_bq_cells_small(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
+                                                        const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
+                                                        const int32_t *__restrict__ nbr, const int32_t *__restrict__ kc,
+                                                        const int32_t *__restrict__ cand_start,
+                                                        const int32_t *__restrict__ mbase, const int64_t *__restrict__ scalars,
+                                                        uint32_t *__restrict__ masks, float r2,
+                                                        uint32_t *__restrict__ cand_idx, int32_t *__restrict__ counts,
+                                                        int32_t *__restrict__ kb) {
+    __shared__ uint32_t scratch_all[8][kSmallK];
+    uint32_t *scratch = scratch_all[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int64_t nCells = scalars[0];
+    const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nCells; c += nWarps) {
+        const int K = __ldg(kc + c);
+        if (K > kSmallK) continue;                                // a dense cell: the block kernel's
+        // lane j < 27 owns neighbour list j and copies it to its slot of the scratch row
+        int len = 0;
+        const uint32_t *L = sorted_pt;
+        if (lane < 27) {
+            const int src = __ldg(nbr + c * 27 + lane);
+            if (src >= 0) { len = __ldg(ccnt + src); L = sorted_pt + __ldg(cstart + src); }
+        }
+        int pre = len;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, pre, o);
+            if (lane >= o) pre += v;
+        }
+        pre -= len;
+        for (int i = 0; i < len; i++) scratch[pre + i] = __ldg(L + i);
+        __syncwarp();
+        const int nq = __ldg(ccnt + c), qs = __ldg(cstart + c), cbase = __ldg(cand_start + c);
+        const int mb = masks ? __ldg(mbase + c) : 0;
+        if (K <= 32) bq_small_cell<1>(xyz, sorted_pt, scratch, K, nq, qs, cbase, mb, masks, cand_idx, counts, r2, lane);
+        else if (K <= 64) bq_small_cell<2>(xyz, sorted_pt, scratch, K, nq, qs, cbase, mb, masks, cand_idx, counts, r2, lane);
+        else bq_small_cell<4>(xyz, sorted_pt, scratch, K, nq, qs, cbase, mb, masks, cand_idx, counts, r2, lane);
+        if (lane == 0) kb[c] = K;
+        __syncwarp();
+    }
+}
+
+// ---- dense cells: one block per cell ----------------------------------------------------------------
+struct DenseSmem {
+    uint32_t bm[kWinWords];          // rank bitmap over the index window [s0, s0 + kWinBits)
+    float4 tile[kTile];              // candidates of the current tile, ascending index (w unused)
+    float qx[kQMax], qy[kQMax], qz[kQMax];
+    int32_t qcnt[kQMax];             // hits so far per query
+    uint8_t qsat[kQMax];             // snapshot at the last tile boundary: the query already holds kCap hits
+    const uint32_t *lptr[27];
+    int32_t llen[27], la[27], lb[27];
+    int32_t wsum[kDenseThreads / 32];
+    uint32_t lo, hi, s0;
+    int32_t tw, cellslot;
+};
+
+// exclusive scan of one int per thread over the block; *total = block sum
+__device__ __forceinline__ int dense_block_exscan(int v, int32_t *wsum, int32_t *total_slot, int *total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[w] = inc;
+    __syncthreads();
+    int before = 0, all = 0;
+#pragma unroll
+    for (int i = 0; i < kDenseThreads / 32; i++) {
+        const int t = wsum[i];
+        if (i < w) before += t;
+        all += t;
+    }
+    if (threadIdx.x == 0) *total_slot = all;
+    __syncthreads();
+    *total = all;
+    return before + inc - v;
+}
+
+// Loads the next non-empty index window at or after `from`: sets one bit per candidate whose index
+// falls into it and returns, per thread, its run of bitmap words [w0, w1), the rank (inside the
+// window) of the first bit of that run and the number of bits in it; S.tw = candidates in the window.
+__device__ __forceinline__ void dense_load_window(DenseSmem &S, uint32_t from, int &w0, int &w1, int &tbase, int &tlocal) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp == 0) {
+        // first unconsumed element of every list -> the window starts at the smallest one
+        int a = 0;
+        uint32_t nxt = 0xffffffffu;
+        if (lane < 27 && S.llen[lane] > 0) {
+            a = from <= S.lo ? 0 : lower_bound_u32(S.lptr[lane], S.llen[lane], from);
+            if (a < S.llen[lane]) nxt = S.lptr[lane][a];
+        }
+        uint32_t mn = nxt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        const uint32_t s0 = mn & ~31u;
+        if (lane < 27) {
+            S.la[lane] = a;
+            int b = S.llen[lane];
+            if (b > 0 && (uint64_t)S.hi >= (uint64_t)s0 + kWinBits) b = lower_bound_u32(S.lptr[lane], b, s0 + (uint32_t)kWinBits);
+            S.lb[lane] = b;
+        }
+        if (lane == 0) S.s0 = s0;
+    }
+    __syncthreads();
+    const uint32_t s0 = S.s0;
+    const uint32_t top = S.hi - s0;                               // hi >= s0 whenever a candidate is left
+    const int W = (int)min((uint32_t)kWinWords, (top >> 5) + 1u);
+    for (int w = tid; w < W; w += kDenseThreads) S.bm[w] = 0u;
+    __syncthreads();
+    for (int j = warp; j < 27; j += kDenseThreads / 32) {
+        const uint32_t *L = S.lptr[j];
+        for (int t = S.la[j] + lane; t < S.lb[j]; t += 32) {
+            const uint32_t v = L[t] - s0;
+            atomicOr(&S.bm[v >> 5], 1u << (v & 31u));
+        }
+    }
+    __syncthreads();
+    const int wpt = (W + kDenseThreads - 1) / kDenseThreads;
+    w0 = min(W, tid * wpt);
+    w1 = min(W, w0 + wpt);
+    int cnt = 0;
+    for (int w = w0; w < w1; w++) cnt += __popc(S.bm[w]);
+    int total;
+    tbase = dense_block_exscan(cnt, S.wsum, &S.tw, &total);
+    tlocal = cnt;
+}
+
+__global__ void __launch_bounds__(kDenseThreads, 3) k_bq_cells_dense(
+    const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cstart,
+    const int32_t *__restrict__ ccnt, const int32_t *__restrict__ nbr, const int32_t *__restrict__ kc,
+    const int32_t *__restrict__ cand_start, const int32_t *__restrict__ mbase, const int32_t *__restrict__ dense,
+    int64_t *scalars, uint32_t *__restrict__ masks, float r2, uint32_t *__restrict__ cand_idx,
+    int32_t *__restrict__ counts, int32_t *__restrict__ kb) {
+    extern __shared__ uint4 dense_smem_raw[];
+    DenseSmem &S = *reinterpret_cast<DenseSmem *>(dense_smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t nDense = scalars[3];
+    for (;;) {
+        if (tid == 0) S.cellslot = (int32_t)atomicAdd((unsigned long long *)&scalars[4], 1ULL);
+        __syncthreads();
+        const int64_t slot = S.cellslot;
+        if (slot >= nDense) break;
+        const int c = __ldg(dense + slot);
+        const int K = __ldg(kc + c), nq = __ldg(ccnt + c), qs = __ldg(cstart + c), cbase = __ldg(cand_start + c);
+        const int mb = masks ? __ldg(mbase + c) : 0;
+        if (warp == 0) {
+            int len = 0;
+            const uint32_t *L = sorted_pt;
+            if (lane < 27) {
+                const int src = __ldg(nbr + (int64_t)c * 27 + lane);
+                if (src >= 0) { len = __ldg(ccnt + src); L = sorted_pt + __ldg(cstart + src); }
+            }
+            uint32_t head = len ? L[0] : 0xffffffffu, tail = len ? L[len - 1] : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                head = min(head, __shfl_xor_sync(0xffffffffu, head, o));
+                tail = max(tail, __shfl_xor_sync(0xffffffffu, tail, o));
+            }
+            if (lane < 27) { S.lptr[lane] = L; S.llen[lane] = len; }
+            if (lane == 0) { S.lo = head; S.hi = tail; }
+        }
+        __syncthreads();
+        int built_max = 0;
+        for (int sg0 = 0; sg0 < nq; sg0 += kQMax) {                    // passes over the cell's queries (one, normally)
+            const int nqs = min(kQMax, nq - sg0);
+            for (int t = tid; t < nqs; t += kDenseThreads) {
+                const uint32_t k = __ldg(sorted_pt + qs + sg0 + t);
+                S.qx[t] = __ldg(xyz + 3 * (int64_t)k); S.qy[t] = __ldg(xyz + 3 * (int64_t)k + 1); S.qz[t] = __ldg(xyz + 3 * (int64_t)k + 2);
+                S.qcnt[t] = 0;
+                S.qsat[t] = 0;
+            }
+            int w0, w1, tbase, tlocal;
+            int rank_base = 0;                                         // rank of the window's first candidate
+            dense_load_window(S, 0u, w0, w1, tbase, tlocal);           // (its barriers also publish the query rows)
+            int built = 0;
+            for (int Rlo = 0; Rlo < K; Rlo += kTile) {
+                const int Rhi = min(Rlo + kTile, K), nt = Rhi - Rlo;
+                for (;;) {                                             // windows that overlap the tile
+                    int r = rank_base + tbase;
+                    if (r < Rhi && r + tlocal > Rlo) {
+                        const uint32_t s0 = S.s0;
+                        for (int w = w0; w < w1 && r < Rhi; w++) {
+                            uint32_t word = S.bm[w];
+                            const int pc = __popc(word);
+                            if (r + pc <= Rlo) { r += pc; continue; }
+                            while (word) {
+                                const int b = __ffs((int)word) - 1;
+                                word &= word - 1u;
+                                if (r >= Rlo && r < Rhi) {
+                                    const uint32_t id = s0 + ((uint32_t)w << 5) + (uint32_t)b;
+                                    const float *p = xyz + 3 * (int64_t)id;
+                                    S.tile[r - Rlo] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+                                    cand_idx[cbase + r] = id;
+                                }
+                                r++;
+                            }
+                        }
+                    }
+                    const int tw = S.tw;
+                    if (rank_base + tw >= Rhi) break;                  // the tile is complete
+                    rank_base += tw;
+                    const uint32_t nextfrom = S.s0 + (uint32_t)kWinBits;   // < 2^27: indices are below 2^26
+                    __syncthreads();                                   // everyone is done with this bitmap
+                    dense_load_window(S, nextfrom, w0, w1, tbase, tlocal);
+                }
+                const int ntp = (nt + 31) & ~31;
+                for (int t = nt + tid; t < ntp; t += kDenseThreads) S.tile[t] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
+                __syncthreads();
+                // ---- test: lane = query, the tile's candidates come as shared-memory broadcasts
+                const int nblk = ntp >> 5;
+                const int G = (nqs + 31) >> 5, nch = (nblk + kChunkBlocks - 1) / kChunkBlocks;
+                for (int item = warp; item < G * nch; item += kDenseThreads / 32) {
+                    const int g = item / nch, ch = item - g * nch;
+                    const int qi = (g << 5) + lane;
+                    const bool live = qi < nqs;
+                    if (!__any_sync(0xffffffffu, live && !S.qsat[qi])) continue;   // all 32 already hold kCap hits
+                    const float ox = live ? S.qx[qi] : NAN, oy = live ? S.qy[qi] : NAN, oz = live ? S.qz[qi] : NAN;
+                    int cnt = 0;
+                    const int b1 = min(nblk, (ch + 1) * kChunkBlocks);
+                    for (int b = ch * kChunkBlocks; b < b1; b++) {
+                        const float4 *tp = S.tile + (b << 5);
+                        unsigned m = 0;
+#pragma unroll
+                        for (int u = 0; u < 32; u++) m |= (unsigned)bq_hit(ox, oy, oz, tp[u], r2) << u;
+                        cnt += __popc(m);
+                        if (masks && live) masks[mb + (int64_t)((Rlo >> 5) + b) * nq + sg0 + qi] = m;
+                    }
+                    if (live && cnt) atomicAdd(&S.qcnt[qi], cnt);
+                }
+                __syncthreads();
+                built = Rhi;
+                int unsat = 0;
+                for (int t = tid; t < nqs; t += kDenseThreads) {
+                    const bool s = S.qcnt[t] >= kCap;
+                    S.qsat[t] = s;
+                    unsat |= !s;
+                }
+                if (!__syncthreads_or(unsat)) break;                  // nobody needs later candidates
+            }
+            for (int t = tid; t < nqs; t += kDenseThreads) counts[qs + sg0 + t] = min(S.qcnt[t], kCap);
+            built_max = max(built_max, built);
+            __syncthreads();
+        }
+        if (tid == 0) kb[c] = built_max;
+    }
+}
+
+// start_len rows from the per-query counts and their exclusive scan (both in query order)
+__global__ void k_bq_start_len(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ counts,
+                               const int32_t *__restrict__ starts, int32_t n, int2 *__restrict__ start_len) {
+    int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) start_len[sorted_pt[q]] = make_int2(starts[q], counts[q]);
+}
+
+// ---- fill -------------------------------------------------------------------------------------------
 constexpr int kFillQ = 4;
 
-__device__ __forceinline__ void bq_fill_one(const float *__restrict__ xyz, uint32_t k, const float4 *__restrict__ cl, int K,
-                                            const int2 *__restrict__ start_len, float r2, int32_t *__restrict__ idx,
-                                            int lane, unsigned lt) {
-    const int2 sl = __ldg(start_len + k);
-    if (sl.y == 0) return;
-    const float ox = __ldg(xyz + 3 * (int64_t)k), oy = __ldg(xyz + 3 * (int64_t)k + 1), oz = __ldg(xyz + 3 * (int64_t)k + 2);
-    int32_t *out = idx + sl.x;
-    int written = 0;
-    for (int base = 0; base < K && written < sl.y; base += 32) {
-        const int e = base + lane;
-        bool hit = false;
-        float4 cd = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (e < K) {
-            cd = __ldg(cl + e);
-            hit = bq_hit(ox, oy, oz, cd, r2);
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        const int pos = written + __popc(m & lt);
-        if (hit && pos < sl.y) out[pos] = __float_as_int(cd.w);
-        written += __popc(m);
-    }
-}
-
+// without masks: a warp per query re-evaluates the predicate over the cell's sorted candidates
 __global__ void __launch_bounds__(256) k_bq_fill(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
                                                  const int32_t *__restrict__ cell, const int32_t *__restrict__ cand_start,
-                                                 const int32_t *__restrict__ kc, const float4 *__restrict__ cand,
+                                                 const int32_t *__restrict__ kb, const uint32_t *__restrict__ cand_idx,
                                                  const int2 *__restrict__ start_len, float r2, int32_t n,
                                                  int32_t *__restrict__ idx) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t q0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kFillQ; q0 < n; q0 += nWarps * kFillQ) {
-        const int nq = (int)((n - q0) < kFillQ ? (n - q0) : kFillQ);
-        uint32_t k[kFillQ];
-        int c[kFillQ];
-        bool same = nq == kFillQ;
-#pragma unroll
-        for (int u = 0; u < kFillQ; u++) {
-            k[u] = u < nq ? sorted_pt[q0 + u] : 0u;
-            c[u] = u < nq ? __ldg(cell + k[u]) : -1;
-            same = same && c[u] == c[0];
-        }
-        if (!same) {
-            for (int u = 0; u < nq; u++)
-                bq_fill_one(xyz, k[u], cand + __ldg(cand_start + c[u]), __ldg(kc + c[u]), start_len, r2, idx, lane, lt);
-            continue;
-        }
-        const int K = __ldg(kc + c[0]);
-        const float4 *cp = cand + __ldg(cand_start + c[0]) + lane;
-        float ox[kFillQ], oy[kFillQ], oz[kFillQ];
-        int wpos[kFillQ], wend[kFillQ];
-#pragma unroll
-        for (int u = 0; u < kFillQ; u++) {
-            const int2 sl = __ldg(start_len + k[u]);
-            ox[u] = __ldg(xyz + 3 * (int64_t)k[u]); oy[u] = __ldg(xyz + 3 * (int64_t)k[u] + 1); oz[u] = __ldg(xyz + 3 * (int64_t)k[u] + 2);
-            wpos[u] = sl.x; wend[u] = sl.x + sl.y;
-        }
-        const float4 pad = make_float4(INFINITY, INFINITY, INFINITY, 0.f);   // never within any radius
-        float4 nx = lane < K ? __ldg(cp) : pad;
-        for (int base = 0; base < K; base += 32) {
-            const float4 cd = nx;
-            cp += 32;
-            nx = (base + 32 + lane < K) ? __ldg(cp) : pad;                   // next tile in flight
-#pragma unroll
-            for (int u = 0; u < kFillQ; u++) {
-                const bool hit = bq_hit(ox[u], oy[u], oz[u], cd, r2);
-                const unsigned m = __ballot_sync(0xffffffffu, hit);
-                const int pos = wpos[u] + __popc(m & lt);
-                if (hit && pos < wend[u]) idx[pos] = __float_as_int(cd.w);
-                wpos[u] += __popc(m);
+    for (int64_t q = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); q < n; q += nWarps) {
+        const uint32_t k = sorted_pt[q];
+        const int2 sl = __ldg(start_len + k);
+        if (sl.y == 0) continue;
+        const int c = __ldg(cell + k);
+        const uint32_t *ci = cand_idx + __ldg(cand_start + c);
+        const int K = __ldg(kb + c);
+        const float ox = __ldg(xyz + 3 * (int64_t)k), oy = __ldg(xyz + 3 * (int64_t)k + 1), oz = __ldg(xyz + 3 * (int64_t)k + 2);
+        int32_t *out = idx + sl.x;
+        int written = 0;
+        for (int base = 0; base < K && written < sl.y; base += 32) {
+            const int e = base + lane;
+            bool hit = false;
+            uint32_t id = 0;
+            if (e < K) {
+                id = __ldg(ci + e);
+                const float *p = xyz + 3 * (int64_t)id;
+                hit = bq_hit(ox, oy, oz, make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f), r2);
             }
-            if (wpos[0] >= wend[0] && wpos[1] >= wend[1] && wpos[2] >= wend[2] && wpos[3] >= wend[3]) break;
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            const int pos = written + __popc(m & lt);
+            if (hit && pos < sl.y) out[pos] = (int)id;
+            written += __popc(m);
         }
     }
 }
@@ -461,7 +558,7 @@ __device__ __forceinline__ void bq_fill_mask_one(uint32_t k, const uint32_t *__r
 
 __global__ void __launch_bounds__(256) k_bq_fill_mask(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cell,
                                                       const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
-                                                      const int32_t *__restrict__ cand_start, const int32_t *__restrict__ kc,
+                                                      const int32_t *__restrict__ cand_start, const int32_t *__restrict__ kb,
                                                       const uint32_t *__restrict__ cand_idx, const int32_t *__restrict__ mbase,
                                                       const uint32_t *__restrict__ masks, const int2 *__restrict__ start_len,
                                                       int32_t n, int32_t *__restrict__ idx) {
@@ -482,14 +579,14 @@ __global__ void __launch_bounds__(256) k_bq_fill_mask(const uint32_t *__restrict
         if (!same) {
             for (int u = 0; u < nqr; u++) {
                 const int cc = c[u];
-                bq_fill_mask_one(k[u], cand_idx + __ldg(cand_start + cc), __ldg(kc + cc),
+                bq_fill_mask_one(k[u], cand_idx + __ldg(cand_start + cc), __ldg(kb + cc),
                                  masks + __ldg(mbase + cc) + (int)(q0 + u - __ldg(cstart + cc)), __ldg(ccnt + cc), start_len,
                                  idx, lane, lt);
             }
             continue;
         }
         const int cc = c[0];
-        const int K = __ldg(kc + cc);
+        const int K = __ldg(kb + cc);
         const int nq = __ldg(ccnt + cc);
         // running pointers, 32-bit output positions: the loop body is ~10 instructions per (query, block)
         const uint32_t *cp = cand_idx + __ldg(cand_start + cc) + lane;
@@ -517,7 +614,7 @@ __global__ void __launch_bounds__(256) k_bq_fill_mask(const uint32_t *__restrict
                     const unsigned m = __shfl_sync(0xffffffffu, mw, j * 4 + u);
                     const int pos = wpos[u] + __popc(m & lt);
                     if (((m >> lane) & 1u) && pos < wend[u]) idx[pos] = cidr[j];
-                    wpos[u] += __popc(m);
+                    wpos[u] = min(wpos[u] + __popc(m), wend[u]);   // words past a full list may be unwritten: stay put
                 }
             }
             done = wpos[0] >= wend[0] && wpos[1] >= wend[1] && wpos[2] >= wend[2] && wpos[3] >= wend[3];
@@ -566,17 +663,12 @@ extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs,
     PG_TRY(radix_sort_pairs(reinterpret_cast<const uint32_t *>(w.cell), nullptr, w.kA, w.vA, w.kB, w.vB, n, bits,
                             w.hist, w.scan_tmp, st, &res));
     const uint32_t *sorted_pt = res == 0 ? w.vA : w.vB;
-    uint32_t *spare2 = res == 0 ? w.kA : w.kB;  // after the sort the key buffers are free: merge tile starts
     PG_CUDA(cudaMemsetAsync(w.ccnt + n, 0, sizeof(int32_t), st));
     PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
     const unsigned gsm = kNumSM * 8;
-    k_bq_neighbours<<<kNumSM * 16, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc);
+    k_bq_neighbours<<<kNumSM * 16, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense);
     k_bq_clear_tail<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n + 1);   // kc beyond nCells must scan as 0
     PG_TRY(scan_exclusive_i32(w.kc, w.cand_start, (int64_t)n + 1, w.scalars + 1, w.scan_tmp, st));
-    k_bq_tiles<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n, (int32_t *)spare2);
-    PG_TRY(scan_exclusive_i32((int32_t *)spare2, (int32_t *)spare2, n, w.scalars + 5, w.scan_tmp, st));
-    k_bq_merge<<<kNumSM * 8, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, (int32_t *)spare2,
-                                           w.scalars, w.cand, w.cand_idx);
     k_bq_mask_sizes<<<gsm, 256, 0, st>>>(w.ccnt, w.kc, w.scalars, n + 1, w.mbase);
     PG_TRY(scan_exclusive_i32(w.mbase, w.mbase, (int64_t)n + 1, w.scalars + 6, w.scan_tmp, st));
     PG_LAUNCH_CHECK();
@@ -600,12 +692,17 @@ extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int
     if (!w.ok) { set_error("pg_ballquery_count: workspace too small (%zu < %zu)", ws_bytes, w.used); return PG_EWORKSPACE; }
     const uint32_t *sorted_pt = bq_sorted(w, n);
     const float r2 = radius * radius;
-    const unsigned grid = (unsigned)div_up(n, 256);
-    if (masks) k_bq_count<true><<<grid, 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kc, w.cand, w.mbase, masks, r2, n, w.counts);
-    else k_bq_count<false><<<grid, 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kc, w.cand, w.mbase, nullptr, r2, n, w.counts);
-    // starts (reuse pslot) and the interleaved (start, len) rows
+    PG_CUDA(cudaFuncSetAttribute(k_bq_cells_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DenseSmem)));
+    const int64_t gsmall_want = div_up(n, 8);
+    const unsigned gsmall = (unsigned)(gsmall_want < (int64_t)kNumSM * 16 ? gsmall_want : (int64_t)kNumSM * 16);
+    k_bq_cells_small<<<gsmall, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars,
+                                             masks, r2, w.cand_idx, w.counts, w.kb);
+    k_bq_cells_dense<<<kNumSM * 3, kDenseThreads, sizeof(DenseSmem), st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc,
+                                                                            w.cand_start, w.mbase, w.dense, w.scalars, masks,
+                                                                            r2, w.cand_idx, w.counts, w.kb);
+    // starts (reuse pslot) in query order, then the interleaved (start, len) rows per point
     PG_TRY(scan_exclusive_i32(w.counts, w.pslot, n, w.scalars + 2, w.scan_tmp, st));
-    k_bq_start_len<<<(unsigned)div_up(n, 256), 256, 0, st>>>(w.counts, w.pslot, n, (int2 *)start_len);
+    k_bq_start_len<<<(unsigned)div_up(n, 256), 256, 0, st>>>(sorted_pt, w.counts, w.pslot, n, (int2 *)start_len);
     PG_LAUNCH_CHECK();
     int64_t total = 0;
     PG_CUDA(cudaMemcpyAsync(&total, w.scalars + 2, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
@@ -630,10 +727,11 @@ extern "C" int pg_ballquery_fill(const float *xyz, int32_t n, float radius, cons
     const uint32_t *sorted_pt = bq_sorted(w, n);
     const float r2 = radius * radius;
     if (masks)
-        k_bq_fill_mask<<<kNumSM * 8, 256, 0, st>>>(sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kc, w.cand_idx, w.mbase,
+        k_bq_fill_mask<<<kNumSM * 8, 256, 0, st>>>(sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx, w.mbase,
                                                    masks, (const int2 *)start_len, n, idx);
     else
-        k_bq_fill<<<kNumSM * 8, 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cand_start, w.kc, w.cand, (const int2 *)start_len, r2, n, idx);
+        k_bq_fill<<<kNumSM * 8, 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cand_start, w.kb, w.cand_idx, (const int2 *)start_len,
+                                              r2, n, idx);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

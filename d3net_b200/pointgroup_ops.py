@@ -135,7 +135,7 @@ class BallQueryBatchP(Function):
         :param batch_offsets: (B+1) int
         :param radius: float
         :param meanActive: int (the reference's initial buffer guess; unused here)
-        :return: idx (nActive), int -- per point ascending, segments laid out in point order
+        :return: idx (nActive), int -- per point ascending, segments laid out in query (cell) order
         :return: start_len (n, 2), int
         (functions/pointgroup_ops.py:115-150)
         '''

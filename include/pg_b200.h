@@ -84,7 +84,7 @@ int pg_point_recover_bp(const float *d_out, float *d_feats, const int32_t *rules
  * at most the first PG_BALLQUERY_CAP.  Three phases over one workspace:
  *   prepare  builds the uniform grid and the per-cell candidate arrays; host_mask_words = number of
  *            uint32 words an optional hit-mask buffer needs (-1: too many, run without);
- *   count    writes start_len int32 [n,2] = (start, cnt), segments laid out in point order
+ *   count    writes start_len int32 [n,2] = (start, cnt), segments laid out in query (cell) order
  *            (deterministic; the reference's atomicAdd placement is not), host_total = sum cnt; when
  *            `masks` (device, mask_words uint32) is given it also records every predicate outcome;
  *   fill     writes idx int32 [total]; with `masks` it only turns recorded bits into indices, without

@@ -191,20 +191,34 @@ def get_iou(proposals_idx, proposals_offset, instance_labels, instance_pointnum)
 # ---------------------------------------------------------------------------------------------
 # canonical forms used by the parity tests (neighbour sets sorted, clusters relabelled)
 # ---------------------------------------------------------------------------------------------
-def canonical_neighbours(idx, start_len):
-    """Per-point neighbour lists re-laid out in point order with each list sorted ascending."""
+def relaid_neighbours(idx, start_len, sort=False):
+    """Per-point neighbour lists re-laid out in point order (segment placement is the producer's
+    choice: the reference places segments by atomicAdd, bfs_cluster.cu:47), each list in its stored
+    order -- or sorted ascending with ``sort``.  Also checks that the segments do not overlap."""
     idx = np.asarray(idx)
     start_len = np.asarray(start_len).reshape(-1, 2)
     lens = start_len[:, 1].astype(np.int64)
     starts = start_len[:, 0].astype(np.int64)
     total = int(lens.sum())
+    assert total <= idx.shape[0]
+    if len(lens):
+        o = np.argsort(starts, kind="stable")
+        o = o[lens[o] > 0]
+        assert (starts[o][1:] >= (starts[o] + lens[o])[:-1]).all(), "neighbour segments overlap"
+        assert len(o) == 0 or (starts[o][0] >= 0 and starts[o][-1] + lens[o][-1] <= idx.shape[0])
     new_start = np.concatenate([[0], np.cumsum(lens)])[:-1]
     # gather position p of list i  ->  idx[starts[i] + p]
     owner = np.repeat(np.arange(len(lens)), lens)
     pos = np.arange(total) - np.repeat(new_start, lens)
     flat = idx[np.repeat(starts, lens) + pos]
-    order = np.lexsort((flat, owner))
-    return flat[order].astype(np.int32), lens.astype(np.int32)
+    if sort:
+        flat = flat[np.lexsort((flat, owner))]
+    return flat.astype(np.int32), lens.astype(np.int32)
+
+
+def canonical_neighbours(idx, start_len):
+    """Per-point neighbour lists re-laid out in point order with each list sorted ascending."""
+    return relaid_neighbours(idx, start_len, sort=True)
 
 
 def canonical_clusters(cluster_idxs, cluster_offsets):

@@ -38,8 +38,11 @@ def check_trace(trace):
         elif name.startswith("ballquery"):
             xyz, bi, bo, idx, sl = rec
             ridx, rsl = o.ballquery_batch_p(_n(xyz), _n(bi), _n(bo), 0.03)
-            _same(_n(sl), rsl, name + " start_len")
-            _same(_n(idx), ridx, name + " idx")
+            # segment placement is free (bfs_cluster.cu:47); lengths and each point's ascending list are not
+            got, glen = o.relaid_neighbours(_n(idx), _n(sl))
+            want, wlen = o.relaid_neighbours(ridx, rsl)
+            _same(glen, wlen, name + " start_len lengths")
+            _same(got, want, name + " idx")
         elif name.startswith("bfs_cluster"):
             sem, idx, sl, ci, co = rec
             rci, rco = o.bfs_cluster(_n(sem), _n(idx), _n(sl), 50)

@@ -35,12 +35,22 @@ def _check_voxel_maps(coords, voxel_coords, p2v, v2p):
     assert voxel_coords.unique(dim=0).size(0) == M                             # no voxel split in two
 
 
+def _owners(sl, n_idx):
+    """Owner point of every idx entry.  Segments may sit anywhere (the reference places them by
+    atomicAdd, bfs_cluster.cu:47) but must tile idx exactly, without gaps or overlap."""
+    starts, lens = sl[:, 0].long(), sl[:, 1].long()
+    order = torch.argsort(starts, stable=True)
+    order = order[lens[order] > 0]
+    ls = lens[order]
+    assert torch.equal(starts[order], torch.cumsum(ls, 0) - ls) and int(ls.sum()) == n_idx
+    return torch.repeat_interleave(order, ls)
+
+
 def _check_neighbours(xyz, batch_idxs, idx, sl, r, rng, n_sample=300):
     n = xyz.size(0)
     starts, lens = sl[:, 0].long(), sl[:, 1].long()
-    assert torch.equal(starts, torch.cumsum(lens, 0) - lens) and int(lens.sum()) == idx.numel()
     assert int(lens.max()) <= 1000
-    owner = torch.repeat_interleave(torch.arange(n, device=xyz.device), lens)
+    owner = _owners(sl, idx.numel())
     j = idx.long()
     assert bool((batch_idxs[owner] == batch_idxs[j]).all())                    # never across scenes
     same_list = owner[1:] == owner[:-1]
@@ -87,7 +97,7 @@ def _check_clusters(sem, idx, sl, ci, co, thr):
     assert torch.equal(lab, lab[co[:-1].long()].repeat_interleave(sizes))      # one label per cluster
     # every edge between equal labels stays inside one component (sizes of both ends agree)
     lens = sl[:, 1].long()
-    owner = torch.repeat_interleave(torch.arange(n, device=sl.device), lens)
+    owner = _owners(sl, idx.numel())
     j = idx.long()
     e = sem[owner] == sem[j]
     two_way = (lens[j] < 1000)                                                 # reverse edge certainly present
@@ -178,8 +188,7 @@ def test_config4_one_million_point_scene(ops):
             assert int((co[1:] - co[:-1]).max()) > 100_000                     # the floor is one component
             import scipy.sparse as sp
             from scipy.sparse.csgraph import connected_components
-            lens = sl[:, 1].long()
-            owner = torch.repeat_interleave(torch.arange(n, device=dev), lens)
+            owner = _owners(sl, idx.numel())
             j = idx.long()
             e = sem[owner] == sem[j]
             a, b = owner[e].cpu().numpy(), j[e].cpu().numpy()
