@@ -126,8 +126,13 @@ def ballquery_fill_impl(xyz, radius, start_len, idx, state):
                                      idx.numel(), _p(ws), ws.numel(), _stream()), "ballquery_batch_p(fill)")
 
 
-def bfs_cluster_impl(semantic_label, ball_query_idxs, start_len, threshold, generic=0):
-    """All CUDA int32 -> (cluster_idxs [S,2], cluster_offsets [nC+1], used_generic_path)."""
+BFS_AUTO, BFS_GENERIC, BFS_TRUSTED = 0, 1, 2      # include/pg_b200.h, `mode` of pg_bfs_cluster_count
+
+
+def bfs_cluster_impl(semantic_label, ball_query_idxs, start_len, threshold, generic=0, trusted=False):
+    """All CUDA int32 -> (cluster_idxs [S,2], cluster_offsets [nC+1], used_generic_path).
+    ``trusted``: the lists are ballquery_batch_p output of this library, untouched -- the sweep skips the
+    validation it needs for foreign neighbour lists (d3net_b200.pointgroup_ops decides this by provenance)."""
     _need(semantic_label, "semantic_label", torch.int32)
     _need(ball_query_idxs, "ball_query_idxs", torch.int32)
     _need(start_len, "start_len", torch.int32)
@@ -141,7 +146,8 @@ def bfs_cluster_impl(semantic_label, ball_query_idxs, start_len, threshold, gene
         ws = _ws(nws, dev)
         sizes = (ctypes.c_int32 * 3)()
         check(L.pg_bfs_cluster_count(_p(semantic_label), _p(ball_query_idxs), _p(start_len), N,
-                                     ball_query_idxs.numel(), int(threshold), int(generic), _p(ws), nws, sizes,
+                                     ball_query_idxs.numel(), int(threshold),
+                                     BFS_GENERIC if generic else (BFS_TRUSTED if trusted else BFS_AUTO), _p(ws), nws, sizes,
                                      _stream()), "bfs_cluster(count)")
         nC, S = int(sizes[0]), int(sizes[1])
         cluster_idxs = torch.empty((S, 2), dtype=torch.int32, device=dev)

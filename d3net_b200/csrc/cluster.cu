@@ -8,14 +8,21 @@
 //
 // The edge relation is symmetric except where a neighbour list was truncated at 1000 entries
 // (bfs_cluster.cu:38-43): j in list(i) but i not in list(j)  <=>  list(j) is full and i > last(list(j)).
-//   fast path    ONE sweep over the edges: union-find with atomic hooking (larger root under smaller,
-//                so a root is its component's minimum) over the two-way edges, taken from their
-//                higher endpoint; one-way edges whose endpoints are not yet connected are parked in a
-//                pending list and settled afterwards by a min-label propagation over that (tiny) list.
+//   fast path    union-find with atomic hooking (larger root under smaller, so a root is its
+//                component's minimum) over the two-way edges, in three steps:
+//                  sample   every point is united with three of its neighbours (first, middle, last);
+//                           in a ball-query graph that already connects almost every component;
+//                  flatten  root[v] = find(v): a read-only snapshot of the partition so far;
+//                  verify   ONE sweep over all edges, lists taken in the order their segments sit in
+//                           idx (= spatial order when the producer is this library's ball query), so
+//                           the snapshot reads of a block hit L1: an edge whose ends share a snapshot
+//                           root is done; the rare others go through the coherent union-find.  One-way
+//                           edges between different components are parked in a pending list and
+//                           settled afterwards by a min-label propagation over that (tiny) list.
 //   generic path min-label propagation over ALL edges with no unions: exact for any directed graph.
 // The fast path is only trusted when the lists check out as a truncated symmetric relation: in range,
 // ascending, and a 64-bit checksum of the two-way edge set that cancels against its own reversal.
-// Both checks ride along in the same sweep and need no extra memory traffic.
+// Both checks ride along in the verify sweep and need no extra memory traffic.
 #include "common.cuh"
 
 namespace pg {
@@ -27,6 +34,7 @@ struct ClWs {
     uint32_t *trunc;     // bitmap: list is full (len >= 1000), i.e. may lack reverse edges
     int32_t *last;       // last entry of a full list: u -> v is two-way  <=>  u <= last[v]
     int32_t *root;       // flattened component root per point (identity on the generic path)
+    uint32_t *snap;      // root | label bits | full bit: what the sweep reads per edge
     int32_t *lab;        // min-ancestor label forest over roots
     int32_t *size;       // points per final label
     int32_t *cid;        // cluster id per kept label (exclusive scan of keep flags)
@@ -35,7 +43,8 @@ struct ClWs {
     uint32_t *key0, *kA, *vA, *kB, *vB;
     int32_t *hist;
     int64_t *scan_tmp;
-    // [0] checksum [1] bad [2] pending count [3] changed [4] nCluster [5] sumNPoint
+    // [0] checksum [1] bad [2] pending count [3] changed [4] nCluster [5] sumNPoint [6] verify work counter
+    // [7] some list is full
     unsigned long long *scalars;
     size_t pend_cap;
     bool ok;
@@ -50,6 +59,7 @@ static ClWs cl_layout(void *ws, size_t ws_bytes, int64_t N_) {
     w.trunc = a.take<uint32_t>(n / 32 + 2);
     w.last = a.take<int32_t>(n);
     w.root = a.take<int32_t>(n);
+    w.snap = a.take<uint32_t>(n);
     w.lab = a.take<int32_t>(n);
     w.size = a.take<int32_t>(n + 1);
     w.cid = a.take<int32_t>(n + 1);
@@ -73,38 +83,62 @@ static ClWs cl_layout(void *ws, size_t ws_bytes, int64_t N_) {
 // Cheap (three integer multiplies); it only has to make accidental cancellation of unmatched edges
 // in the checksum a 2^-64-class event, not resist an adversary.
 __device__ __forceinline__ unsigned long long mix64(unsigned a, unsigned b) {
-    const unsigned x = (a ^ 0x5bd1e995u) * 0x9E3779B1u;
-    const unsigned y = (b + 0x7f4a7c15u) * 0x85EBCA77u;
-    return (unsigned long long)(x ^ (x >> 15)) * (unsigned long long)((y ^ (y >> 13)) | 1u) + a;
+    const unsigned x = a * 0x9E3779B1u + 0x5bd1e995u;
+    const unsigned y = b * 0x85EBCA77u + 0x7f4a7c15u;
+    return (unsigned long long)(x ^ (x >> 15)) * (unsigned long long)((y ^ (y >> 13)) | 1u);
 }
 
-// one thread per point, launched over ceil(N / 32) * 32 threads so every bitmap word has a full warp
+// one thread per point, launched over ceil(N / 32) * 32 threads so every bitmap word has a full warp.
+// Besides the per-point records it plants the first tree edges without a single atomic: a point
+// hangs itself under the first entry of its list (the smallest index in its ball) when that is a
+// smaller, equal-label point that lists it back -- parents only ever point to smaller indices, so the
+// result is a forest, and in a ball-query graph every ball-sized neighbourhood is already one tree.
 __global__ void k_cl_prep(const int32_t *__restrict__ label, const int32_t *__restrict__ idx,
-                          const int2 *__restrict__ start_len, int32_t N, int64_t nActive, uint2 *__restrict__ pl,
-                          uint32_t *__restrict__ trunc, int32_t *__restrict__ last, int32_t *__restrict__ root,
-                          int32_t *__restrict__ lab, unsigned long long *scalars) {
+                          const int2 *__restrict__ start_len, int32_t N, int64_t nActive, int hook,
+                          uint2 *__restrict__ pl, uint32_t *__restrict__ trunc, int32_t *__restrict__ last,
+                          int32_t *__restrict__ root, int32_t *__restrict__ lab, uint32_t *__restrict__ skey, int shift,
+                          unsigned long long *scalars) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     bool full = false;
     if (v < N) {
         const int2 sl = start_len[v];
+        skey[v] = (uint32_t)(sl.x < 0 ? 0 : sl.x) >> shift;   // where the list sits in idx: the sweep order
         int lst = 0x7fffffff;
+        int parent = v;
+        const int lv = __ldg(label + v);
         if (sl.y < 0 || sl.x < 0 || (int64_t)sl.x + sl.y > nActive) scalars[1] = 2;   // malformed row
-        else if (sl.y >= kCapC) { lst = __ldg(idx + sl.x + sl.y - 1); full = true; }
-        pl[v] = make_uint2((unsigned)v, (unsigned)__ldg(label + v));
+        else {
+            if (sl.y >= kCapC) { lst = __ldg(idx + sl.x + sl.y - 1); full = true; }
+            if (hook && sl.y > 0) {
+                int j = __ldg(idx + sl.x);
+                if (j == v && sl.y > 1) j = __ldg(idx + sl.x + 1);
+                if (j >= 0 && j < v && __ldg(label + j) == lv) {
+                    const int2 sj = __ldg(start_len + j);
+                    bool back = true;                              // does j list v?  (only a full list may not)
+                    if (sj.y >= kCapC)
+                        back = sj.x >= 0 && (int64_t)sj.x + sj.y <= nActive && v <= __ldg(idx + sj.x + sj.y - 1);
+                    if (back) parent = j;
+                }
+            }
+        }
+        pl[v] = make_uint2((unsigned)parent, (unsigned)lv);
         last[v] = lst;
         root[v] = v;
         lab[v] = v;
     }
     const unsigned m = __ballot_sync(0xffffffffu, full);
     if ((threadIdx.x & 31) == 0 && (v >> 5) <= (N >> 5)) trunc[v >> 5] = m;
+    if (m && (threadIdx.x & 31) == 0) scalars[7] = 1;
 }
 
-// union-find on pl[].x
-// (parent reads go to L2 with ld.cg: an L1-stale "x is still a root" could spin the CAS loop)
+// union-find on pl[].x.  Parent reads are ordinary (L1-cached) loads: a component's root line is read
+// by every find that ends there, and served from L2 alone it becomes a serialised hot spot.  A stale
+// parent is still an ancestor (pointers only ever move towards the root), so stale reads cost steps,
+// never correctness; the one place that needs fresh data takes it from the CAS itself (below).
 __device__ __forceinline__ int uf_find(uint2 *pl, int x) {
-    int p = (int)__ldcg(&pl[x].x);
+    int p = (int)pl[x].x;
     while (p != x) {
-        const int gp = (int)__ldcg(&pl[p].x);
+        const int gp = (int)pl[p].x;
         if (gp != p) pl[x].x = (unsigned)gp;   // path halving; pointers only ever move to smaller ancestors
         x = p;
         p = gp;
@@ -112,108 +146,165 @@ __device__ __forceinline__ int uf_find(uint2 *pl, int x) {
     return x;
 }
 
-// a, b: roots as far as the caller knows; returns the root of the merged set as far as this thread can tell
+// a, b: roots as far as the caller knows; returns the root of the merged set as far as this thread can tell.
+// When the CAS fails its return value IS the fresh parent of `hi`: the retry continues from there, so a
+// stale "still a root" in L1 cannot spin the loop -- every failure moves strictly up the tree.
 __device__ __forceinline__ int uf_union_roots(uint2 *pl, int a, int b) {
     for (;;) {
         if (a == b) return a;
         const int hi = max(a, b), lo = min(a, b);
         const unsigned old = atomicCAS(&pl[hi].x, (unsigned)hi, (unsigned)lo);
         if (old == (unsigned)hi) return lo;
-        a = uf_find(pl, hi);     // hi was hooked by somebody else meanwhile
+        a = uf_find(pl, (int)old);     // hi was hooked by somebody else meanwhile
         b = uf_find(pl, lo);
     }
 }
 
-// The single edge sweep of the fast path.  G lanes share one point's list (coalesced reads of idx).
-template <int G>
-__global__ void __launch_bounds__(256) k_cl_union(const int32_t *__restrict__ idx, const int2 *__restrict__ start_len,
-                                                  uint2 *pl, const uint32_t *__restrict__ trunc,
-                                                  const int32_t *__restrict__ last, int32_t N, int2 *__restrict__ pend,
-                                                  unsigned pend_cap, unsigned long long *scalars) {
-    const int sub = threadIdx.x % G;
-    const int64_t groups = (int64_t)gridDim.x * (blockDim.x / G);
-    unsigned long long chk = 0;
+// a, b: distinct nodes that were roots a moment ago.  Plain loads first: most callers find the pair
+// already united by somebody else and never issue the atomic.
+__device__ __forceinline__ int uf_union_checked(uint2 *pl, int a, int b) {
+    a = uf_find(pl, a);
+    b = uf_find(pl, b);
+    return uf_union_roots(pl, a, b);
+}
+
+// Snapshot word per point, written by k_cl_flatten and read (through the read-only L1 path) once per edge
+// by the sweep:  [31] the point's list is full   [30:26] low 5 bits of its label   [25:0] its root.
+// Equal roots = already connected.  Different label bits = never connected.  Only a pair that differs in
+// the root field alone needs the forest.
+constexpr unsigned kSnapRoot = 0x03ffffffu, kSnapLabel = 0x7c000000u, kSnapFull = 0x80000000u;
+
+// sample: after the first flatten every point probes two more of its neighbours (middle and last entry
+// of its list) and unites the two trees when their snapshot roots differ.  Only two-way edges between
+// equal labels are used, exactly the edges the verify sweep would unite along: this is a head start
+// that leaves the sweep almost nothing but "same root" answers.
+__global__ void k_cl_sample(const int32_t *__restrict__ idx, const int2 *__restrict__ start_len, uint2 *pl,
+                            const int32_t *__restrict__ last, const uint32_t *__restrict__ snap, int32_t N) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int2 sl = start_len[i];
+    if (sl.y <= 1) return;
+    int jj[2];
+    jj[0] = __ldg(idx + sl.x + (sl.y >> 1));
+    jj[1] = __ldg(idx + sl.x + sl.y - 1);
+    const unsigned si = __ldg(snap + i);
+    unsigned sj[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) sj[u] = ((unsigned)jj[u] < (unsigned)N) ? __ldg(snap + jj[u]) : si;
+    int ri = (int)(si & kSnapRoot);
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+        const int j = jj[u];
+        const unsigned x = (si ^ sj[u]) & ~kSnapFull;
+        if (x == 0u || x > kSnapRoot) continue;                      // same tree, or different label bits
+        if (pl[j].y != pl[i].y) continue;
+        if ((sj[u] & kSnapFull) && i > __ldg(last + j)) continue;    // j does not list i back
+        ri = uf_union_checked(pl, ri, (int)(sj[u] & kSnapRoot));
+    }
+}
+
+// verify: the single sweep over all edges.  G lanes share one point's list (coalesced, streaming reads of
+// idx); lists are taken in `order` (ascending segment start) in chunks handed out by an atomic counter,
+// so the lists a block works on at any time belong to neighbouring points and their snapshot reads
+// mostly hit L1.  TRUSTED: the caller vouches that the lists are this library's ball-query output
+// (in range, a truncated symmetric relation) -- no range checks, no checksum.
+constexpr int kVerThreads = 512;
+
+template <int G, bool TRUSTED>
+__global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__restrict__ idx, const int2 *__restrict__ start_len,
+                                                              const uint32_t *__restrict__ order, uint2 *pl,
+                                                              const int32_t *__restrict__ last,
+                                                              const uint32_t *__restrict__ snap, int32_t N,
+                                                              int2 *__restrict__ pend, unsigned pend_cap,
+                                                              unsigned long long *scalars) {
+    constexpr int kGroups = kVerThreads / G;
+    constexpr int kChunk = kGroups * 4;
+    __shared__ long long s_base[2];
+    const int sub = threadIdx.x % G, grp = threadIdx.x / G;
+    unsigned long long chk = 0, chk_rev = 0;
     bool bad = false;
-    // the loop bound is rounded up to whole groups so that every lane of a warp takes part in the shuffle
-    const int64_t n_up = ((int64_t)N + groups - 1) / groups * groups;
-    for (int64_t i64 = (int64_t)blockIdx.x * (blockDim.x / G) + threadIdx.x / G; i64 < n_up; i64 += groups) {
-        const bool live = i64 < N;
-        const int i = live ? (int)i64 : 0;
-        // one lane of the group finds the point's root; the others get it by shuffle
-        int ri = (live && sub == 0) ? uf_find(pl, i) : 0;
-        ri = __shfl_sync(0xffffffffu, ri, 0, G);
-        if (!live) continue;
-        const int2 sl = start_len[i];
-        const unsigned li = pl[i].y;
-        // software pipeline, kU edges per lane per trip: all index loads first, then all bitmap words,
-        // then all (parent, label) records -- three dependent round trips per trip instead of per edge
-        constexpr int kU = 4;
-        for (int e0 = sub; e0 < sl.y; e0 += kU * G) {
-            int jj[kU], pv[kU];
-            unsigned tw[kU];
-            uint2 w[kU];
-            bool use[kU], twoway[kU];
+    const bool any_full = scalars[7] != 0;       // some list holds kCap entries: reverse edges may be missing
+    if (threadIdx.x == 0) s_base[0] = (long long)atomicAdd(&scalars[6], (unsigned long long)kChunk);
+    __syncthreads();
+    for (int round = 0;; round++) {
+        const long long base = s_base[round & 1];
+        if (base >= N) break;
+        // the next chunk is claimed now and published after this one's work: its latency hides behind the lists
+        long long nxt = 0;
+        if (threadIdx.x == 0) nxt = (long long)atomicAdd(&scalars[6], (unsigned long long)kChunk);
+        const long long stop = base + kChunk < N ? base + kChunk : N;
+        for (long long p = base + grp; p < stop; p += kGroups) {
+            const int i = (int)__ldg(order + p);
+            const int2 sl = __ldg(start_len + i);
+            const unsigned si = __ldg(snap + i);
+            int ri = (int)(si & kSnapRoot);          // current root of i's set as far as this group knows
+            constexpr int kU = 4;
+            for (int e0 = sub; e0 < sl.y; e0 += kU * G) {
+                int jj[kU];
+                unsigned sj[kU];
 #pragma unroll
-            for (int u = 0; u < kU; u++) {
-                const int e = e0 + u * G;
-                jj[u] = e < sl.y ? __ldg(idx + sl.x + e) : -1;
-                pv[u] = (e < sl.y && e > 0) ? __ldg(idx + sl.x + e - 1) : -1;      // same lines as a neighbour lane's jj
-            }
-#pragma unroll
-            for (int u = 0; u < kU; u++) {
-                use[u] = jj[u] >= 0 && jj[u] < N && jj[u] != i;
-                if (e0 + u * G < sl.y && (jj[u] < 0 || jj[u] >= N)) bad = true;
-                if (pv[u] >= jj[u] && e0 + u * G < sl.y && e0 + u * G > 0) bad = true;   // lists must ascend
-                tw[u] = use[u] ? __ldg(trunc + (jj[u] >> 5)) : 0u;
-            }
-#pragma unroll
-            for (int u = 0; u < kU; u++) {
-                const bool jfull = (tw[u] >> (jj[u] & 31)) & 1u;
-                twoway[u] = !jfull || i <= __ldg(last + jj[u]);
-                if (use[u] && twoway[u]) {
-                    // each two-way pair {a > b} is seen as a -> b and as b -> a: the two terms cancel
-                    if (jj[u] < i) chk += mix64((unsigned)i, (unsigned)jj[u]);
-                    else { chk -= mix64((unsigned)jj[u], (unsigned)i); use[u] = false; }   // taken from the higher endpoint
+                for (int u = 0; u < kU; u++) {
+                    const int e = e0 + u * G;
+                    jj[u] = e < sl.y ? __ldcs(idx + sl.x + e) : i;                  // padding reads as the self edge
                 }
-                w[u] = use[u] ? __ldcg(pl + jj[u]) : make_uint2(0u, 0u);
-            }
 #pragma unroll
-            for (int u = 0; u < kU; u++) {
-                if (!use[u] || w[u].y != li) continue;
-                const int j = jj[u];
-                const int p = (int)w[u].x;
-                if (p == ri) continue;                 // already under the same root
-                // climb from j's parent to its root, stopping early at ri (spares the hot root line)
-                int r = p;
-                while (r != ri) {
-                    const int g = (int)__ldcg(&pl[r].x);
-                    if (g == r) break;
-                    r = g;
+                for (int u = 0; u < kU; u++) {
+                    if (!TRUSTED && (unsigned)jj[u] >= (unsigned)N) { bad = true; jj[u] = i; }
+                    sj[u] = __ldg(snap + jj[u]);
                 }
-                if (r != p) pl[j].x = (unsigned)r;     // compress j straight onto the ancestor found
-                if (r == ri) continue;
-                if (twoway[u]) {
-                    ri = uf_union_roots(pl, ri, r);
-                } else {
-                    // one-way edge i -> j whose ends are not (yet) connected: park it
-                    if (uf_find(pl, ri) == uf_find(pl, r)) continue;
-                    const unsigned long long slot = atomicAdd(&scalars[2], 1ULL);
-                    if (slot < pend_cap) pend[slot] = make_int2(i, j);
+                if (!TRUSTED) {
+#pragma unroll
+                    for (int u = 0; u < kU; u++) {
+                        if (jj[u] == i) continue;
+                        const bool twoway = !any_full || !(sj[u] & kSnapFull) || i <= __ldg(last + jj[u]);
+                        // each two-way pair {a > b} is seen as a -> b and as b -> a: the two sums must agree
+                        const unsigned long long t = mix64((unsigned)max(i, jj[u]), (unsigned)min(i, jj[u]));
+                        if (twoway && jj[u] < i) chk += t;
+                        if (twoway && jj[u] > i) chk_rev += t;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kU; u++) {
+                    const unsigned x = (si ^ sj[u]) & ~kSnapFull;
+                    if (x == 0u || x > kSnapRoot) continue;        // the common cases end here
+                    const int j = jj[u];
+                    if (pl[j].y != pl[i].y) continue;
+                    const bool twoway = !(sj[u] & kSnapFull) || i <= __ldg(last + j);
+                    const int a = uf_find(pl, ri), b = uf_find(pl, (int)(sj[u] & kSnapRoot));
+                    ri = a;
+                    if (a == b) continue;
+                    if (twoway) {
+                        ri = uf_union_roots(pl, a, b);
+                    } else {
+                        // one-way edge i -> j whose ends are not connected (yet): park it
+                        const unsigned long long slot = atomicAdd(&scalars[2], 1ULL);
+                        if (slot < pend_cap) pend[slot] = make_int2(i, j);
+                    }
                 }
             }
         }
+        if (threadIdx.x == 0) s_base[(round + 1) & 1] = nxt;
+        __syncthreads();
     }
+    if (!TRUSTED) {
+        chk -= chk_rev;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) chk += __shfl_xor_sync(0xffffffffu, chk, o);
-    if ((threadIdx.x & 31) == 0 && chk) atomicAdd(&scalars[0], chk);
-    if (bad) atomicMax(&scalars[1], 1ULL);
+        for (int o = 16; o > 0; o >>= 1) chk += __shfl_xor_sync(0xffffffffu, chk, o);
+        if ((threadIdx.x & 31) == 0 && chk) atomicAdd(&scalars[0], chk);
+        if (bad) atomicMax(&scalars[1], 1ULL);
+    }
 }
 
 // Roots go to their own array: writing them back into the forest would race with the path-halving
 // stores of other threads' finds, which may re-install an intermediate ancestor after the root.
-__global__ void k_cl_flatten(uint2 *pl, int32_t *__restrict__ root, int32_t N) {
+__global__ void k_cl_flatten(uint2 *pl, const uint32_t *__restrict__ trunc, int32_t *__restrict__ root,
+                             uint32_t *__restrict__ snap, int32_t N) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v < N) root[v] = uf_find(pl, v);
+    if (v >= N) return;
+    const int r = uf_find(pl, v);
+    root[v] = r;
+    const unsigned full = (trunc[v >> 5] >> (v & 31)) & 1u;
+    snap[v] = (unsigned)r | ((pl[v].y & 31u) << 26) | (full << 31);
 }
 
 // resolve() on the label forest.  Its shortcut writes must be atomicMin: lab[x] is also the target
@@ -352,32 +443,50 @@ extern "C" size_t pg_bfs_cluster_workspace_bytes(int64_t N) {
 
 extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t *ball_query_idxs,
                                     const int32_t *start_len, int32_t N, int64_t nActive, int32_t threshold,
-                                    int generic, void *ws, size_t ws_bytes, int32_t *host_sizes, void *stream) {
+                                    int mode, void *ws, size_t ws_bytes, int32_t *host_sizes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     PG_CHECK_ARG(host_sizes, "null host_sizes");
     host_sizes[0] = host_sizes[1] = host_sizes[2] = 0;
     PG_CHECK_ARG(N >= 0 && nActive >= 0, "negative size");
+    PG_CHECK_ARG(N <= (1 << 26), "N out of range (0 .. 2^26)");
+    PG_CHECK_ARG(mode == PG_BFS_AUTO || mode == PG_BFS_GENERIC || mode == PG_BFS_TRUSTED, "unknown mode");
     if (N == 0) return PG_OK;
     PG_CHECK_ARG(semantic_label && start_len && ws && (ball_query_idxs || nActive == 0), "null pointer");
+    const int generic = mode == PG_BFS_GENERIC;
     ClWs w = cl_layout(ws, ws_bytes, N);
     if (!w.ok) { set_error("pg_bfs_cluster_count: workspace too small (%zu < %zu)", ws_bytes, w.used); return PG_EWORKSPACE; }
     const int2 *sl = (const int2 *)start_len;
     const unsigned nb = (unsigned)div_up(N, 256);
     const bool wide = nActive / N >= 12;          // lanes per neighbour list: 32 for long lists, 8 for short
     const unsigned eg = kNumSM * 8;
-
     PG_CUDA(cudaMemsetAsync(w.scalars, 0, 8 * sizeof(unsigned long long), st));
     PG_CUDA(cudaMemsetAsync(w.size, 0, ((size_t)N + 1) * sizeof(int32_t), st));
-    k_cl_prep<<<(unsigned)div_up((int64_t)N + 32, 256), 256, 0, st>>>(semantic_label, ball_query_idxs, sl, N, nActive, w.pl,
-                                                                     w.trunc, w.last, w.root, w.lab, w.scalars);
+    // sweep order = ascending segment start, on the top 16 bits of the position (two radix passes)
+    int abits = 0;
+    while ((1ll << abits) <= nActive) abits++;
+    const int shift = abits > 16 ? abits - 16 : 0;
+    k_cl_prep<<<(unsigned)div_up((int64_t)N + 32, 256), 256, 0, st>>>(semantic_label, ball_query_idxs, sl, N, nActive,
+                                                                     generic ? 0 : 1, w.pl, w.trunc, w.last, w.root, w.lab,
+                                                                     w.key0, shift, w.scalars);
     unsigned long long h[4] = {0, 0, 0, 0};
     bool use_generic = generic != 0;
+    const bool trusted = mode == PG_BFS_TRUSTED;
     if (!use_generic) {
-        if (wide) k_cl_union<32><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.trunc, w.last, N, w.pend,
-                                                     (unsigned)w.pend_cap, w.scalars);
-        else k_cl_union<8><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.trunc, w.last, N, w.pend,
-                                               (unsigned)w.pend_cap, w.scalars);
-        k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.root, N);
+        int res = 0;
+        PG_TRY(radix_sort_pairs(w.key0, nullptr, w.kA, w.vA, w.kB, w.vB, N, abits - shift < 1 ? 1 : abits - shift, w.hist,
+                                w.scan_tmp, st, &res));
+        const uint32_t *order = res == 0 ? w.vA : w.vB;
+        k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
+        k_cl_sample<<<nb, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.last, w.snap, N);
+        k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
+        const unsigned vg = kNumSM * 3;
+#define PG_VERIFY(G, T)                                                                                              \
+    k_cl_verify<G, T><<<vg, kVerThreads, 0, st>>>(ball_query_idxs, sl, order, w.pl, w.last, w.snap, N, w.pend,     \
+                                                  (unsigned)w.pend_cap, w.scalars)
+        if (trusted) { if (wide) PG_VERIFY(32, true); else PG_VERIFY(8, true); }
+        else { if (wide) PG_VERIFY(32, false); else PG_VERIFY(8, false); }
+#undef PG_VERIFY
+        k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
         PG_LAUNCH_CHECK();
     }
     PG_CUDA(cudaMemcpyAsync(h, w.scalars, sizeof(h), cudaMemcpyDeviceToHost, st));

@@ -157,7 +157,23 @@ class BallQueryBatchP(Function):
         return None, None, None, None, None
 
 
-ballquery_batch_p = BallQueryBatchP.apply
+def _stamp(idx, start_len):
+    """Provenance of a neighbour-list pair: the two tensors, as produced here and never written since
+    (torch bumps ``_version`` on every in-place write).  bfs_cluster may then skip the validation it
+    runs on foreign lists."""
+    idx._pg_lists = (start_len.data_ptr(), start_len._version, idx._version, tuple(start_len.shape))
+
+
+def _stamped(idx, start_len):
+    tag = getattr(idx, "_pg_lists", None)
+    return (tag is not None and idx.is_cuda and start_len.is_cuda
+            and tag == (start_len.data_ptr(), start_len._version, idx._version, tuple(start_len.shape)))
+
+
+def ballquery_batch_p(coords, batch_idxs, batch_offsets, radius, meanActive):
+    idx, start_len = BallQueryBatchP.apply(coords, batch_idxs, batch_offsets, radius, meanActive)
+    _stamp(idx, start_len)
+    return idx, start_len
 
 
 class BFSCluster(Function):
@@ -176,7 +192,7 @@ class BFSCluster(Function):
         assert start_len.is_contiguous()
         dev = PG_OP._compute_device(semantic_label)
         ci, co, _ = PG_OP.bfs_cluster_impl(semantic_label.to(dev), ball_query_idxs.to(dev), start_len.to(dev),
-                                           threshold)
+                                           threshold, trusted=_stamped(ball_query_idxs, start_len))
         if not semantic_label.is_cuda:
             ci, co = ci.cpu(), co.cpu()
         ctx.mark_non_differentiable(ci, co)

@@ -43,6 +43,12 @@ extern "C" {
 
 #define PG_BALLQUERY_CAP 1000 /* bfs_cluster.cu:20,38 -- at most the first 1000 neighbours by index */
 
+/* pg_bfs_cluster_count `mode` */
+#define PG_BFS_AUTO 0    /* validate the lists in the sweep; fall back to the any-digraph path if they fail */
+#define PG_BFS_GENERIC 1 /* force the any-digraph propagation path */
+#define PG_BFS_TRUSTED 2 /* the caller vouches that (idx, start_len) are pg_ballquery_* output, unmodified:
+                            in range and a truncated symmetric relation -- the sweep skips its validation */
+
 const char *pg_last_error(void);
 int pg_abi_version(void);
 
@@ -106,12 +112,13 @@ int pg_ballquery_fill(const float *xyz, int32_t n, float radius, const int32_t *
  * and cluster order are identical).  nActive = length of ball_query_idxs.  phase 1 stores
  * host_sizes = {nCluster, sumNPoint, 1 if the generic path ran}; phase 2
  * writes cluster_idxs int32 [sumNPoint,2] = (cluster_id, point) and cluster_offsets int32 [nCluster+1].
- * `generic` != 0 forces the any-digraph propagation path; 0 picks it automatically
- * when the neighbour lists are not a truncated symmetric relation.
+ * `mode`: PG_BFS_AUTO checks, in the same sweep, that the lists are a truncated symmetric relation and
+ * switches to the any-digraph propagation path when they are not; PG_BFS_GENERIC forces
+ * that path; PG_BFS_TRUSTED skips the check (only for lists that came from pg_ballquery_* untouched).
  * ---------------------------------------------------------------------------------------------- */
 size_t pg_bfs_cluster_workspace_bytes(int64_t N);
 int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t *ball_query_idxs,
-                         const int32_t *start_len, int32_t N, int64_t nActive, int32_t threshold, int generic,
+                         const int32_t *start_len, int32_t N, int64_t nActive, int32_t threshold, int mode,
                          void *ws, size_t ws_bytes, int32_t *host_sizes, void *stream);
 int pg_bfs_cluster_fill(int32_t N, int32_t nCluster, int32_t sumNPoint, void *ws, size_t ws_bytes,
                         int32_t *cluster_idxs, int32_t *cluster_offsets, void *stream);

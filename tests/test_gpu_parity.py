@@ -325,6 +325,36 @@ def test_bfs_long_chain(ops, oracle):
     assert g and co.tolist() == [0, N]
 
 
+def test_bfs_trusted_lists_by_provenance(ops, oracle):
+    """Lists that come straight from this library's ball query carry a provenance stamp and take the
+    sweep without validation; any in-place write, slice or copy drops the stamp.  Both sweeps must give
+    the reference's clusters (lists with truncation included)."""
+    from d3net_b200 import PG_OP, pointgroup_ops as pgo
+    rng = np.random.default_rng(3)
+    blobs = [rng.normal(c, 0.006, (1700, 3)) for c in ([0, 0, 0], [0.045, 0, 0], [0.4, 0.1, 0])]
+    xyz = np.concatenate(blobs + [rng.uniform(-1, 1, (3000, 3))]).astype(np.float32)
+    xyz = xyz[rng.permutation(len(xyz))]
+    n = len(xyz)
+    bi, bo = np.zeros(n, np.int32), np.array([0, n], np.int32)
+    sem = rng.integers(1, 3, n).astype(np.int32)
+    idx, sl = ops.ballquery_batch_p(cu(xyz), cu(bi), cu(bo), 0.03, 50)
+    assert pgo._stamped(idx, sl) and int((sl[:, 1] == 1000).sum()) > 0
+    ridx, rsl = oracle.ballquery_batch_p(xyz, bi, bo, 0.03)
+    rci, rco = oracle.bfs_cluster(sem, ridx, rsl, 5)
+    want = oracle.canonical_clusters(rci, rco)
+    for trusted in (True, False):
+        ci, co, generic = PG_OP.bfs_cluster_impl(cu(sem), idx, sl, 5, trusted=trusted)
+        assert not generic
+        np.testing.assert_array_equal(npy(co), rco)
+        for a, b in zip(oracle.canonical_clusters(npy(ci), npy(co)), want):
+            np.testing.assert_array_equal(a, b)
+    ci, co = ops.bfs_cluster(cu(sem), idx, sl, 5)                 # the operator picks the trusted sweep itself
+    np.testing.assert_array_equal(npy(co), rco)
+    assert not pgo._stamped(idx.clone(), sl) and not pgo._stamped(idx, sl.clone()) and not pgo._stamped(idx[:-1], sl)
+    idx[0] = idx[0]                                               # an in-place write bumps the version
+    assert not pgo._stamped(idx, sl)
+
+
 def test_bfs_empty(ops):
     z = torch.zeros(0, dtype=torch.int32).cuda()
     ci, co = ops.bfs_cluster(z, z, torch.zeros((0, 2), dtype=torch.int32).cuda(), 50)

@@ -3,7 +3,9 @@
 import csv, subprocess, sys
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 25
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern],
+which = int(sys.argv[4]) if len(sys.argv) > 4 else 0
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern,
+                      "--launch-skip", str(which), "--launch-count", "1"],
                      capture_output=True, text=True).stdout.splitlines()
 # possibly several kernels: split on "Kernel Name" rows, take the first instance
 blocks, cur = [], []
@@ -14,8 +16,7 @@ for ln in txt:
     else:
         cur.append(ln)
 if cur: blocks.append(cur)
-which = int(sys.argv[4]) if len(sys.argv) > 4 else 0
-b = blocks[which]
+b = blocks[0]
 print(b[0][:150])
 rows = list(csv.reader(b[1:]))
 hdr = rows[0]; ix = {h: i for i, h in enumerate(hdr)}
