@@ -31,9 +31,9 @@ namespace pg {
 constexpr int kCap = PG_BALLQUERY_CAP;
 constexpr int kSmallK = 128;             // sparse/dense class boundary (candidates per cell)
 constexpr int kTile = 1024;              // candidates per shared-memory tile (dense cells)
-constexpr int kWinBits = 1 << 18;        // index window covered by the rank bitmap
+constexpr int kWinBits = 160 * 1024;     // index window covered by the rank bitmap (a 150k-point scene in one)
 constexpr int kWinWords = kWinBits / 32;
-constexpr int kQMax = 1024;              // queries of one dense cell handled per pass
+constexpr int kQMax = 512;               // queries of one dense cell handled per pass
 constexpr int kDenseThreads = 256;
 constexpr int kChunkBlocks = 4;          // 32-candidate blocks per (query group, chunk) work item
 
@@ -41,6 +41,7 @@ struct BqWs {
     int4 *keys;
     GroupTable tab;
     int32_t *pslot, *cell, *ccnt, *cstart, *kc, *kb, *cand_start, *counts, *nbr, *mbase, *dense;
+    uint2 *crange;      // dense cells: (smallest, largest) candidate index
     uint32_t *cand_idx;
     uint32_t *kA, *vA, *kB, *vB;
     int32_t *hist;
@@ -69,6 +70,7 @@ static BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
     w.counts = a.take<int32_t>(n + 1);
     w.nbr = a.take<int32_t>(n * 27);
     w.dense = a.take<int32_t>(n);
+    w.crange = a.take<uint2>(n);
     w.kA = a.take<uint32_t>(n);
     w.vA = a.take<uint32_t>(n);
     w.kB = a.take<uint32_t>(n);
@@ -107,16 +109,16 @@ __global__ void __launch_bounds__(256) k_bq_neighbours(const int4 *__restrict__ 
                                                        const uint32_t *__restrict__ sorted_pt,
                                                        const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
                                                        int64_t *scalars, int32_t *__restrict__ nbr,
-                                                       int32_t *__restrict__ kc, int32_t *__restrict__ dense) {
+                                                       int32_t *__restrict__ kc, int32_t *__restrict__ dense,
+                                                       uint2 *__restrict__ crange) {
     const int64_t nc = scalars[0];
     const int lane = threadIdx.x & 31;
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nc; c += nWarps) {
         const int4 k = keys[sorted_pt[cstart[c]]];
-        int cnt = 0;
+        int cnt = 0, id = -1;
         if (lane < 27) {
             const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
-            int id;
             if (lane == 13) id = (int)c;
             else {
                 // wrapping adds: far-coordinate cells may sit at the int32 limits
@@ -132,6 +134,20 @@ __global__ void __launch_bounds__(256) k_bq_neighbours(const int4 *__restrict__ 
         if (lane == 0) {
             kc[c] = cnt;
             if (cnt > kSmallK) dense[atomicAdd((unsigned long long *)&scalars[3], 1ULL)] = (int32_t)c;
+        }
+        if (cnt > kSmallK) {          // a dense cell: the index range of its candidates (lists ascend)
+            uint32_t head = 0xffffffffu, tail = 0u;
+            if (id >= 0) {
+                const int s0 = cstart[id], l0 = ccnt[id];
+                head = sorted_pt[s0];
+                tail = sorted_pt[s0 + l0 - 1];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                head = min(head, __shfl_xor_sync(0xffffffffu, head, o));
+                tail = max(tail, __shfl_xor_sync(0xffffffffu, tail, o));
+            }
+            if (lane == 0) crange[c] = make_uint2(head, tail);
         }
     }
 }
@@ -289,6 +305,7 @@ __global__ void __launch_bounds__(256) k_bq_cells_small(const float *__restrict_
 struct DenseSmem {
     uint32_t bm[kWinWords];          // rank bitmap over the index window [s0, s0 + kWinBits)
     float4 tile[kTile];              // candidates of the current tile, ascending index (w unused)
+    uint32_t tidx[kTile];            // their indices
     float qx[kQMax], qy[kQMax], qz[kQMax];
     int32_t qcnt[kQMax];             // hits so far per query
     uint8_t qsat[kQMax];             // snapshot at the last tile boundary: the query already holds kCap hits
@@ -372,21 +389,26 @@ __device__ __forceinline__ void dense_load_window(DenseSmem &S, uint32_t from, i
     tlocal = cnt;
 }
 
-__global__ void __launch_bounds__(kDenseThreads, 3) k_bq_cells_dense(
+__global__ void __launch_bounds__(kDenseThreads, 4) k_bq_cells_dense(
     const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cstart,
     const int32_t *__restrict__ ccnt, const int32_t *__restrict__ nbr, const int32_t *__restrict__ kc,
     const int32_t *__restrict__ cand_start, const int32_t *__restrict__ mbase, const int32_t *__restrict__ dense,
-    int64_t *scalars, uint32_t *__restrict__ masks, float r2, uint32_t *__restrict__ cand_idx,
-    int32_t *__restrict__ counts, int32_t *__restrict__ kb) {
+    const uint2 *__restrict__ crange, int64_t *scalars, uint32_t *__restrict__ masks, float r2,
+    uint32_t *__restrict__ cand_idx, int32_t *__restrict__ counts, int32_t *__restrict__ kb) {
     extern __shared__ uint4 dense_smem_raw[];
     DenseSmem &S = *reinterpret_cast<DenseSmem *>(dense_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nDense = scalars[3];
+    // hit <=> d2 < r2.  d2 is a sum of squares: +0 .. +inf or the canonical NaN, so the float compare is
+    // the signed compare of the bit patterns, and its outcome is the sign bit of (bits(d2) - bits(r2)).
+    const int thr = (r2 == r2) ? __float_as_int(r2) : 0;         // NaN radius: nothing is a neighbour
+    if (tid == 0) S.cellslot = (int32_t)atomicAdd((unsigned long long *)&scalars[4], 1ULL);
     for (;;) {
-        if (tid == 0) S.cellslot = (int32_t)atomicAdd((unsigned long long *)&scalars[4], 1ULL);
         __syncthreads();
         const int64_t slot = S.cellslot;
         if (slot >= nDense) break;
+        int32_t next_slot = 0;                                   // claimed now, published after this cell's work
+        if (tid == 0) next_slot = (int32_t)atomicAdd((unsigned long long *)&scalars[4], 1ULL);
         const int c = __ldg(dense + slot);
         const int K = __ldg(kc + c), nq = __ldg(ccnt + c), qs = __ldg(cstart + c), cbase = __ldg(cand_start + c);
         const int mb = masks ? __ldg(mbase + c) : 0;
@@ -396,15 +418,10 @@ __global__ void __launch_bounds__(kDenseThreads, 3) k_bq_cells_dense(
             if (lane < 27) {
                 const int src = __ldg(nbr + (int64_t)c * 27 + lane);
                 if (src >= 0) { len = __ldg(ccnt + src); L = sorted_pt + __ldg(cstart + src); }
+                S.lptr[lane] = L;
+                S.llen[lane] = len;
             }
-            uint32_t head = len ? L[0] : 0xffffffffu, tail = len ? L[len - 1] : 0u;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                head = min(head, __shfl_xor_sync(0xffffffffu, head, o));
-                tail = max(tail, __shfl_xor_sync(0xffffffffu, tail, o));
-            }
-            if (lane < 27) { S.lptr[lane] = L; S.llen[lane] = len; }
-            if (lane == 0) { S.lo = head; S.hi = tail; }
+            if (lane == 0) { const uint2 rg = __ldg(crange + c); S.lo = rg.x; S.hi = rg.y; }
         }
         __syncthreads();
         int built_max = 0;
@@ -433,12 +450,7 @@ __global__ void __launch_bounds__(kDenseThreads, 3) k_bq_cells_dense(
                             while (word) {
                                 const int b = __ffs((int)word) - 1;
                                 word &= word - 1u;
-                                if (r >= Rlo && r < Rhi) {
-                                    const uint32_t id = s0 + ((uint32_t)w << 5) + (uint32_t)b;
-                                    const float *p = xyz + 3 * (int64_t)id;
-                                    S.tile[r - Rlo] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
-                                    cand_idx[cbase + r] = id;
-                                }
+                                if (r >= Rlo && r < Rhi) S.tidx[r - Rlo] = s0 + ((uint32_t)w << 5) + (uint32_t)b;
                                 r++;
                             }
                         }
@@ -451,7 +463,18 @@ __global__ void __launch_bounds__(kDenseThreads, 3) k_bq_cells_dense(
                     dense_load_window(S, nextfrom, w0, w1, tbase, tlocal);
                 }
                 const int ntp = (nt + 31) & ~31;
-                for (int t = nt + tid; t < ntp; t += kDenseThreads) S.tile[t] = make_float4(INFINITY, INFINITY, INFINITY, 0.f);
+                __syncthreads();
+                // coordinates: every thread fetches a few candidates, all loads in flight together
+                for (int t = tid; t < ntp; t += kDenseThreads) {
+                    float4 v = make_float4(INFINITY, INFINITY, INFINITY, 0.f);     // padding never passes the predicate
+                    if (t < nt) {
+                        const uint32_t id = S.tidx[t];
+                        const float *p = xyz + 3 * (int64_t)id;
+                        v = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+                        cand_idx[cbase + Rlo + t] = id;
+                    }
+                    S.tile[t] = v;
+                }
                 __syncthreads();
                 // ---- test: lane = query, the tile's candidates come as shared-memory broadcasts
                 const int nblk = ntp >> 5;
@@ -468,7 +491,12 @@ __global__ void __launch_bounds__(kDenseThreads, 3) k_bq_cells_dense(
                         const float4 *tp = S.tile + (b << 5);
                         unsigned m = 0;
 #pragma unroll
-                        for (int u = 0; u < 32; u++) m |= (unsigned)bq_hit(ox, oy, oz, tp[u], r2) << u;
+                        for (int u = 31; u >= 0; u--) {           // candidate 31 first: it ends up in bit 31
+                            const float4 cd = tp[u];
+                            const float dx = __fsub_rn(ox, cd.x), dy = __fsub_rn(oy, cd.y), dz = __fsub_rn(oz, cd.z);
+                            const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+                            m = __funnelshift_l((unsigned)(__float_as_int(d2) - thr), m, 1);
+                        }
                         cnt += __popc(m);
                         if (masks && live) masks[mb + (int64_t)((Rlo >> 5) + b) * nq + sg0 + qi] = m;
                     }
@@ -488,7 +516,7 @@ __global__ void __launch_bounds__(kDenseThreads, 3) k_bq_cells_dense(
             built_max = max(built_max, built);
             __syncthreads();
         }
-        if (tid == 0) kb[c] = built_max;
+        if (tid == 0) { kb[c] = built_max; S.cellslot = next_slot; }
     }
 }
 
@@ -666,7 +694,7 @@ extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs,
     PG_CUDA(cudaMemsetAsync(w.ccnt + n, 0, sizeof(int32_t), st));
     PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
     const unsigned gsm = kNumSM * 8;
-    k_bq_neighbours<<<kNumSM * 16, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense);
+    k_bq_neighbours<<<kNumSM * 16, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense, w.crange);
     k_bq_clear_tail<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n + 1);   // kc beyond nCells must scan as 0
     PG_TRY(scan_exclusive_i32(w.kc, w.cand_start, (int64_t)n + 1, w.scalars + 1, w.scan_tmp, st));
     k_bq_mask_sizes<<<gsm, 256, 0, st>>>(w.ccnt, w.kc, w.scalars, n + 1, w.mbase);
@@ -693,13 +721,14 @@ extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int
     const uint32_t *sorted_pt = bq_sorted(w, n);
     const float r2 = radius * radius;
     PG_CUDA(cudaFuncSetAttribute(k_bq_cells_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DenseSmem)));
+    PG_CUDA(cudaMemsetAsync(w.scalars + 4, 0, sizeof(int64_t), st));   // the dense kernel's work counter
     const int64_t gsmall_want = div_up(n, 8);
     const unsigned gsmall = (unsigned)(gsmall_want < (int64_t)kNumSM * 16 ? gsmall_want : (int64_t)kNumSM * 16);
     k_bq_cells_small<<<gsmall, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars,
                                              masks, r2, w.cand_idx, w.counts, w.kb);
-    k_bq_cells_dense<<<kNumSM * 3, kDenseThreads, sizeof(DenseSmem), st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc,
-                                                                            w.cand_start, w.mbase, w.dense, w.scalars, masks,
-                                                                            r2, w.cand_idx, w.counts, w.kb);
+    k_bq_cells_dense<<<kNumSM * 4, kDenseThreads, sizeof(DenseSmem), st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc,
+                                                                            w.cand_start, w.mbase, w.dense, w.crange, w.scalars,
+                                                                            masks, r2, w.cand_idx, w.counts, w.kb);
     // starts (reuse pslot) in query order, then the interleaved (start, len) rows per point
     PG_TRY(scan_exclusive_i32(w.counts, w.pslot, n, w.scalars + 2, w.scan_tmp, st));
     k_bq_start_len<<<(unsigned)div_up(n, 256), 256, 0, st>>>(sorted_pt, w.counts, w.pslot, n, (int2 *)start_len);

@@ -204,10 +204,14 @@ __global__ void k_cl_sample(const int32_t *__restrict__ idx, const int2 *__restr
 }
 
 // verify: the single sweep over all edges.  G lanes share one point's list (coalesced, streaming reads of
-// idx); lists are taken in `order` (ascending segment start) in chunks handed out by an atomic counter,
-// so the lists a block works on at any time belong to neighbouring points and their snapshot reads
-// mostly hit L1.  TRUSTED: the caller vouches that the lists are this library's ball-query output
-// (in range, a truncated symmetric relation) -- no range checks, no checksum.
+// idx).  Lists are taken in `order` (ascending segment start): a block claims a chunk of consecutive
+// lists from an atomic counter, so the lists it works on at any time belong to neighbouring points
+// and their snapshot reads mostly hit L1.  Everything with latency is taken one step ahead: the next
+// chunk is claimed and its list headers (point, start, length, snapshot) are fetched into shared
+// memory while the current chunk is processed; inside a chunk every lane group pulls lists from a
+// shared counter and always has the idx loads of its NEXT trip in flight, across list boundaries.
+// TRUSTED: the caller vouches that the lists are this library's ball-query output (in range, a
+// truncated symmetric relation) -- no range checks, no checksum.
 constexpr int kVerThreads = 512;
 
 template <int G, bool TRUSTED>
@@ -218,35 +222,89 @@ __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__r
                                                               int2 *__restrict__ pend, unsigned pend_cap,
                                                               unsigned long long *scalars) {
     constexpr int kGroups = kVerThreads / G;
-    constexpr int kChunk = kGroups * 4;
+    constexpr int kChunk = kGroups * 8 > kVerThreads ? kVerThreads : kGroups * 8;   // lists per claim (<= one per thread)
+    constexpr int kU = 4;
+    __shared__ int4 hdr[2][kChunk];              // (point, start, length, snapshot word) per list of a chunk
     __shared__ long long s_base[2];
-    const int sub = threadIdx.x % G, grp = threadIdx.x / G;
+    __shared__ int s_take[2];                    // next unclaimed list of the chunk
+    const int tid = threadIdx.x, sub = tid % G;
+    const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) / G * G));
     unsigned long long chk = 0, chk_rev = 0;
     bool bad = false;
     const bool any_full = scalars[7] != 0;       // some list holds kCap entries: reverse edges may be missing
-    if (threadIdx.x == 0) s_base[0] = (long long)atomicAdd(&scalars[6], (unsigned long long)kChunk);
-    __syncthreads();
-    for (int round = 0;; round++) {
-        const long long base = s_base[round & 1];
-        if (base >= N) break;
-        // the next chunk is claimed now and published after this one's work: its latency hides behind the lists
-        long long nxt = 0;
-        if (threadIdx.x == 0) nxt = (long long)atomicAdd(&scalars[6], (unsigned long long)kChunk);
-        const long long stop = base + kChunk < N ? base + kChunk : N;
-        for (long long p = base + grp; p < stop; p += kGroups) {
+
+    auto fetch_header = [&](long long base, int4 &h) {
+        h = make_int4(0, 0, 0, 0);
+        const long long p = base + tid;
+        if (tid < kChunk && p < N) {
             const int i = (int)__ldg(order + p);
             const int2 sl = __ldg(start_len + i);
-            const unsigned si = __ldg(snap + i);
-            int ri = (int)(si & kSnapRoot);          // current root of i's set as far as this group knows
-            constexpr int kU = 4;
-            for (int e0 = sub; e0 < sl.y; e0 += kU * G) {
-                int jj[kU];
-                unsigned sj[kU];
+            h = make_int4(i, sl.x, sl.y, (int)__ldg(snap + i));
+        }
+    };
+    if (tid == 0) {
+        s_base[0] = (long long)atomicAdd(&scalars[6], (unsigned long long)kChunk);
+        s_base[1] = (long long)atomicAdd(&scalars[6], (unsigned long long)kChunk);
+        s_take[0] = 0;
+        s_take[1] = 0;
+    }
+    __syncthreads();
+    {
+        int4 h;
+        fetch_header(s_base[0], h);
+        if (tid < kChunk) hdr[0][tid] = h;
+    }
+    __syncthreads();
+    for (int round = 0;; round++) {
+        const int cur = round & 1;
+        const long long base = s_base[cur];
+        if (base >= N) break;
+        const int nl = (int)(N - base < kChunk ? N - base : kChunk);
+        // one step ahead: headers of the next chunk (its base was claimed a round ago), claim of the one after
+        const long long base1 = s_base[cur ^ 1];
+        int4 h1;
+        fetch_header(base1, h1);
+        long long claim = 0;
+        if (tid == 0) claim = (long long)atomicAdd(&scalars[6], (unsigned long long)kChunk);
+
+        auto grab = [&]() {                       // next list of the chunk for this lane group (-1: none left)
+            int L = 0;
+            if (sub == 0) L = atomicAdd(&s_take[cur], 1);
+            L = __shfl_sync(gmask, L, 0, G);
+            return L < nl ? L : -1;
+        };
+        auto load_trip = [&](const int4 &H, int e0, int (&nj)[kU]) {
 #pragma unroll
-                for (int u = 0; u < kU; u++) {
-                    const int e = e0 + u * G;
-                    jj[u] = e < sl.y ? __ldcs(idx + sl.x + e) : i;                  // padding reads as the self edge
+            for (int u = 0; u < kU; u++) {
+                const int e = e0 + u * G;
+                nj[u] = e < H.z ? __ldcs(idx + H.y + e) : H.x;        // padding reads as the self edge
+            }
+        };
+        int L = grab();
+        if (L >= 0) {
+            int4 H = hdr[cur][L];
+            int e0 = sub;
+            int nj[kU];
+            load_trip(H, e0, nj);
+            int ri = (int)((unsigned)H.w & kSnapRoot);   // current root of the list owner's set as far as this group knows
+            for (;;) {
+                int jj[kU];
+#pragma unroll
+                for (int u = 0; u < kU; u++) jj[u] = nj[u];
+                // the next trip (possibly of the next list) goes in flight before this one is looked at
+                int4 H2 = H;
+                int e2 = e0 + kU * G;
+                bool more = true;
+                if (e2 - sub >= H.z) {
+                    const int L2 = grab();
+                    more = L2 >= 0;
+                    if (more) { H2 = hdr[cur][L2]; e2 = sub; }
                 }
+                if (more) load_trip(H2, e2, nj);
+
+                const int i = H.x;
+                const unsigned si = (unsigned)H.w;
+                unsigned sj[kU];
 #pragma unroll
                 for (int u = 0; u < kU; u++) {
                     if (!TRUSTED && (unsigned)jj[u] >= (unsigned)N) { bad = true; jj[u] = i; }
@@ -281,9 +339,15 @@ __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__r
                         if (slot < pend_cap) pend[slot] = make_int2(i, j);
                     }
                 }
+                if (!more) break;
+                if (H2.x != H.x) ri = (int)((unsigned)H2.w & kSnapRoot);
+                H = H2;
+                e0 = e2;
             }
         }
-        if (threadIdx.x == 0) s_base[(round + 1) & 1] = nxt;
+        __syncthreads();                          // everyone is done with hdr[cur], s_take[cur], s_base[cur]
+        if (tid < kChunk) hdr[cur ^ 1][tid] = h1;   // (published for the next round by the barrier below)
+        if (tid == 0) { s_base[cur] = claim; s_take[cur] = 0; }
         __syncthreads();
     }
     if (!TRUSTED) {
