@@ -69,6 +69,8 @@ _int = ctypes.c_int
 SIGNATURES = {
     "pg_last_error": (ctypes.c_char_p, []),
     "pg_abi_version": (_int, []),
+    "pg_kernel_timing": (None, [_int]),
+    "pg_kernel_timing_report": (_sz, [ctypes.c_char_p, _sz]),
     "pg_voxelize_idx_workspace_bytes": (_sz, [_i64]),
     "pg_voxelize_idx_map": (_int, [_vp, _i64, _int, _vp, _vp, _sz, _vp, _vp]),
     "pg_voxelize_idx_fill": (_int, [_vp, _vp, _i64, _i32, _i32, _int, _vp, _sz, _vp, _vp, _vp]),
@@ -119,3 +121,21 @@ def check(rc, what):
     if rc != 0:
         msg = lib().pg_last_error()
         raise PgError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else ""))
+
+
+def kernel_timing(enable):
+    """Switch the library's per-kernel CUDA-event timers on (clearing them) or off."""
+    lib().pg_kernel_timing(1 if enable else 0)
+
+
+def kernel_timing_report():
+    """{kernel name: (launches, total ms)} of the launches since kernel_timing(True); waits for them."""
+    L = lib()
+    n = L.pg_kernel_timing_report(None, 0)
+    buf = ctypes.create_string_buffer(n + 1)
+    L.pg_kernel_timing_report(buf, n + 1)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.split("\t")
+        out[name] = (int(cnt), float(ms))
+    return out

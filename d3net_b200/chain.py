@@ -70,11 +70,11 @@ def _gather_rows(ops, feats, idx):
 
 
 def get_batch_offsets(batch_idxs, batch_size):
-    """model/pointgroup.py:112-122 without the Python loop."""
-    counts = torch.bincount(batch_idxs.long(), minlength=batch_size)[:batch_size]
-    out = torch.zeros(batch_size + 1, dtype=torch.int32, device=batch_idxs.device)
-    out[1:] = torch.cumsum(counts, 0).int()
-    return out
+    """model/pointgroup.py:112-122 without the Python loop.  The points of a collated batch are laid out
+    scene after scene (lib/dataset/pipeline.py:955-963), so batch_idxs ascends and the offsets are the
+    positions where each scene id would be inserted."""
+    bounds = torch.arange(batch_size + 1, dtype=batch_idxs.dtype, device=batch_idxs.device)
+    return torch.searchsorted(batch_idxs, bounds).int()
 
 
 def clusters_voxelization(ops, clusters_idx, clusters_offset, feats, coords, fullscale, scale, mode, rand6,

@@ -694,7 +694,8 @@ extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs,
     PG_CUDA(cudaMemsetAsync(w.ccnt + n, 0, sizeof(int32_t), st));
     PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
     const unsigned gsm = kNumSM * 8;
-    k_bq_neighbours<<<kNumSM * 16, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense, w.crange);
+    { PG_KTIME("k_bq_neighbours", st);
+    k_bq_neighbours<<<kNumSM * 16, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense, w.crange); }
     k_bq_clear_tail<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n + 1);   // kc beyond nCells must scan as 0
     PG_TRY(scan_exclusive_i32(w.kc, w.cand_start, (int64_t)n + 1, w.scalars + 1, w.scan_tmp, st));
     k_bq_mask_sizes<<<gsm, 256, 0, st>>>(w.ccnt, w.kc, w.scalars, n + 1, w.mbase);
@@ -724,11 +725,13 @@ extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int
     PG_CUDA(cudaMemsetAsync(w.scalars + 4, 0, sizeof(int64_t), st));   // the dense kernel's work counter
     const int64_t gsmall_want = div_up(n, 8);
     const unsigned gsmall = (unsigned)(gsmall_want < (int64_t)kNumSM * 16 ? gsmall_want : (int64_t)kNumSM * 16);
+    { PG_KTIME("k_bq_cells_small", st);
     k_bq_cells_small<<<gsmall, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars,
-                                             masks, r2, w.cand_idx, w.counts, w.kb);
+                                             masks, r2, w.cand_idx, w.counts, w.kb); }
+    { PG_KTIME("k_bq_cells_dense", st);
     k_bq_cells_dense<<<kNumSM * 4, kDenseThreads, sizeof(DenseSmem), st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc,
                                                                             w.cand_start, w.mbase, w.dense, w.crange, w.scalars,
-                                                                            masks, r2, w.cand_idx, w.counts, w.kb);
+                                                                            masks, r2, w.cand_idx, w.counts, w.kb); }
     // starts (reuse pslot) in query order, then the interleaved (start, len) rows per point
     PG_TRY(scan_exclusive_i32(w.counts, w.pslot, n, w.scalars + 2, w.scan_tmp, st));
     k_bq_start_len<<<(unsigned)div_up(n, 256), 256, 0, st>>>(sorted_pt, w.counts, w.pslot, n, (int2 *)start_len);
@@ -755,6 +758,7 @@ extern "C" int pg_ballquery_fill(const float *xyz, int32_t n, float radius, cons
     if (!w.ok) { set_error("pg_ballquery_fill: workspace too small"); return PG_EWORKSPACE; }
     const uint32_t *sorted_pt = bq_sorted(w, n);
     const float r2 = radius * radius;
+    PG_KTIME(masks ? "k_bq_fill_mask" : "k_bq_fill", st);
     if (masks)
         k_bq_fill_mask<<<kNumSM * 8, 256, 0, st>>>(sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx, w.mbase,
                                                    masks, (const int2 *)start_len, n, idx);

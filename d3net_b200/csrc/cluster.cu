@@ -541,14 +541,16 @@ extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t
                                 w.scan_tmp, st, &res));
         const uint32_t *order = res == 0 ? w.vA : w.vB;
         k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
-        k_cl_sample<<<nb, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.last, w.snap, N);
+        { PG_KTIME("k_cl_sample", st);
+        k_cl_sample<<<nb, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.last, w.snap, N); }
         k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
         const unsigned vg = kNumSM * 3;
 #define PG_VERIFY(G, T)                                                                                              \
     k_cl_verify<G, T><<<vg, kVerThreads, 0, st>>>(ball_query_idxs, sl, order, w.pl, w.last, w.snap, N, w.pend,     \
                                                   (unsigned)w.pend_cap, w.scalars)
+        { PG_KTIME(trusted ? "k_cl_verify<trusted>" : "k_cl_verify<validating>", st);
         if (trusted) { if (wide) PG_VERIFY(32, true); else PG_VERIFY(8, true); }
-        else { if (wide) PG_VERIFY(32, false); else PG_VERIFY(8, false); }
+        else { if (wide) PG_VERIFY(32, false); else PG_VERIFY(8, false); } }
 #undef PG_VERIFY
         k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
         PG_LAUNCH_CHECK();
@@ -586,7 +588,8 @@ extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t
             if (!changed) break;
         }
     }
-    k_cl_label<<<nb, 256, 0, st>>>(w.root, w.lab, N, w.size, w.key0);
+    { PG_KTIME("k_cl_label", st);
+    k_cl_label<<<nb, 256, 0, st>>>(w.root, w.lab, N, w.size, w.key0); }
     k_cl_keep<<<nb, 256, 0, st>>>(w.key0, w.size, N, threshold, w.cid);
     PG_CUDA(cudaMemsetAsync(w.cid + N, 0, sizeof(int32_t), st));
     PG_TRY(scan_exclusive_i32(w.cid, w.cid, (int64_t)N + 1, (int64_t *)(w.scalars + 4), w.scan_tmp, st));

@@ -45,6 +45,19 @@ void set_error(const char *fmt, ...);
         if (_rc != PG_OK) return _rc; \
     } while (0)
 
+// Kernel timing (pg_kernel_timing): when switched on, a launch wrapped in a KTimer scope is bracketed by
+// two CUDA events on its own stream; pg_kernel_timing_report() sums them per kernel name.  Off by
+// default (one predictable branch per launch); bench.py uses it for the per-kernel roofline numbers.
+struct KTimer {
+    int slot;
+    cudaStream_t st;
+    KTimer(const char *name, cudaStream_t stream);
+    ~KTimer();
+};
+#define PG_KT_CAT2(a, b) a##b
+#define PG_KT_CAT(a, b) PG_KT_CAT2(a, b)
+#define PG_KTIME(name, st) pg::KTimer PG_KT_CAT(_pg_kt_, __LINE__)(name, st)
+
 inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b = 256) { return (a + b - 1) / b * b; }
 

@@ -1,6 +1,12 @@
 // Device-wide primitives used by several ops: exclusive scan, stable LSD radix sort of pairs, and
 // hash grouping of int4 keys (first-occurrence numbering).  Hand-written; no CUB/Thrust.
 #include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -383,6 +389,65 @@ int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot, int3
 }
 
 }  // namespace pg
+
+// ---------------------------------------------------------------------------------------------
+// kernel timing
+// ---------------------------------------------------------------------------------------------
+namespace pg {
+namespace {
+struct KtRec { const char *name; cudaEvent_t a, b; };
+std::mutex g_kt_mu;
+std::vector<KtRec> g_kt;
+bool g_kt_on = false;
+}  // namespace
+
+KTimer::KTimer(const char *name, cudaStream_t stream) : slot(-1), st(stream) {
+    if (!g_kt_on) return;
+    KtRec r{name, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    std::lock_guard<std::mutex> lk(g_kt_mu);
+    slot = (int)g_kt.size();
+    g_kt.push_back(r);
+}
+KTimer::~KTimer() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_kt_mu);
+    cudaEventRecord(g_kt[slot].b, st);
+}
+}  // namespace pg
+
+extern "C" void pg_kernel_timing(int enable) {
+    std::lock_guard<std::mutex> lk(pg::g_kt_mu);
+    for (auto &r : pg::g_kt) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    pg::g_kt.clear();
+    pg::g_kt_on = enable != 0;
+}
+
+extern "C" size_t pg_kernel_timing_report(char *buf, size_t cap) {
+    std::lock_guard<std::mutex> lk(pg::g_kt_mu);
+    std::map<std::string, std::pair<long long, double>> agg;
+    for (auto &r : pg::g_kt) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) == cudaSuccess && cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            auto &e = agg[r.name];
+            e.first += 1;
+            e.second += ms;
+        }
+    }
+    std::string out;
+    char line[256];
+    for (auto &kv : agg) {
+        snprintf(line, sizeof(line), "%s\t%lld\t%.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        out += line;
+    }
+    if (buf && cap) {
+        const size_t n = out.size() < cap - 1 ? out.size() : cap - 1;
+        memcpy(buf, out.data(), n);
+        buf[n] = 0;
+    }
+    return out.size();
+}
 
 extern "C" const char *pg_last_error(void) { return pg::last_error(); }
 extern "C" int pg_abi_version(void) { return 1; }

@@ -346,6 +346,7 @@ extern "C" int pg_sec_mean(const float *inp, const int32_t *offsets, float *out,
     if ((int64_t)nProposal * C == 0) return PG_OK;
     PG_CHECK_ARG(offsets && out, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    PG_KTIME("k_sec_mean", st);
     if (C <= 4 * kMeanThreads) {
         const unsigned grid = (unsigned)(nProposal < kNumSM * 8 ? nProposal : kNumSM * 8);
         k_sec_mean<<<grid, kMeanThreads, 0, st>>>(inp, offsets, out, nProposal, C);

@@ -207,7 +207,8 @@ static int voxelize_launch(bool fp, const float *src, float *dst, const int32_t 
 #define PG_VOX(VV)                                                                                     \
     if (fp) k_voxelize_fp<VV><<<grid, 256, 0, st>>>(src, dst, rules, M, W, Cv, average);               \
     else k_voxelize_bp<VV><<<grid, 256, 0, st>>>(src, dst, rules, M, W, Cv, average)
-    if (V == 4) { PG_VOX(4); } else if (V == 2) { PG_VOX(2); } else { PG_VOX(1); }
+    { PG_KTIME(fp ? "k_voxelize_fp" : "k_voxelize_bp", st);
+    if (V == 4) { PG_VOX(4); } else if (V == 2) { PG_VOX(2); } else { PG_VOX(1); } }
 #undef PG_VOX
     PG_LAUNCH_CHECK();
     return PG_OK;
@@ -267,7 +268,8 @@ extern "C" int pg_voxelize_idx_fill(const int64_t *coords, const int32_t *input_
     const int W = maxActive + 1;
     const int64_t total = (int64_t)M * W;
     const unsigned grid = (unsigned)(div_up(total, 256) < (int64_t)kNumSM * 32 ? div_up(total, 256) : (int64_t)kNumSM * 32);
-    k_vox_fill<<<grid, 256, 0, st>>>(coords, w.cnt, w.voff, sorted, M, W, mode, output_coords, output_map);
+    { PG_KTIME("k_vox_fill", st);
+    k_vox_fill<<<grid, 256, 0, st>>>(coords, w.cnt, w.voff, sorted, M, W, mode, output_coords, output_map); }
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

@@ -52,6 +52,13 @@ extern "C" {
 const char *pg_last_error(void);
 int pg_abi_version(void);
 
+/* Measurement aid (no reference counterpart): with timing enabled the library brackets its main kernels
+ * with CUDA events on the launching stream.  pg_kernel_timing(1) clears and starts, (0) clears and stops;
+ * the report waits for the recorded events and writes one "name<TAB>launches<TAB>total_ms" line per
+ * kernel into buf (NUL-terminated, truncated to cap) and returns the untruncated length. */
+void pg_kernel_timing(int enable);
+size_t pg_kernel_timing_report(char *buf, size_t cap);
+
 /* ------------------------------------------------------------------------------------------------
  * voxelize_idx     replaces PG_OP.voxelize_idx (src/pointgroup_ops.cpp:13, voxelize.cpp:11-152)
  * coords: int64 [N,4] (batch, x, y, z); every column is narrowed to int32 like the reference's
