@@ -119,6 +119,7 @@ def kernel_algorithmic_bytes(batch, out):
     nP = out["proposals_offset"].numel() - 1
     Mc = out["proposals_voxel_feats"].shape[0]
     nA = out["nActive_shift"] + out["nActive_raw"]
+    maps = out["v2p_map_numel"] + out["proposals_v2p_map_numel"]      # int32 [M, maxActive + 1] rows
     return {
         # ball query, count phase: coords + scene ids in, (start, len) rows out -- per set
         "k_bq_cells_dense": 2 * (12 * n + 4 * n + 8 * n),
@@ -128,9 +129,9 @@ def kernel_algorithmic_bytes(batch, out):
         "k_cl_verify<trusted>": 4 * nA + 2 * (8 * n + 4 * n),
         "k_cl_verify<validating>": 4 * nA + 2 * (8 * n + 4 * n),
         # voxelization: features in, voxel means out, one map row per voxel (scene C=134, clusters C=16)
-        "k_voxelize_fp": 4 * N * C + 4 * M * C + 8 * M + 4 * S * 16 + 4 * Mc * 16 + 8 * Mc,
-        # voxelization_idx, fill phase: coords in (first point of each voxel), coords + map rows out
-        "k_vox_fill": 32 * M + 32 * M + 8 * M + 32 * Mc + 32 * Mc + 8 * Mc,
+        "k_voxelize_fp": 4 * N * C + 4 * M * C + 4 * S * 16 + 4 * Mc * 16 + 4 * maps,
+        # voxelization_idx, fill phase: coords in (first point of each voxel), coords + zero-padded map rows out
+        "k_vox_fill": 32 * M + 32 * M + 32 * Mc + 32 * Mc + 4 * maps,
         "k_sec_mean": 4 * S * 3 + 4 * (nP + 1) + 4 * nP * 3,
     }
 

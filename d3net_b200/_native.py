@@ -100,11 +100,12 @@ def lib():
     """The loaded library with argtypes bound.  Raises if it is absent -- there is no CPU path."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("PG_B200_LIB", LIB_PATH)      # kernel-variant experiments load another build
+        if not os.path.exists(path):
             raise RuntimeError(
                 "d3net_b200: %s is missing. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
-        L = ctypes.CDLL(LIB_PATH)
+                "(nvcc, sm_100a). There is no CPU fallback." % path)
+        L = ctypes.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)          # AttributeError here = header / library mismatch
             fn.restype = res

@@ -156,6 +156,7 @@ def proposal_chain(ops, batch, rand6=None, timer=None, trace=None):
     if trace is not None:
         trace["voxelization(scene)"] = (batch["feats"], v2p_map, voxel_feats)
     out["voxel_locs"], out["voxel_feats"], out["p2v_map"] = voxel_locs, voxel_feats, p2v_map
+    out["v2p_map_numel"] = v2p_map.numel()
 
     # ---- clustering on the predicted-object points (pointgroup.py:284-316)
     semantic_preds = batch["semantic_preds"]
@@ -210,6 +211,7 @@ def proposal_chain(ops, batch, rand6=None, timer=None, trace=None):
         scenes.SCORE_SCALE, scenes.SCORE_MODE, rand6, timer, trace)
     out["proposals_center"], out["proposals_size"] = proposals_center, proposals_size
     out["proposals_voxel_feats"], out["proposals_voxel_coords"] = prop_voxel_feats, prop_voxel_coords
+    out["proposals_v2p_map_numel"] = _v2p.numel()
 
     # ---- score features per point and proposal pooling (pointgroup.py:332-334; the score U-Net is
     #      out of scope, its per-voxel output is stood in for by its input)

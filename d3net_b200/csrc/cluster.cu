@@ -160,33 +160,33 @@ __device__ __forceinline__ int uf_union_roots(uint2 *pl, int a, int b) {
     }
 }
 
-// a, b: distinct nodes that were roots a moment ago.  Plain loads first: most callers find the pair
-// already united by somebody else and never issue the atomic.
-__device__ __forceinline__ int uf_union_checked(uint2 *pl, int a, int b) {
-    a = uf_find(pl, a);
-    b = uf_find(pl, b);
-    return uf_union_roots(pl, a, b);
-}
-
 // Snapshot word per point, written by k_cl_flatten and read (through the read-only L1 path) once per edge
 // by the sweep:  [31] the point's list is full   [30:26] low 5 bits of its label   [25:0] its root.
 // Equal roots = already connected.  Different label bits = never connected.  Only a pair that differs in
 // the root field alone needs the forest.
 constexpr unsigned kSnapRoot = 0x03ffffffu, kSnapLabel = 0x7c000000u, kSnapFull = 0x80000000u;
 
-// sample: after the first flatten every point probes two more of its neighbours (middle and last entry
-// of its list) and unites the two trees when their snapshot roots differ.  Only two-way edges between
-// equal labels are used, exactly the edges the verify sweep would unite along: this is a head start
-// that leaves the sweep almost nothing but "same root" answers.
+// sample rounds: between two flattens every point probes two of its neighbours and, where the snapshot
+// roots differ, tries to hang the larger root under the smaller with ONE compare-and-swap -- no find, no
+// retry: if the larger root has been taken meanwhile the link is simply dropped (some other link took
+// it; whatever stays unmerged is merged by the verify sweep).  Every root that sees a smaller
+// neighbouring root is hooked by somebody, so each round shrinks the forest Boruvka-fashion.  Only
+// two-way edges between equal labels are used, exactly the edges the sweep would unite along.
+constexpr int kSampleRounds = 1;
+
 __global__ void k_cl_sample(const int32_t *__restrict__ idx, const int2 *__restrict__ start_len, uint2 *pl,
-                            const int32_t *__restrict__ last, const uint32_t *__restrict__ snap, int32_t N) {
+                            const int32_t *__restrict__ last, const uint32_t *__restrict__ snap, int32_t N, int round) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int2 sl = start_len[i];
     if (sl.y <= 1) return;
+    // round 0: last and middle entry; later rounds: the quarter points, the eighths, ...
+    const int den = 2 << round;
+    const int p0 = round == 0 ? sl.y - 1 : (int)(((long long)sl.y) / den);
+    const int p1 = round == 0 ? sl.y >> 1 : (int)(((long long)sl.y * (den - 1)) / den);
     int jj[2];
-    jj[0] = __ldg(idx + sl.x + (sl.y >> 1));
-    jj[1] = __ldg(idx + sl.x + sl.y - 1);
+    jj[0] = __ldg(idx + sl.x + p0);
+    jj[1] = __ldg(idx + sl.x + p1);
     const unsigned si = __ldg(snap + i);
     unsigned sj[2];
 #pragma unroll
@@ -199,7 +199,10 @@ __global__ void k_cl_sample(const int32_t *__restrict__ idx, const int2 *__restr
         if (x == 0u || x > kSnapRoot) continue;                      // same tree, or different label bits
         if (pl[j].y != pl[i].y) continue;
         if ((sj[u] & kSnapFull) && i > __ldg(last + j)) continue;    // j does not list i back
-        ri = uf_union_checked(pl, ri, (int)(sj[u] & kSnapRoot));
+        const int rj = (int)(sj[u] & kSnapRoot);
+        if (rj == ri) continue;
+        const int hi = max(ri, rj), lo = min(ri, rj);
+        if (atomicCAS(&pl[hi].x, (unsigned)hi, (unsigned)lo) == (unsigned)hi && hi == ri) ri = lo;
     }
 }
 
@@ -367,6 +370,7 @@ __global__ void k_cl_flatten(uint2 *pl, const uint32_t *__restrict__ trunc, int3
     if (v >= N) return;
     const int r = uf_find(pl, v);
     root[v] = r;
+    pl[v].x = (unsigned)r;        // a hint only (another thread's halving store may replace it with another ancestor)
     const unsigned full = (trunc[v >> 5] >> (v & 31)) & 1u;
     snap[v] = (unsigned)r | ((pl[v].y & 31u) << 26) | (full << 31);
 }
@@ -541,9 +545,12 @@ extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t
                                 w.scan_tmp, st, &res));
         const uint32_t *order = res == 0 ? w.vA : w.vB;
         k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
-        { PG_KTIME("k_cl_sample", st);
-        k_cl_sample<<<nb, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.last, w.snap, N); }
-        k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
+        for (int round = 0; round < kSampleRounds; round++) {
+            { PG_KTIME("k_cl_sample", st);
+            k_cl_sample<<<nb, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.last, w.snap, N, round); }
+            PG_KTIME("k_cl_flatten", st);
+            k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
+        }
         const unsigned vg = kNumSM * 3;
 #define PG_VERIFY(G, T)                                                                                              \
     k_cl_verify<G, T><<<vg, kVerThreads, 0, st>>>(ball_query_idxs, sl, order, w.pl, w.last, w.snap, N, w.pend,     \

@@ -63,21 +63,49 @@ __global__ void k_max_i32(const int32_t *__restrict__ v, const int64_t *__restri
 
 // output_map rows [cnt, p0 < p1 < ..., 0-pad] (voxelize.cpp:139-149; modes 0/1/2: :121-138) and
 // output_coords = coords row of rule[1] (voxelize.cpp:39-47)
+__device__ __forceinline__ int vox_map_entry(const uint32_t *__restrict__ sorted, int mode, int j, int n, int off) {
+    if (mode == 3 || mode == 4) return (j == 0) ? n : (j <= n ? (int)sorted[off + j - 1] : 0);
+    return (j == 0) ? 1 : (int)sorted[mode == 2 ? off + n - 1 : off];
+}
+
+// VEC: every thread produces four consecutive entries of the flat [M * W] map and stores them as one
+// int4 -- one division per four entries, fully coalesced 16-byte stores (most of the map is padding).
+template <bool VEC>
 __global__ void k_vox_fill(const int64_t *__restrict__ coords, const int32_t *__restrict__ cnt,
                            const int32_t *__restrict__ voff, const uint32_t *__restrict__ sorted, int32_t M,
                            int32_t W, int mode, int64_t *__restrict__ out_coords, int32_t *__restrict__ out_map) {
     const int64_t total = (int64_t)M * W;
-    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
-         t += (int64_t)gridDim.x * blockDim.x) {
-        const int v = (int)(t / W), j = (int)(t - (int64_t)v * W);
-        const int n = cnt[v], off = voff[v];
-        int val;
-        if (mode == 3 || mode == 4) {
-            val = (j == 0) ? n : (j <= n ? (int)sorted[off + j - 1] : 0);
-        } else {
-            val = (j == 0) ? 1 : (int)sorted[mode == 2 ? off + n - 1 : off];
+    if (VEC) {
+        const int64_t quads = total >> 2;
+        {   // the (up to three) entries past the last full quad
+            const int64_t t = (quads << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+            if (t < total) {
+                const int v = (int)(t / W), j = (int)(t - (int64_t)v * W);
+                out_map[t] = vox_map_entry(sorted, mode, j, cnt[v], voff[v]);
+            }
         }
-        out_map[t] = val;
+        for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
+            const int64_t t = q << 2;
+            int v = (int)(t / W), j = (int)(t - (int64_t)v * W);
+            int n = cnt[v], off = voff[v];
+            int val[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                val[u] = vox_map_entry(sorted, mode, j, n, off);
+                if (++j == W && u < 3) {
+                    j = 0;
+                    ++v;                                 // v < M: entry t + u + 1 exists
+                    n = cnt[v];
+                    off = voff[v];
+                }
+            }
+            __stcs(reinterpret_cast<int4 *>(out_map) + q, make_int4(val[0], val[1], val[2], val[3]));
+        }
+    } else {
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+            const int v = (int)(t / W), j = (int)(t - (int64_t)v * W);
+            out_map[t] = vox_map_entry(sorted, mode, j, cnt[v], voff[v]);
+        }
     }
     const int64_t total_c = (int64_t)M * 4;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total_c;
@@ -267,9 +295,12 @@ extern "C" int pg_voxelize_idx_fill(const int64_t *coords, const int32_t *input_
     PG_TRY(scan_exclusive_i32(w.cnt, w.voff, M, nullptr, w.scan_tmp, st));
     const int W = maxActive + 1;
     const int64_t total = (int64_t)M * W;
-    const unsigned grid = (unsigned)(div_up(total, 256) < (int64_t)kNumSM * 32 ? div_up(total, 256) : (int64_t)kNumSM * 32);
+    const bool vec = ((uintptr_t)output_map & 15u) == 0;
+    const int64_t units = vec ? (total >> 2 > (int64_t)M * 4 ? total >> 2 : (int64_t)M * 4) : total;
+    const unsigned grid = (unsigned)(div_up(units, 256) < (int64_t)kNumSM * 32 ? div_up(units, 256) : (int64_t)kNumSM * 32);
     { PG_KTIME("k_vox_fill", st);
-    k_vox_fill<<<grid, 256, 0, st>>>(coords, w.cnt, w.voff, sorted, M, W, mode, output_coords, output_map); }
+    if (vec) k_vox_fill<true><<<grid, 256, 0, st>>>(coords, w.cnt, w.voff, sorted, M, W, mode, output_coords, output_map);
+    else k_vox_fill<false><<<grid, 256, 0, st>>>(coords, w.cnt, w.voff, sorted, M, W, mode, output_coords, output_map); }
     PG_LAUNCH_CHECK();
     return PG_OK;
 }
