@@ -25,7 +25,7 @@ void set_error(const char *fmt, ...) {
 const char *last_error() { return g_err; }
 
 // ---------------------------------------------------------------------------------------------
-// exclusive scan (reduce / spine / apply)
+// exclusive scan (single pass, decoupled look-back)
 // ---------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
 constexpr int kScanRounds = 16;
@@ -52,120 +52,31 @@ __device__ __forceinline__ int block_scan_incl(int v, int *warp_tot /*[32] smem*
     return v + before;
 }
 
-__global__ void __launch_bounds__(kScanThreads) k_scan_reduce(const int32_t *__restrict__ in, int64_t n,
-                                                              int64_t *__restrict__ block_sums) {
-    __shared__ long long wsum[kScanThreads / 32];
-    const int64_t base = (int64_t)blockIdx.x * kScanTile;
-    long long s = 0;
-#pragma unroll 4
-    for (int r = 0; r < kScanRounds; r++) {
-        int64_t i = base + r * kScanThreads + threadIdx.x;
-        if (i < n) s += in[i];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        long long t = 0;
-        for (int i = 0; i < kScanThreads / 32; i++) t += wsum[i];
-        block_sums[blockIdx.x] = t;
-    }
-}
+// Single pass with decoupled look-back: a block takes the next tile (ticket from an atomic counter, so
+// every earlier tile is already running or done), scans it, publishes its aggregate, and warp 0 walks
+// back over the predecessors' published words -- 32 at a time -- until it meets an inclusive prefix.
+// One 64-bit word per tile: [63:62] 0 = nothing yet, 1 = aggregate, 2 = inclusive prefix; [61:0] value.
+// tmp[0] is the ticket counter, tmp[1 + t] tile t's word; the launcher zeroes them.
+constexpr unsigned long long kSpValueMask = (1ULL << 62) - 1;
 
-__global__ void __launch_bounds__(1024) k_scan_spine(int64_t *__restrict__ block_sums, int64_t nb,
-                                                     int64_t *__restrict__ total) {
-    __shared__ long long wtot[32];
-    __shared__ long long carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int64_t c = 0; c < nb; c += 1024) {
-        int64_t i = c + threadIdx.x;
-        long long v = (i < nb) ? block_sums[i] : 0, x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            long long t = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += t;
-        }
-        if (lane == 31) wtot[w] = x;
-        __syncthreads();
-        long long before = 0, all = 0;
-        for (int k = 0; k < 32; k++) {
-            long long t = wtot[k];
-            if (k < w) before += t;
-            all += t;
-        }
-        long long carry = carry_s;
-        if (i < nb) block_sums[i] = carry + before + x - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = carry + all;
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        block_sums[nb] = carry_s;
-        if (total) *total = carry_s;
-    }
-}
-
-__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const int32_t *__restrict__ in,
-                                                             int32_t *__restrict__ out, int64_t n,
-                                                             const int64_t *__restrict__ block_offs) {
+__global__ void __launch_bounds__(kScanThreads) k_scan_onepass(const int32_t *__restrict__ in, int32_t *__restrict__ out,
+                                                               int64_t n, unsigned long long *tmp, int64_t *__restrict__ total,
+                                                               int aligned) {
     __shared__ int warp_tot[32];
-    const int64_t base = (int64_t)blockIdx.x * kScanTile;
-    int carry = (int)block_offs[blockIdx.x];
-    for (int r = 0; r < kScanRounds; r++) {
-        int64_t i = base + r * kScanThreads + threadIdx.x;
-        if (base + r * kScanThreads >= n) break;
-        int v = (i < n) ? in[i] : 0, tot;
-        int inc = block_scan_incl(v, warp_tot, &tot);
-        if (i < n) out[i] = carry + inc - v;
-        carry += tot;
-    }
-}
-
-// 16-byte-aligned fast path: a thread owns 16 consecutive items (four int4 loads), scans them in
-// registers, and the block combines thread totals once -- two barriers per 4096-item tile instead of
-// two per 256 items.
-__global__ void __launch_bounds__(kScanThreads) k_scan_reduce_v(const int32_t *__restrict__ in, int64_t n,
-                                                                int64_t *__restrict__ block_sums) {
-    __shared__ long long wsum[kScanThreads / 32];
-    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanRounds;
-    long long s = 0;
-    if (base + kScanRounds <= n) {
-        const int4 *p = reinterpret_cast<const int4 *>(in + base);
-#pragma unroll
-        for (int k = 0; k < kScanRounds / 4; k++) {
-            const int4 v = __ldg(p + k);
-            s += (long long)v.x + v.y + v.z + v.w;
-        }
-    } else {
-        for (int k = 0; k < kScanRounds; k++)
-            if (base + k < n) s += in[base + k];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = s;
+    __shared__ long long s_tile, s_prefix;
+    if (threadIdx.x == 0) s_tile = (long long)atomicAdd(tmp, 1ULL);
     __syncthreads();
-    if (threadIdx.x == 0) {
-        long long t = 0;
-        for (int i = 0; i < kScanThreads / 32; i++) t += wsum[i];
-        block_sums[blockIdx.x] = t;
-    }
-}
-
-__global__ void __launch_bounds__(kScanThreads) k_scan_apply_v(const int32_t *__restrict__ in, int32_t *__restrict__ out,
-                                                               int64_t n, const int64_t *__restrict__ block_offs) {
-    __shared__ int warp_tot[32];
-    const int64_t base = (int64_t)blockIdx.x * kScanTile + (int64_t)threadIdx.x * kScanRounds;
+    const int64_t t = s_tile;
+    volatile unsigned long long *state = tmp + 1;
+    const int64_t base = t * kScanTile + (int64_t)threadIdx.x * kScanRounds;
     int v[kScanRounds];
-    const bool full = base + kScanRounds <= n;
+    const bool full = aligned && base + kScanRounds <= n;
     if (full) {
         const int4 *p = reinterpret_cast<const int4 *>(in + base);
 #pragma unroll
         for (int k = 0; k < kScanRounds / 4; k++) {
-            const int4 t = __ldg(p + k);
-            v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+            const int4 q = __ldg(p + k);
+            v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
         }
     } else {
 #pragma unroll
@@ -173,10 +84,43 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply_v(const int32_t *__
     }
     int tsum = 0;
 #pragma unroll
-    for (int k = 0; k < kScanRounds; k++) { const int t = v[k]; v[k] = tsum; tsum += t; }
+    for (int k = 0; k < kScanRounds; k++) { const int q = v[k]; v[k] = tsum; tsum += q; }
     int tot;
     const int incl = block_scan_incl(tsum, warp_tot, &tot);
-    const int off = (int)block_offs[blockIdx.x] + incl - tsum;
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        long long prefix = 0;
+        if (t == 0) {
+            if (lane == 0) state[0] = (2ULL << 62) | (unsigned long long)(long long)tot;
+        } else {
+            if (lane == 0) state[t] = (1ULL << 62) | ((unsigned long long)(long long)tot & kSpValueMask);
+            int64_t hi = t - 1;                       // the newest predecessor not yet added
+            for (;;) {
+                const int64_t k = hi - lane;
+                unsigned long long w = (2ULL << 62);  // below tile 0: an inclusive prefix of 0
+                if (k >= 0) w = state[k];
+                const unsigned flag = (unsigned)(w >> 62);
+                const unsigned empty = __ballot_sync(0xffffffffu, flag == 0u);
+                const unsigned incl_m = __ballot_sync(0xffffffffu, flag == 2u);
+                // usable lanes: from lane 0 up to the first inclusive word, all of them published
+                const int stop = incl_m ? __ffs((int)incl_m) - 1 : 31;
+                if (empty & ((stop == 31 ? 0xffffffffu : ((2u << stop) - 1u)))) continue;   // somebody in range is not there yet
+                long long val = (lane <= stop) ? (long long)(w & kSpValueMask) : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                prefix += val;
+                if (incl_m) break;
+                hi -= 32;
+            }
+            if (lane == 0) state[t] = (2ULL << 62) | ((unsigned long long)(prefix + tot) & kSpValueMask);
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (total && (t + 1) * (int64_t)kScanTile >= n) *total = prefix + tot;
+        }
+    }
+    __syncthreads();
+    const int off = (int)s_prefix + incl - tsum;
     if (full) {
         int4 *q = reinterpret_cast<int4 *>(out + base);
 #pragma unroll
@@ -199,11 +143,9 @@ int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, int64_t *tota
     }
     const int64_t nb = div_up(n, kScanTile);
     const bool aligned = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
-    if (aligned) k_scan_reduce_v<<<(unsigned)nb, kScanThreads, 0, st>>>(in, n, tmp);
-    else k_scan_reduce<<<(unsigned)nb, kScanThreads, 0, st>>>(in, n, tmp);
-    k_scan_spine<<<1, 1024, 0, st>>>(tmp, nb, total);
-    if (aligned) k_scan_apply_v<<<(unsigned)nb, kScanThreads, 0, st>>>(in, out, n, tmp);
-    else k_scan_apply<<<(unsigned)nb, kScanThreads, 0, st>>>(in, out, n, tmp);
+    PG_CUDA(cudaMemsetAsync(tmp, 0, (size_t)(nb + 1) * sizeof(int64_t), st));
+    k_scan_onepass<<<(unsigned)nb, kScanThreads, 0, st>>>(in, out, n, reinterpret_cast<unsigned long long *>(tmp), total,
+                                                         aligned ? 1 : 0);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }
