@@ -312,3 +312,26 @@ def gather_rows(src, idx, out=None):
         check(_L().pg_gather_rows(_p(src), _p(idx), int(idx.dtype == torch.int64), _p(out), n, C, _stream()),
               "gather_rows")
     return out
+
+
+def cluster_coords(coords, cluster_idxs, cluster_offsets, fullscale, scale, rand6):
+    """Fused glue of clusters_voxelization (model/pointgroup.py:125-167): -> (clusters_coords int64 [S,4],
+    center fp32 [nC,3], size fp32 [nC,3]); bit-identical to the torch op sequence it replaces."""
+    _need(coords, "coords", torch.float32)
+    _need(cluster_idxs, "cluster_idxs", torch.int32)
+    _need(cluster_offsets, "cluster_offsets", torch.int32)
+    _need(rand6, "rand6", torch.float32)
+    if coords.dim() != 2 or coords.size(1) != 3 or rand6.numel() != 6:
+        raise ValueError("coords must be [N,3] and rand6 hold 6 values")
+    S, nC = cluster_idxs.size(0), cluster_offsets.numel() - 1
+    dev = coords.device
+    out = torch.empty((S, 4), dtype=torch.int64, device=dev)
+    center = torch.empty((nC, 3), dtype=torch.float32, device=dev)
+    size = torch.empty((nC, 3), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        L = _L()
+        nws = L.pg_cluster_coords_workspace_bytes(nC)
+        ws = _ws(nws, dev)
+        check(L.pg_cluster_coords(_p(coords), _p(cluster_idxs), _p(cluster_offsets), S, nC, int(fullscale), float(scale),
+                                  _p(rand6), _p(ws), nws, _p(out), _p(center), _p(size), _stream()), "cluster_coords")
+    return out, center, size

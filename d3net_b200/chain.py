@@ -77,13 +77,36 @@ def get_batch_offsets(batch_idxs, batch_size):
     return torch.searchsorted(batch_idxs, bounds).int()
 
 
+def _clusters_voxelization_tail(ops, clusters_coords, clusters_feats, n_clusters, mode, timer, trace, box):
+    t = timer.start("voxelization_idx(clusters)")
+    voxel_coords, p2v_map, v2p_map = ops.voxelization_idx(clusters_coords, n_clusters, mode)
+    timer.stop(t)
+    if trace is not None:
+        trace["voxelization_idx(clusters)"] = (clusters_coords, n_clusters, voxel_coords, p2v_map, v2p_map)
+    t = timer.start("voxelization(clusters)")
+    voxel_feats = ops.voxelization(clusters_feats, v2p_map, mode)                         # (M, C)
+    timer.stop(t)
+    if trace is not None:
+        trace["voxelization(clusters)"] = (clusters_feats, v2p_map, voxel_feats)
+    return voxel_feats, voxel_coords, p2v_map, v2p_map, box
+
+
 def clusters_voxelization(ops, clusters_idx, clusters_offset, feats, coords, fullscale, scale, mode, rand6,
-                          timer=None, trace=None):
+                          timer=None, trace=None, fused_glue=False):
     """model/pointgroup.py:125-178.  ``rand6`` replaces the two torch.rand(3) draws (:161) so runs are
-    reproducible.  Returns (voxel_feats [M,C], voxel_coords int64 [M,4], p2v_map, v2p_map, (center, size))."""
+    reproducible.  Returns (voxel_feats [M,C], voxel_coords int64 [M,4], p2v_map, v2p_map, (center, size)).
+    ``fused_glue``: use the package's fused kernel for everything between the gathers and
+    voxelization_idx (bit-identical; an edit a caller makes to this function, not to the operator API)."""
     timer = timer or _NoTimer()
     c_idxs = clusters_idx[:, 1].long()
     clusters_feats = _gather_rows(ops, feats, c_idxs)
+    if fused_glue:
+        t = timer.start("cluster_voxel_coords(fused glue)")
+        clusters_coords, center, size = ops.cluster_voxel_coords(coords, clusters_idx, clusters_offset, fullscale, scale,
+                                                                 rand6)
+        timer.stop(t)
+        return _clusters_voxelization_tail(ops, clusters_coords, clusters_feats, clusters_offset.numel() - 1, mode, timer,
+                                           trace, (center, size))
     clusters_coords = coords[c_idxs]
     cid = clusters_idx[:, 0].long()
 
@@ -117,21 +140,11 @@ def clusters_voxelization(ops, clusters_idx, clusters_offset, feats, coords, ful
     clusters_coords = clusters_coords.long()
     clusters_coords = torch.cat([cid.view(-1, 1), clusters_coords], 1).contiguous()       # (sumNPoint, 1 + 3)
 
-    n_clusters = clusters_offset.numel() - 1
-    t = timer.start("voxelization_idx(clusters)")
-    voxel_coords, p2v_map, v2p_map = ops.voxelization_idx(clusters_coords, n_clusters, mode)
-    timer.stop(t)
-    if trace is not None:
-        trace["voxelization_idx(clusters)"] = (clusters_coords, n_clusters, voxel_coords, p2v_map, v2p_map)
-    t = timer.start("voxelization(clusters)")
-    voxel_feats = ops.voxelization(clusters_feats, v2p_map, mode)                         # (M, C)
-    timer.stop(t)
-    if trace is not None:
-        trace["voxelization(clusters)"] = (clusters_feats, v2p_map, voxel_feats)
-    return voxel_feats, voxel_coords, p2v_map, v2p_map, (clusters_center, clusters_size)
+    return _clusters_voxelization_tail(ops, clusters_coords, clusters_feats, clusters_offset.numel() - 1, mode, timer,
+                                       trace, (clusters_center, clusters_size))
 
 
-def proposal_chain(ops, batch, rand6=None, timer=None, trace=None):
+def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=False):
     """One pass of the hot path over one collated batch (all tensors on one CUDA device).
 
     batch: locs fp32 [N,3], locs_scaled int64 [N,4], feats fp32 [N,134], pt_feats fp32 [N,16],
@@ -208,7 +221,7 @@ def proposal_chain(ops, batch, rand6=None, timer=None, trace=None):
     (prop_voxel_feats, prop_voxel_coords, prop_p2v_map, _v2p,
      (proposals_center, proposals_size)) = clusters_voxelization(
         ops, proposals_idx, proposals_offset, batch["pt_feats"], batch["locs"], scenes.SCORE_FULLSCALE,
-        scenes.SCORE_SCALE, scenes.SCORE_MODE, rand6, timer, trace)
+        scenes.SCORE_SCALE, scenes.SCORE_MODE, rand6, timer, trace, fused_glue)
     out["proposals_center"], out["proposals_size"] = proposals_center, proposals_size
     out["proposals_voxel_feats"], out["proposals_voxel_coords"] = prop_voxel_feats, prop_voxel_coords
     out["proposals_v2p_map_numel"] = _v2p.numel()

@@ -344,3 +344,11 @@ class GatherRows(Function):
 
 
 gather_rows = GatherRows.apply
+
+
+def cluster_voxel_coords(coords, cluster_idxs, cluster_offsets, fullscale, scale, rand6):
+    """Not part of the reference's operator API: the glue of clusters_voxelization (model/pointgroup.py:125-167)
+    as one fused op, for callers willing to edit that function.  Returns (clusters_coords int64 [S,4] for
+    voxelization_idx, center [nC,3], size [nC,3]); not differentiable (the reference's `.long()` is not either)."""
+    return PG_OP.cluster_coords(coords.contiguous(), cluster_idxs.contiguous(), cluster_offsets.contiguous(), fullscale,
+                                scale, rand6.contiguous())

@@ -174,6 +174,19 @@ int pg_get_iou(const int32_t *proposals_idx, const int32_t *proposals_offset,
 int pg_gather_rows(const float *src, const void *idx, int idx_is_int64, float *dst, int64_t nIdx, int32_t C,
                    void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * cluster_coords     (no native counterpart: the caller-side glue of clusters_voxelization,
+ *                    model/pointgroup.py:125-167, ~40 torch kernels + sec_mean / sec_min / sec_max there)
+ * For proposals given as bfs_cluster output (cluster_idxs int32 [S,2], cluster_offsets int32 [nC+1]) over
+ * point coordinates fp32 [N,3]: out_coords int64 [S,4] = (cluster id, voxel x, y, z) on the fullscale^3
+ * grid, center / size fp32 [nC,3] = the proposals' axis-aligned boxes.  rand6 (device, 6 floats) stands
+ * for the two torch.rand(3) draws of :161.  Bit-identical to the torch sequence, operation by operation.
+ * ---------------------------------------------------------------------------------------------- */
+size_t pg_cluster_coords_workspace_bytes(int32_t nCluster);
+int pg_cluster_coords(const float *coords, const int32_t *cluster_idxs, const int32_t *cluster_offsets,
+                      int32_t sumNPoint, int32_t nCluster, int32_t fullscale, float scale, const float *rand6,
+                      void *ws, size_t ws_bytes, int64_t *out_coords, float *center, float *size, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

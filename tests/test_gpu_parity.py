@@ -487,3 +487,23 @@ def test_ballquery_mask_and_recompute_paths_agree(ops):
         PG_OP.ballquery_fill_impl(xyz, 0.03, sl, idx, state)
         res.append((sl, idx))
     assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+
+
+def test_fused_cluster_glue_equals_torch_sequence(ops):
+    """the fused clusters_voxelization glue gives, bit for bit, what the reference's
+    torch op sequence (model/pointgroup.py:125-167) gives on the GPU -- coordinates, centres, sizes and
+    everything downstream -- including a non-trivial random offset."""
+    from d3net_b200 import chain, scenes
+    nb = scenes.make_batch(2, 20000, config_id=5, geometry_points=20000)
+    batch = chain.batch_to_device(nb, torch.device("cuda"))
+    rand6 = torch.tensor([0.11, 0.52, 0.93, 0.37, 0.08, 0.64], device="cuda")
+    a = chain.proposal_chain(ops, batch, rand6)
+    b = chain.proposal_chain(ops, batch, rand6, fused_glue=True)
+    assert a["proposals_offset"].numel() > 3
+    for k in ("proposals_center", "proposals_size", "proposals_voxel_coords", "proposals_voxel_feats",
+              "proposals_score_feats", "ious"):
+        assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape, k
+        if a[k].dtype.is_floating_point:
+            assert torch.equal(a[k].view(torch.int32), b[k].view(torch.int32)), k
+        else:
+            assert torch.equal(a[k], b[k]), k
