@@ -93,6 +93,7 @@ SIGNATURES = {
     "pg_sec_max": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pg_get_iou": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "pg_gather_rows": (_int, [_vp, _vp, _int, _vp, _i64, _i32, _vp]),
+    "pg_pack_proposals": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "pg_cluster_coords_workspace_bytes": (_sz, [_i32]),
     "pg_cluster_coords": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
 }

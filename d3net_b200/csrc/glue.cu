@@ -158,9 +158,82 @@ __global__ void k_glue_cluster_coords(const float *__restrict__ coords, const in
     *dst = make_longlong4((long long)ci.x, (long long)x, (long long)y, (long long)z);
 }
 
+// ---- pack_proposals: the padded per-scene proposal block that is all-gathered (d3net_b200/dist.py) ----
+// Row layout (46 floats): score feats 16 | 8 box corners x 3 | centre 3 | semantic class | score | mask.
+// Scene s keeps its first P proposals in proposal order (convert_stack_to_batch without the randperm,
+// model/pointgroup.py:237-257).  One block ranks the proposals (a proposal's slot = number of earlier
+// proposals of its scene), then the rows are written one thread per float.
+constexpr int kPackWidth = 46;
+
+__global__ void __launch_bounds__(1024) k_pack_rank(const int2 *__restrict__ proposals_idx, const int32_t *__restrict__ offsets,
+                                                    const int64_t *__restrict__ locs_scaled, int32_t nP,
+                                                    int32_t *__restrict__ scene_of, int32_t *__restrict__ slot_of) {
+    extern __shared__ int32_t sc[];                 // scene id per proposal
+    for (int p = threadIdx.x; p < nP; p += blockDim.x) {
+        const int first = __ldg(&proposals_idx[__ldg(offsets + p)].y);
+        sc[p] = (int32_t)__ldg(locs_scaled + 4 * (int64_t)first);      // proposals_batchId (:349)
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < nP; p += blockDim.x) {
+        const int mine = sc[p];
+        int r = 0;
+        for (int q = 0; q < p; q++) r += sc[q] == mine;
+        scene_of[p] = mine;
+        slot_of[p] = r;
+    }
+}
+
+__global__ void k_pack_rows(const int2 *__restrict__ proposals_idx, const int32_t *__restrict__ offsets,
+                            const int64_t *__restrict__ semantic_preds, const float *__restrict__ center,
+                            const float *__restrict__ size, const float *__restrict__ feats, const float *__restrict__ score,
+                            const int32_t *__restrict__ scene_of, const int32_t *__restrict__ slot_of, int32_t nP, int32_t C,
+                            int32_t B, int32_t P, float *__restrict__ out) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)nP * kPackWidth) return;
+    const int p = (int)(t / kPackWidth), j = (int)(t - (int64_t)p * kPackWidth);
+    const int b = scene_of[p], s = slot_of[p];
+    if (s >= P || b < 0 || b >= B) return;
+    float v;
+    if (j < 16) v = j < C ? feats[(int64_t)p * C + j] : 0.f;
+    else if (j < 40) {
+        const int k = (j - 16) / 3, a = (j - 16) - 3 * k;              // corner k (sign bits x, y, z = 4, 2, 1), axis a
+        const float sign = ((k >> (2 - a)) & 1) ? 1.f : -1.f;
+        v = __fadd_rn(center[p * 3 + a], __fmul_rn(__fmul_rn(0.5f, size[p * 3 + a]), sign));
+    } else if (j < 43) v = center[p * 3 + (j - 40)];
+    else if (j == 43) v = (float)semantic_preds[__ldg(&proposals_idx[__ldg(offsets + p)].y)];     // sem_cls (:359)
+    else if (j == 44) v = score[p];
+    else v = 1.f;
+    out[((int64_t)b * P + s) * kPackWidth + j] = v;
+}
+
 }  // namespace pg
 
 using namespace pg;
+
+extern "C" int pg_pack_proposals(const int32_t *proposals_idx, const int32_t *proposals_offset, const int64_t *locs_scaled,
+                                 const int64_t *semantic_preds, const float *center, const float *size, const float *feats,
+                                 const float *score, int32_t nProposal, int32_t C, int32_t B, int32_t P, int32_t *ws,
+                                 float *out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PG_CHECK_ARG(nProposal >= 0 && B >= 0 && P >= 0 && C >= 0, "negative size");
+    PG_CHECK_ARG(nProposal <= 49152, "more proposals than one ranking block holds (49152)");
+    if ((int64_t)B * P > 0) {
+        PG_CHECK_ARG(out, "null pointer");
+        PG_CUDA(cudaMemsetAsync(out, 0, (size_t)B * P * kPackWidth * sizeof(float), st));
+    }
+    if (nProposal == 0 || (int64_t)B * P == 0) return PG_OK;
+    PG_CHECK_ARG(proposals_idx && proposals_offset && locs_scaled && semantic_preds && center && size && feats && score && ws,
+                 "null pointer");
+    const size_t smem = (size_t)nProposal * sizeof(int32_t);
+    if (smem > 48 * 1024)
+        PG_CUDA(cudaFuncSetAttribute(k_pack_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_pack_rank<<<1, 1024, smem, st>>>((const int2 *)proposals_idx, proposals_offset, locs_scaled, nProposal, ws, ws + nProposal);
+    const int64_t total = (int64_t)nProposal * kPackWidth;
+    k_pack_rows<<<(unsigned)div_up(total, 256), 256, 0, st>>>((const int2 *)proposals_idx, proposals_offset, semantic_preds, center,
+                                                              size, feats, score, ws, ws + nProposal, nProposal, C, B, P, out);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
 
 extern "C" size_t pg_cluster_coords_workspace_bytes(int32_t nCluster) {
     return (size_t)(nCluster > 0 ? nCluster : 1) * sizeof(GlueParams) + 256;

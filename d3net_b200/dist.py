@@ -21,8 +21,35 @@ def scene_shard(n_scenes, rank, world_size):
 
 
 def pack_proposals(out, batch, max_num_proposal=256):
-    """Device-side, loop-free restatement of convert_stack_to_batch's padding (without its randperm):
-    per scene the first `max_num_proposal` proposals -> [B, P, 46] fp32."""
+    """convert_stack_to_batch's padding (without its randperm): per scene the first `max_num_proposal`
+    proposals -> [B, P, 46] fp32.  CUDA tensors go through the library's two pack kernels; the torch
+    restatement below is the CPU path (gloo tests) and what the kernels are tested against."""
+    if out["proposals_score_feats"].is_cuda:
+        return _pack_proposals_cuda(out, batch, max_num_proposal)
+    return pack_proposals_torch(out, batch, max_num_proposal)
+
+
+def _pack_proposals_cuda(out, batch, P):
+    import ctypes
+    from . import _native
+    B = int(batch["n_scenes"])
+    feats = out["proposals_score_feats"].contiguous()
+    dev = feats.device
+    n_prop, C = feats.shape
+    packed = torch.empty((B, P, PACK_WIDTH), dtype=torch.float32, device=dev)
+    score = torch.sigmoid(feats[:, 0]).contiguous() if n_prop else feats.new_zeros(0)      # stand-in objectness score
+    ws = torch.empty(max(2 * n_prop, 1), dtype=torch.int32, device=dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    with torch.cuda.device(dev):
+        _native.check(_native.lib().pg_pack_proposals(
+            p(out["proposals_idx"]), p(out["proposals_offset"]), p(batch["locs_scaled"]), p(batch["semantic_preds"]),
+            p(out["proposals_center"].contiguous()), p(out["proposals_size"].contiguous()), p(feats), p(score), n_prop, C, B, P,
+            p(ws), p(packed), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "pack_proposals")
+    return packed
+
+
+def pack_proposals_torch(out, batch, max_num_proposal=256):
+    """Loop-free torch restatement of the padding."""
     B = int(batch["n_scenes"])
     P = max_num_proposal
     dev = out["proposals_score_feats"].device

@@ -187,6 +187,17 @@ int pg_cluster_coords(const float *coords, const int32_t *cluster_idxs, const in
                       int32_t sumNPoint, int32_t nCluster, int32_t fullscale, float scale, const float *rand6,
                       void *ws, size_t ws_bytes, int64_t *out_coords, float *center, float *size, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * pack_proposals     (multi-GPU plumbing, no native counterpart: the padding step of convert_stack_to_batch,
+ *                    model/pointgroup.py:237-257, for the block that is all-gathered between ranks)
+ * out fp32 [B, P, 46] (zero-filled here): scene b keeps its first P proposals in proposal order; row =
+ * score feats 16 | 8 corners x 3 | centre 3 | semantic class | score | mask.  ws: 2 * nProposal int32.
+ * ---------------------------------------------------------------------------------------------- */
+int pg_pack_proposals(const int32_t *proposals_idx, const int32_t *proposals_offset, const int64_t *locs_scaled,
+                      const int64_t *semantic_preds, const float *center, const float *size, const float *feats,
+                      const float *score, int32_t nProposal, int32_t C, int32_t B, int32_t P, int32_t *ws, float *out,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

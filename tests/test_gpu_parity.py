@@ -458,6 +458,9 @@ def test_pack_proposals(ops):
         first = torch.nonzero(scene == b).view(-1)[0]
         assert torch.equal(packed[b, 0, :16], out["proposals_score_feats"][first])
     assert torch.equal(pgdist.all_gather_proposals(packed), packed)      # world size 1: identity
+    for P in (64, 5, 1):                                                 # the pack kernels against the torch restatement
+        a, b = pgdist.pack_proposals(out, batch, P), pgdist.pack_proposals_torch(out, batch, P)
+        assert torch.equal(a.view(torch.int32), b.view(torch.int32))
 
 
 def test_gather_rows(ops):
