@@ -86,13 +86,16 @@ def voxelize_idx_impl(coords, mode):
     return output_coords, input_map, output_map
 
 
-# hit masks are used while they stay under this many bytes (they cost 1 bit per tested pair)
+# Hit masks cost 1 bit per tested (query, candidate) pair -- about 25 words per point at 330 neighbours per
+# point.  The buffer is sized from n alone (no round trip to learn the exact need); a batch that needs more
+# runs without masks (the fill phase then evaluates the predicates again).
+BALLQUERY_MASK_WORDS_PER_POINT = 48
 BALLQUERY_MASK_BUDGET_BYTES = 4 << 30
 
 
-def ballquery_count_impl(xyz, batch_idxs, batch_offsets, radius, use_masks=True):
+def ballquery_count_impl(xyz, batch_idxs, batch_offsets, radius, use_masks=True, mask_words=None):
     """Phases 1+2: returns (start_len int32 [n,2], total, state) where state carries the workspace and the
-    optional hit-mask buffer to ballquery_fill_impl."""
+    hit-mask buffer (None when it was not used) to ballquery_fill_impl."""
     _need(xyz, "coords", torch.float32)
     _need(batch_idxs, "batch_idxs", torch.int32)
     _need(batch_offsets, "batch_offsets", torch.int32)
@@ -104,18 +107,21 @@ def ballquery_count_impl(xyz, batch_idxs, batch_offsets, radius, use_masks=True)
         L = _L()
         nws = L.pg_ballquery_workspace_bytes(n)
         ws = _ws(nws, dev)
-        words = ctypes.c_int64(0)
         check(L.pg_ballquery_prepare(_p(xyz), _p(batch_idxs), _p(batch_offsets), n, batch_offsets.numel() - 1,
-                                     float(radius), _p(ws), nws, ctypes.byref(words), _stream()),
-              "ballquery_batch_p(prepare)")
+                                     float(radius), _p(ws), nws, _stream()), "ballquery_batch_p(prepare)")
         masks = None
-        if use_masks and 0 < words.value and words.value * 4 <= BALLQUERY_MASK_BUDGET_BYTES:
-            masks = torch.empty(words.value, dtype=torch.int32, device=dev)
+        if use_masks and n > 0:
+            if mask_words is None:
+                mask_words = min(BALLQUERY_MASK_WORDS_PER_POINT * n + 1024, BALLQUERY_MASK_BUDGET_BYTES // 4)
+            masks = torch.empty(int(mask_words), dtype=torch.int32, device=dev)
         start_len = torch.empty((n, 2), dtype=torch.int32, device=dev)
         total = ctypes.c_int64(0)
+        used = ctypes.c_int(0)
         check(L.pg_ballquery_count(_p(xyz), n, float(radius), _p(start_len), _p(masks),
                                    masks.numel() if masks is not None else 0, _p(ws), nws, ctypes.byref(total),
-                                   _stream()), "ballquery_batch_p(count)")
+                                   ctypes.byref(used), _stream()), "ballquery_batch_p(count)")
+        if not used.value:
+            masks = None
     return start_len, int(total.value), (ws, masks)
 
 

@@ -79,8 +79,8 @@ SIGNATURES = {
     "pg_point_recover_fp": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pg_point_recover_bp": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _vp]),
     "pg_ballquery_workspace_bytes": (_sz, [_i64]),
-    "pg_ballquery_prepare": (_int, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _sz, _vp, _vp]),
-    "pg_ballquery_count": (_int, [_vp, _i32, _f32, _vp, _vp, _i64, _vp, _sz, _vp, _vp]),
+    "pg_ballquery_prepare": (_int, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _sz, _vp]),
+    "pg_ballquery_count": (_int, [_vp, _i32, _f32, _vp, _vp, _i64, _vp, _sz, _vp, _vp, _vp]),
     "pg_ballquery_fill": (_int, [_vp, _i32, _f32, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "pg_bfs_cluster_workspace_bytes": (_sz, [_i64]),
     "pg_bfs_cluster_count": (_int, [_vp, _vp, _vp, _i32, _i64, _i32, _int, _vp, _sz, _vp, _vp]),

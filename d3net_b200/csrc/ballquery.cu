@@ -264,13 +264,14 @@ __global__ void __launch_bounds__(256) k_bq_cells_small(const float *__restrict_
                                                         const int32_t *__restrict__ nbr, const int32_t *__restrict__ kc,
                                                         const int32_t *__restrict__ cand_start,
                                                         const int32_t *__restrict__ mbase, const int64_t *__restrict__ scalars,
-                                                        uint32_t *__restrict__ masks, float r2,
+                                                        uint32_t *__restrict__ masks, int64_t mask_capacity, float r2,
                                                         uint32_t *__restrict__ cand_idx, int32_t *__restrict__ counts,
                                                         int32_t *__restrict__ kb) {
     __shared__ uint32_t scratch_all[8][kSmallK];
     uint32_t *scratch = scratch_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int64_t nCells = scalars[0];
+    if (scalars[6] > mask_capacity) masks = nullptr;            // the caller's mask buffer is too small: run without
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nCells; c += nWarps) {
         const int K = __ldg(kc + c);
@@ -393,12 +394,13 @@ __global__ void __launch_bounds__(kDenseThreads, 4) k_bq_cells_dense(
     const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cstart,
     const int32_t *__restrict__ ccnt, const int32_t *__restrict__ nbr, const int32_t *__restrict__ kc,
     const int32_t *__restrict__ cand_start, const int32_t *__restrict__ mbase, const int32_t *__restrict__ dense,
-    const uint2 *__restrict__ crange, int64_t *scalars, uint32_t *__restrict__ masks, float r2,
+    const uint2 *__restrict__ crange, int64_t *scalars, uint32_t *__restrict__ masks, int64_t mask_capacity, float r2,
     uint32_t *__restrict__ cand_idx, int32_t *__restrict__ counts, int32_t *__restrict__ kb) {
     extern __shared__ uint4 dense_smem_raw[];
     DenseSmem &S = *reinterpret_cast<DenseSmem *>(dense_smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nDense = scalars[3];
+    if (scalars[6] > mask_capacity) masks = nullptr;            // the caller's mask buffer is too small: run without
     // hit <=> d2 < r2.  d2 is a sum of squares: +0 .. +inf or the canonical NaN, so the float compare is
     // the signed compare of the bit patterns, and its outcome is the sign bit of (bits(d2) - bits(r2)).
     const int thr = (r2 == r2) ? __float_as_int(r2) : 0;         // NaN radius: nothing is a neighbour
@@ -668,12 +670,9 @@ static const uint32_t *bq_sorted(const BqWs &w, int32_t n) {
 }
 
 extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs, const int32_t *batch_offsets, int32_t n,
-                                    int32_t B, float radius, void *ws, size_t ws_bytes, int64_t *host_mask_words,
-                                    void *stream) {
+                                    int32_t B, float radius, void *ws, size_t ws_bytes, void *stream) {
     (void)batch_offsets; (void)B;   // scene membership comes from batch_idxs
     cudaStream_t st = (cudaStream_t)stream;
-    PG_CHECK_ARG(host_mask_words, "null host_mask_words");
-    *host_mask_words = 0;
     PG_CHECK_ARG(n >= 0 && n <= (1 << 26), "n out of range (0 .. 2^26)");
     if (n == 0) return PG_OK;
     PG_CHECK_ARG(xyz && batch_idxs && ws, "null pointer");
@@ -701,18 +700,16 @@ extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs,
     k_bq_mask_sizes<<<gsm, 256, 0, st>>>(w.ccnt, w.kc, w.scalars, n + 1, w.mbase);
     PG_TRY(scan_exclusive_i32(w.mbase, w.mbase, (int64_t)n + 1, w.scalars + 6, w.scan_tmp, st));
     PG_LAUNCH_CHECK();
-    int64_t words = 0;
-    PG_CUDA(cudaMemcpyAsync(&words, w.scalars + 6, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
-    PG_CUDA(cudaStreamSynchronize(st));
-    *host_mask_words = words >= 0x7fffffffLL ? -1 : words;   // -1: too many for int32 bases, run without masks
     return PG_OK;
 }
 
 extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int32_t *start_len, uint32_t *masks,
-                                  int64_t mask_words, void *ws, size_t ws_bytes, int64_t *host_total, void *stream) {
+                                  int64_t mask_words, void *ws, size_t ws_bytes, int64_t *host_total, int *host_masks_used,
+                                  void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    PG_CHECK_ARG(host_total, "null host_total");
+    PG_CHECK_ARG(host_total && host_masks_used, "null host_total / host_masks_used");
     *host_total = 0;
+    *host_masks_used = 0;
     PG_CHECK_ARG(n >= 0 && n <= (1 << 26), "n out of range (0 .. 2^26)");
     if (n == 0) return PG_OK;
     PG_CHECK_ARG(xyz && start_len && ws, "null pointer");
@@ -723,23 +720,27 @@ extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int
     const float r2 = radius * radius;
     PG_CUDA(cudaFuncSetAttribute(k_bq_cells_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DenseSmem)));
     PG_CUDA(cudaMemsetAsync(w.scalars + 4, 0, sizeof(int64_t), st));   // the dense kernel's work counter
+    // masks are used when they fit the caller's buffer (and int32 bases): decided on the device, reported below
+    const int64_t mask_cap = masks ? (mask_words < 0x7fffffffLL ? mask_words : 0x7ffffffeLL) : -1;
     const int64_t gsmall_want = div_up(n, 8);
     const unsigned gsmall = (unsigned)(gsmall_want < (int64_t)kNumSM * 16 ? gsmall_want : (int64_t)kNumSM * 16);
     { PG_KTIME("k_bq_cells_small", st);
     k_bq_cells_small<<<gsmall, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars,
-                                             masks, r2, w.cand_idx, w.counts, w.kb); }
+                                             masks, mask_cap, r2, w.cand_idx, w.counts, w.kb); }
     { PG_KTIME("k_bq_cells_dense", st);
     k_bq_cells_dense<<<kNumSM * 4, kDenseThreads, sizeof(DenseSmem), st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc,
                                                                             w.cand_start, w.mbase, w.dense, w.crange, w.scalars,
-                                                                            masks, r2, w.cand_idx, w.counts, w.kb); }
+                                                                            masks, mask_cap, r2, w.cand_idx, w.counts, w.kb); }
     // starts (reuse pslot) in query order, then the interleaved (start, len) rows per point
     PG_TRY(scan_exclusive_i32(w.counts, w.pslot, n, w.scalars + 2, w.scan_tmp, st));
     k_bq_start_len<<<(unsigned)div_up(n, 256), 256, 0, st>>>(sorted_pt, w.counts, w.pslot, n, (int2 *)start_len);
     PG_LAUNCH_CHECK();
-    int64_t total = 0;
-    PG_CUDA(cudaMemcpyAsync(&total, w.scalars + 2, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    int64_t back[5] = {0, 0, 0, 0, 0};               // scalars [2] total neighbours ... [6] mask words
+    PG_CUDA(cudaMemcpyAsync(back, w.scalars + 2, sizeof(back), cudaMemcpyDeviceToHost, st));
     PG_CUDA(cudaStreamSynchronize(st));
+    const int64_t total = back[0];
     *host_total = total;
+    *host_masks_used = (masks && back[4] <= mask_cap) ? 1 : 0;
     if (total > 0x7fffffffLL) {
         set_error("pg_ballquery_count: %lld neighbours do not fit the int32 start offsets of start_len", (long long)total);
         return PG_EOVERFLOW;

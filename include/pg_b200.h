@@ -95,19 +95,21 @@ int pg_point_recover_bp(const float *d_out, float *d_feats, const int32_t *rules
  * ballquery_batch_p     replaces PG_OP.ballquery_batch_p (bfs_cluster.h:15, bfs_cluster.cu:15-90)
  * Per point i: every k of the same scene with fma(dz,dz,fma(dx,dx,dy*dy)) < fl(r*r), ascending k,
  * at most the first PG_BALLQUERY_CAP.  Three phases over one workspace:
- *   prepare  builds the uniform grid and the per-cell candidate arrays; host_mask_words = number of
- *            uint32 words an optional hit-mask buffer needs (-1: too many, run without);
+ *   prepare  builds the uniform grid (cells, sorted point lists, neighbour cells); asynchronous;
  *   count    writes start_len int32 [n,2] = (start, cnt), segments laid out in query (cell) order
- *            (deterministic; the reference's atomicAdd placement is not), host_total = sum cnt; when
- *            `masks` (device, mask_words uint32) is given it also records every predicate outcome;
- *   fill     writes idx int32 [total]; with `masks` it only turns recorded bits into indices, without
- *            it the predicates are evaluated again.  Pass the same masks pointer (or NULL) to both.
+ *            (deterministic; the reference's atomicAdd placement is not), host_total = sum cnt.  `masks`
+ *            (device, capacity mask_words uint32; may be NULL) is an optional buffer in which the pass
+ *            records every predicate outcome; it is used when the batch needs no more words than it
+ *            holds (about 25 per point at 330 neighbours per point) -- host_masks_used says whether;
+ *   fill     writes idx int32 [total].  With masks it only turns recorded bits into indices; pass NULL
+ *            when host_masks_used was 0 and the predicates are evaluated again.
  * ---------------------------------------------------------------------------------------------- */
 size_t pg_ballquery_workspace_bytes(int64_t n);
 int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs, const int32_t *batch_offsets, int32_t n,
-                         int32_t B, float radius, void *ws, size_t ws_bytes, int64_t *host_mask_words, void *stream);
+                         int32_t B, float radius, void *ws, size_t ws_bytes, void *stream);
 int pg_ballquery_count(const float *xyz, int32_t n, float radius, int32_t *start_len, uint32_t *masks,
-                       int64_t mask_words, void *ws, size_t ws_bytes, int64_t *host_total, void *stream);
+                       int64_t mask_words, void *ws, size_t ws_bytes, int64_t *host_total, int *host_masks_used,
+                       void *stream);
 int pg_ballquery_fill(const float *xyz, int32_t n, float radius, const int32_t *start_len, const uint32_t *masks,
                       int32_t *idx, int64_t idx_capacity, void *ws, size_t ws_bytes, void *stream);
 

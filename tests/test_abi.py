@@ -56,10 +56,11 @@ def test_argument_validation_without_a_gpu(lib):
     assert lib.pg_voxelize_idx_map(None, 0, 9, None, None, 0, sizes, None) == -1           # bad mode
     assert b"mode" in lib.pg_last_error()
     assert lib.pg_voxelize_idx_map(None, 5, 4, None, None, 0, sizes, None) == -1           # null pointers
-    assert lib.pg_ballquery_prepare(None, None, None, 0, 1, 0.03, None, 0, ctypes.byref(total), None) == 0
-    assert total.value == 0
-    assert lib.pg_ballquery_prepare(None, None, None, -1, 1, 0.03, None, 0, ctypes.byref(total), None) == -1
-    assert lib.pg_ballquery_count(None, 0, 0.03, None, None, 0, None, 0, ctypes.byref(total), None) == 0
+    assert lib.pg_ballquery_prepare(None, None, None, 0, 1, 0.03, None, 0, None) == 0
+    assert lib.pg_ballquery_prepare(None, None, None, -1, 1, 0.03, None, 0, None) == -1
+    used = ctypes.c_int(7)
+    assert lib.pg_ballquery_count(None, 0, 0.03, None, None, 0, None, 0, ctypes.byref(total), ctypes.byref(used), None) == 0
+    assert used.value == 0 and total.value == 0
     assert lib.pg_ballquery_fill(None, 0, 0.03, None, None, None, 0, None, 0, None) == 0
     assert lib.pg_bfs_cluster_count(None, None, None, 0, 0, 50, 0, None, 0, sizes, None) == 0
     assert lib.pg_voxelize_fp(None, None, None, 0, 1, 16, 1, None) == 0

@@ -483,13 +483,15 @@ def test_ballquery_mask_and_recompute_paths_agree(ops):
     s = object_subset(small_batch(2, 15000))
     xyz, bi, bo = cu(s["shifted"]), cu(s["batch_idxs"]), cu(s["batch_offsets"])
     res = []
-    for use_masks in (True, False):
-        sl, total, state = PG_OP.ballquery_count_impl(xyz, bi, bo, 0.03, use_masks=use_masks)
-        assert (state[1] is not None) == use_masks
+    # masks on / masks off / a mask buffer too small for the batch (the device falls back by itself)
+    for use_masks, words, expect in ((True, None, True), (False, None, False), (True, 4096, False)):
+        sl, total, state = PG_OP.ballquery_count_impl(xyz, bi, bo, 0.03, use_masks=use_masks, mask_words=words)
+        assert (state[1] is not None) == expect
         idx = torch.empty(total, dtype=torch.int32, device="cuda")
         PG_OP.ballquery_fill_impl(xyz, 0.03, sl, idx, state)
         res.append((sl, idx))
-    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    for r in res[1:]:
+        assert torch.equal(res[0][0], r[0]) and torch.equal(res[0][1], r[1])
 
 
 def test_fused_cluster_glue_equals_torch_sequence(ops):
