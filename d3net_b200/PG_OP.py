@@ -135,10 +135,12 @@ def ballquery_fill_impl(xyz, radius, start_len, idx, state):
 BFS_AUTO, BFS_GENERIC, BFS_TRUSTED = 0, 1, 2      # include/pg_b200.h, `mode` of pg_bfs_cluster_count
 
 
-def bfs_cluster_impl(semantic_label, ball_query_idxs, start_len, threshold, generic=0, trusted=False):
+def bfs_cluster_impl(semantic_label, ball_query_idxs, start_len, threshold, generic=0, trusted=False, grid_ws=None):
     """All CUDA int32 -> (cluster_idxs [S,2], cluster_offsets [nC+1], used_generic_path).
     ``trusted``: the lists are ballquery_batch_p output of this library, untouched -- the sweep skips the
-    validation it needs for foreign neighbour lists (d3net_b200.pointgroup_ops decides this by provenance)."""
+    validation it needs for foreign neighbour lists (d3net_b200.pointgroup_ops decides this by provenance).
+    ``grid_ws`` (with ``trusted``): the workspace tensor of the ball query that produced the lists, untouched --
+    cells whose neighbourhood is already one component are not swept at all (pg_bfs_cluster_count_grid)."""
     _need(semantic_label, "semantic_label", torch.int32)
     _need(ball_query_idxs, "ball_query_idxs", torch.int32)
     _need(start_len, "start_len", torch.int32)
@@ -151,16 +153,29 @@ def bfs_cluster_impl(semantic_label, ball_query_idxs, start_len, threshold, gene
         nws = L.pg_bfs_cluster_workspace_bytes(N)
         ws = _ws(nws, dev)
         sizes = (ctypes.c_int32 * 3)()
-        check(L.pg_bfs_cluster_count(_p(semantic_label), _p(ball_query_idxs), _p(start_len), N,
-                                     ball_query_idxs.numel(), int(threshold),
-                                     BFS_GENERIC if generic else (BFS_TRUSTED if trusted else BFS_AUTO), _p(ws), nws, sizes,
-                                     _stream()), "bfs_cluster(count)")
+        if trusted and not generic and grid_ws is not None and N > 0:
+            check(L.pg_bfs_cluster_count_grid(_p(semantic_label), _p(ball_query_idxs), _p(start_len), N,
+                                              ball_query_idxs.numel(), int(threshold), _p(ws), nws, _p(grid_ws),
+                                              grid_ws.numel(), sizes, _stream()), "bfs_cluster(count, grid)")
+        else:
+            check(L.pg_bfs_cluster_count(_p(semantic_label), _p(ball_query_idxs), _p(start_len), N,
+                                         ball_query_idxs.numel(), int(threshold),
+                                         BFS_GENERIC if generic else (BFS_TRUSTED if trusted else BFS_AUTO), _p(ws), nws,
+                                         sizes, _stream()), "bfs_cluster(count)")
         nC, S = int(sizes[0]), int(sizes[1])
         cluster_idxs = torch.empty((S, 2), dtype=torch.int32, device=dev)
         cluster_offsets = torch.empty(nC + 1, dtype=torch.int32, device=dev)
         check(L.pg_bfs_cluster_fill(N, nC, S, _p(ws), nws, _p(cluster_idxs), _p(cluster_offsets), _stream()),
               "bfs_cluster(fill)")
     return cluster_idxs, cluster_offsets, bool(sizes[2])
+
+
+def bfs_cluster_debug():
+    """Diagnostics of this thread's last bfs_cluster count phase: [checksum != 0, bad lists, parked one-way
+    edges, propagation sweeps, neighbour lists the edge sweep read]."""
+    d = (ctypes.c_longlong * 5)()
+    _L().pg_bfs_cluster_debug(d)
+    return list(d)
 
 
 def _vox(fn, src, dst, rules, M, maxActive, C, *extra):
@@ -341,3 +356,41 @@ def cluster_coords(coords, cluster_idxs, cluster_offsets, fullscale, scale, rand
         check(L.pg_cluster_coords(_p(coords), _p(cluster_idxs), _p(cluster_offsets), S, nC, int(fullscale), float(scale),
                                   _p(rand6), _p(ws), nws, _p(out), _p(center), _p(size), _stream()), "cluster_coords")
     return out, center, size
+
+
+def cross_iou(proposals_idx, nProposal, N, want_npoint=False):
+    """Sparse replacement of the dense-mask matmul of PointGroup.test (model/pointgroup.py:577-590):
+    proposals_idx int32 [S, 2] CUDA rows (proposal, point) -> cross_ious fp32 [nProposal, nProposal]
+    (and, on request, the distinct point count per proposal, proposals_mask.sum(1) of :582)."""
+    _need(proposals_idx, "proposals_idx", torch.int32)
+    if proposals_idx.dim() != 2 or proposals_idx.size(1) != 2:
+        raise ValueError("proposals_idx must be [sumNPoint, 2]")
+    S, nP, N = proposals_idx.size(0), int(nProposal), int(N)
+    dev = proposals_idx.device
+    out = torch.empty((nP, nP), dtype=torch.float32, device=dev)
+    npoint = torch.empty(nP, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        L = _L()
+        nws = L.pg_cross_iou_workspace_bytes(S, nP, N)
+        ws = _ws(nws, dev)
+        check(L.pg_cross_iou(_p(proposals_idx), S, nP, N, _p(ws), nws, _p(out), _p(npoint), _stream()), "cross_iou")
+    return (out, npoint) if want_npoint else out
+
+
+def nms_instances(cross_ious, scores, threshold):
+    """get_nms_instances (lib/utils/eval.py:75-97) on the device: -> int32 [nPick] kept proposals, best first."""
+    _need(cross_ious, "cross_ious", torch.float32)
+    _need(scores, "scores", torch.float32)
+    n = scores.numel()
+    if cross_ious.dim() != 2 or cross_ious.size(0) != n or cross_ious.size(1) != n:
+        raise ValueError("cross_ious must be [n, n] for n scores")
+    dev = scores.device
+    pick = torch.empty(n, dtype=torch.int32, device=dev)
+    cnt = ctypes.c_int32(0)
+    with torch.cuda.device(dev):
+        L = _L()
+        nws = L.pg_nms_instances_workspace_bytes(n)
+        ws = _ws(nws, dev)
+        check(L.pg_nms_instances(_p(cross_ious), _p(scores), n, float(threshold), _p(ws), nws, _p(pick),
+                                 ctypes.byref(cnt), _stream()), "nms_instances")
+    return pick[:cnt.value]

@@ -84,6 +84,8 @@ SIGNATURES = {
     "pg_ballquery_fill": (_int, [_vp, _i32, _f32, _vp, _vp, _vp, _i64, _vp, _sz, _vp]),
     "pg_bfs_cluster_workspace_bytes": (_sz, [_i64]),
     "pg_bfs_cluster_count": (_int, [_vp, _vp, _vp, _i32, _i64, _i32, _int, _vp, _sz, _vp, _vp]),
+    "pg_bfs_cluster_count_grid": (_int, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "pg_bfs_cluster_debug": (None, [_vp]),
     "pg_bfs_cluster_fill": (_int, [_i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
     "pg_roipool_workspace_bytes": (_sz, [_i32, _i32]),
     "pg_roipool_fp": (_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _sz, _vp]),
@@ -94,6 +96,10 @@ SIGNATURES = {
     "pg_get_iou": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp]),
     "pg_gather_rows": (_int, [_vp, _vp, _int, _vp, _i64, _i32, _vp]),
     "pg_pack_proposals": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "pg_cross_iou_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "pg_cross_iou": (_int, [_vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
+    "pg_nms_instances_workspace_bytes": (_sz, [_i32]),
+    "pg_nms_instances": (_int, [_vp, _vp, _i32, _f32, _vp, _sz, _vp, _vp, _vp]),
     "pg_cluster_coords_workspace_bytes": (_sz, [_i32]),
     "pg_cluster_coords": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
 }

@@ -25,6 +25,7 @@
 #include <math.h>
 
 #include "common.cuh"
+#include "ballquery.cuh"
 
 namespace pg {
 
@@ -36,54 +37,6 @@ constexpr int kWinWords = kWinBits / 32;
 constexpr int kQMax = 512;               // queries of one dense cell handled per pass
 constexpr int kDenseThreads = 256;
 constexpr int kChunkBlocks = 4;          // 32-candidate blocks per (query group, chunk) work item
-
-struct BqWs {
-    int4 *keys;
-    GroupTable tab;
-    int32_t *pslot, *cell, *ccnt, *cstart, *kc, *kb, *cand_start, *counts, *nbr, *mbase, *dense;
-    uint2 *crange;      // dense cells: (smallest, largest) candidate index
-    uint32_t *cand_idx;
-    uint32_t *kA, *vA, *kB, *vB;
-    int32_t *hist;
-    int64_t *scan_tmp;
-    // [0] nCells [1] total candidates [2] total neighbours [3] nDense [4] dense work counter [6] mask words
-    int64_t *scalars;
-    bool ok;
-    size_t used;
-};
-
-static BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
-    Arena a(ws, ws_bytes);
-    BqWs w;
-    const size_t n = (size_t)(n_ > 0 ? n_ : 1);
-    w.tab.cap = group_table_cap(n_);
-    w.keys = a.take<int4>(n);
-    w.tab.slot_rep = a.take<int32_t>(w.tab.cap);
-    w.tab.slot_gid = a.take<int32_t>(w.tab.cap);
-    w.pslot = a.take<int32_t>(n);
-    w.cell = a.take<int32_t>(n);
-    w.ccnt = a.take<int32_t>(n + 1);
-    w.cstart = a.take<int32_t>(n + 1);
-    w.kc = a.take<int32_t>(n + 1);
-    w.kb = a.take<int32_t>(n + 1);
-    w.cand_start = a.take<int32_t>(n + 1);
-    w.counts = a.take<int32_t>(n + 1);
-    w.nbr = a.take<int32_t>(n * 27);
-    w.dense = a.take<int32_t>(n);
-    w.crange = a.take<uint2>(n);
-    w.kA = a.take<uint32_t>(n);
-    w.vA = a.take<uint32_t>(n);
-    w.kB = a.take<uint32_t>(n);
-    w.vB = a.take<uint32_t>(n);
-    w.hist = a.take<int32_t>(radix_tmp_count(n_));
-    w.scan_tmp = a.take<int64_t>(scan_tmp_count((int64_t)(n + radix_tmp_count(n_))));
-    w.scalars = a.take<int64_t>(8);
-    w.cand_idx = a.take<uint32_t>(n * 27);
-    w.mbase = a.take<int32_t>(n + 1);
-    w.ok = a.ok;
-    w.used = a.used;
-    return w;
-}
 
 // Far coordinates (|x/s| >= 2^30) have an fp32 spacing above the radius, so two of them can only be
 // neighbours along that axis when they are the SAME float: any function of the bit pattern is a
@@ -631,6 +584,30 @@ __global__ void __launch_bounds__(256) k_bq_fill_mask(const uint32_t *__restrict
         // and their latency is paid once per eight blocks.
         const int nb = (K + 31) >> 5;
         const uint32_t *mp8 = masks + __ldg(mbase + cc) + (int)(q0 - __ldg(cstart + cc)) + (int64_t)(lane >> 2) * nq + (lane & 3);
+        const unsigned lanebit = 1u << lane;
+        // A list shorter than the cap holds every hit of its query, so the recorded bits ARE the list: no
+        // position needs checking against the segment's end.  Only a group with a full list (kCap entries:
+        // later hits are dropped, and words past the last one may not have been written) takes the checked loop.
+        const bool capped = wend[0] - wpos[0] >= kCap || wend[1] - wpos[1] >= kCap || wend[2] - wpos[2] >= kCap ||
+                            wend[3] - wpos[3] >= kCap;
+        if (!capped) {
+            for (int b0 = 0; b0 < nb; b0 += 8) {
+                const unsigned mw = (b0 + (lane >> 2) < nb) ? __ldg(mp8 + (int64_t)b0 * nq) : 0u;
+                int cidr[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) cidr[j] = ((b0 + j) * 32 + lane < K) ? (int)__ldg(cp + (b0 + j) * 32) : 0;
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+#pragma unroll
+                    for (int u = 0; u < kFillQ; u++) {
+                        const unsigned m = __shfl_sync(0xffffffffu, mw, j * 4 + u);
+                        if (m & lanebit) idx[wpos[u] + __popc(m & lt)] = cidr[j];
+                        wpos[u] += __popc(m);
+                    }
+                }
+            }
+            continue;
+        }
         bool done = false;
         for (int b0 = 0; b0 < nb && !done; b0 += 8) {
             const unsigned mw = (b0 + (lane >> 2) < nb) ? __ldg(mp8 + (int64_t)b0 * nq) : 0u;
@@ -643,7 +620,7 @@ __global__ void __launch_bounds__(256) k_bq_fill_mask(const uint32_t *__restrict
                 for (int u = 0; u < kFillQ; u++) {
                     const unsigned m = __shfl_sync(0xffffffffu, mw, j * 4 + u);
                     const int pos = wpos[u] + __popc(m & lt);
-                    if (((m >> lane) & 1u) && pos < wend[u]) idx[pos] = cidr[j];
+                    if ((m & lanebit) && pos < wend[u]) idx[pos] = cidr[j];
                     wpos[u] = min(wpos[u] + __popc(m), wend[u]);   // words past a full list may be unwritten: stay put
                 }
             }
@@ -659,14 +636,6 @@ using namespace pg;
 extern "C" size_t pg_ballquery_workspace_bytes(int64_t n) {
     if (n < 0) n = 0;
     return bq_layout(nullptr, 0, n).used + 256;
-}
-
-// ping-pong parity of the radix sort (prepare / count / fill must agree on where sorted_pt landed)
-static const uint32_t *bq_sorted(const BqWs &w, int32_t n) {
-    int bits = 0;
-    while ((1ll << bits) < (long long)n) bits++;
-    const int passes = (bits + 7) / 8 < 1 ? 1 : (bits + 7) / 8;
-    return (passes & 1) ? w.vA : w.vB;
 }
 
 extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs, const int32_t *batch_offsets, int32_t n,
@@ -694,7 +663,7 @@ extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs,
     PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
     const unsigned gsm = kNumSM * 8;
     { PG_KTIME("k_bq_neighbours", st);
-    k_bq_neighbours<<<kNumSM * 16, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense, w.crange); }
+    k_bq_neighbours<<<kNumSM * PG_RESIDENT(k_bq_neighbours, 256, 0) * 2, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense, w.crange); }
     k_bq_clear_tail<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n + 1);   // kc beyond nCells must scan as 0
     PG_TRY(scan_exclusive_i32(w.kc, w.cand_start, (int64_t)n + 1, w.scalars + 1, w.scan_tmp, st));
     k_bq_mask_sizes<<<gsm, 256, 0, st>>>(w.ccnt, w.kc, w.scalars, n + 1, w.mbase);
@@ -723,7 +692,8 @@ extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int
     // masks are used when they fit the caller's buffer (and int32 bases): decided on the device, reported below
     const int64_t mask_cap = masks ? (mask_words < 0x7fffffffLL ? mask_words : 0x7ffffffeLL) : -1;
     const int64_t gsmall_want = div_up(n, 8);
-    const unsigned gsmall = (unsigned)(gsmall_want < (int64_t)kNumSM * 16 ? gsmall_want : (int64_t)kNumSM * 16);
+    const int64_t gsmall_max = (int64_t)kNumSM * PG_RESIDENT(k_bq_cells_small, 256, 0) * 4;
+    const unsigned gsmall = (unsigned)(gsmall_want < gsmall_max ? gsmall_want : gsmall_max);
     { PG_KTIME("k_bq_cells_small", st);
     k_bq_cells_small<<<gsmall, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars,
                                              masks, mask_cap, r2, w.cand_idx, w.counts, w.kb); }
@@ -761,10 +731,10 @@ extern "C" int pg_ballquery_fill(const float *xyz, int32_t n, float radius, cons
     const float r2 = radius * radius;
     PG_KTIME(masks ? "k_bq_fill_mask" : "k_bq_fill", st);
     if (masks)
-        k_bq_fill_mask<<<kNumSM * 8, 256, 0, st>>>(sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx, w.mbase,
+        k_bq_fill_mask<<<kNumSM * PG_RESIDENT(k_bq_fill_mask, 256, 0) * 4, 256, 0, st>>>(sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx, w.mbase,
                                                    masks, (const int2 *)start_len, n, idx);
     else
-        k_bq_fill<<<kNumSM * 8, 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cand_start, w.kb, w.cand_idx, (const int2 *)start_len,
+        k_bq_fill<<<kNumSM * PG_RESIDENT(k_bq_fill, 256, 0) * 4, 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cand_start, w.kb, w.cand_idx, (const int2 *)start_len,
                                               r2, n, idx);
     PG_LAUNCH_CHECK();
     return PG_OK;

@@ -1,0 +1,64 @@
+// Workspace layout of the ball query (ballquery.cu), shared with bfs_cluster's grid-assisted sweep
+// (cluster.cu), which reads the uniform grid the producing ball query left behind.
+#pragma once
+#include "common.cuh"
+
+namespace pg {
+
+struct BqWs {
+    int4 *keys;
+    GroupTable tab;
+    int32_t *pslot, *cell, *ccnt, *cstart, *kc, *kb, *cand_start, *counts, *nbr, *mbase, *dense;
+    uint2 *crange;      // dense cells: (smallest, largest) candidate index
+    uint32_t *cand_idx;
+    uint32_t *kA, *vA, *kB, *vB;
+    int32_t *hist;
+    int64_t *scan_tmp;
+    // [0] nCells [1] total candidates [2] total neighbours [3] nDense [4] dense work counter [6] mask words
+    int64_t *scalars;
+    bool ok;
+    size_t used;
+};
+
+inline BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
+    Arena a(ws, ws_bytes);
+    BqWs w;
+    const size_t n = (size_t)(n_ > 0 ? n_ : 1);
+    w.tab.cap = group_table_cap(n_);
+    w.keys = a.take<int4>(n);
+    w.tab.slot_rep = a.take<int32_t>(w.tab.cap);
+    w.tab.slot_gid = a.take<int32_t>(w.tab.cap);
+    w.pslot = a.take<int32_t>(n);
+    w.cell = a.take<int32_t>(n);
+    w.ccnt = a.take<int32_t>(n + 1);
+    w.cstart = a.take<int32_t>(n + 1);
+    w.kc = a.take<int32_t>(n + 1);
+    w.kb = a.take<int32_t>(n + 1);
+    w.cand_start = a.take<int32_t>(n + 1);
+    w.counts = a.take<int32_t>(n + 1);
+    w.nbr = a.take<int32_t>(n * 27);
+    w.dense = a.take<int32_t>(n);
+    w.crange = a.take<uint2>(n);
+    w.kA = a.take<uint32_t>(n);
+    w.vA = a.take<uint32_t>(n);
+    w.kB = a.take<uint32_t>(n);
+    w.vB = a.take<uint32_t>(n);
+    w.hist = a.take<int32_t>(radix_tmp_count(n_));
+    w.scan_tmp = a.take<int64_t>(scan_tmp_count((int64_t)(n + radix_tmp_count(n_))));
+    w.scalars = a.take<int64_t>(8);
+    w.cand_idx = a.take<uint32_t>(n * 27);
+    w.mbase = a.take<int32_t>(n + 1);
+    w.ok = a.ok;
+    w.used = a.used;
+    return w;
+}
+
+// ping-pong parity of the radix sort (prepare / count / fill must agree on where sorted_pt landed)
+inline const uint32_t *bq_sorted(const BqWs &w, int32_t n) {
+    int bits = 0;
+    while ((1ll << bits) < (long long)n) bits++;
+    const int passes = (bits + 7) / 8 < 1 ? 1 : (bits + 7) / 8;
+    return (passes & 1) ? w.vA : w.vB;
+}
+
+}  // namespace pg

@@ -24,6 +24,7 @@
 // ascending, and a 64-bit checksum of the two-way edge set that cancels against its own reversal.
 // Both checks ride along in the verify sweep and need no extra memory traffic.
 #include "common.cuh"
+#include "ballquery.cuh"
 
 namespace pg {
 
@@ -40,11 +41,14 @@ struct ClWs {
     int32_t *cid;        // cluster id per kept label (exclusive scan of keep flags)
     int32_t *csize;      // sizes in cluster order -> offsets
     int2 *pend;          // parked one-way edges (i -> j)
+    uint2 *cellsum;      // grid-assisted mode, per ball-query cell: (main label, snapshot root | flags F1 F2 F3)
+    uint32_t *cstate;    //   settled flag per cell
+    int32_t *cqueue;     //   cells queued for the point-level recheck
     uint32_t *key0, *kA, *vA, *kB, *vB;
     int32_t *hist;
     int64_t *scan_tmp;
     // [0] checksum [1] bad [2] pending count [3] changed [4] nCluster [5] sumNPoint [6] verify work counter
-    // [7] some list is full
+    // [7] some list is full [8] lists left to the sweep (grid-assisted mode) [9] cells queued for the recheck
     unsigned long long *scalars;
     size_t pend_cap;
     bool ok;
@@ -66,6 +70,9 @@ static ClWs cl_layout(void *ws, size_t ws_bytes, int64_t N_) {
     w.csize = a.take<int32_t>(n + 1);
     w.pend_cap = n + 1024;
     w.pend = a.take<int2>(w.pend_cap);
+    w.cellsum = a.take<uint2>(n);
+    w.cstate = a.take<uint32_t>(n);
+    w.cqueue = a.take<int32_t>(n);
     w.key0 = a.take<uint32_t>(n);
     w.kA = a.take<uint32_t>(n);
     w.vA = a.take<uint32_t>(n);
@@ -73,7 +80,7 @@ static ClWs cl_layout(void *ws, size_t ws_bytes, int64_t N_) {
     w.vB = a.take<uint32_t>(n);
     w.hist = a.take<int32_t>(radix_tmp_count(N_));
     w.scan_tmp = a.take<int64_t>(scan_tmp_count((int64_t)(n + radix_tmp_count(N_))));
-    w.scalars = a.take<unsigned long long>(8);
+    w.scalars = a.take<unsigned long long>(12);
     w.ok = a.ok;
     w.used = a.used;
     return w;
@@ -174,26 +181,30 @@ constexpr unsigned kSnapRoot = 0x03ffffffu, kSnapLabel = 0x7c000000u, kSnapFull 
 // two-way edges between equal labels are used, exactly the edges the sweep would unite along.
 constexpr int kSampleRounds = 1;
 
+template <int P>
 __global__ void k_cl_sample(const int32_t *__restrict__ idx, const int2 *__restrict__ start_len, uint2 *pl,
                             const int32_t *__restrict__ last, const uint32_t *__restrict__ snap, int32_t N, int round) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int2 sl = start_len[i];
     if (sl.y <= 1) return;
-    // round 0: last and middle entry; later rounds: the quarter points, the eighths, ...
+    // round 0: last and middle entry (P = 2), plus the quarter points (P = 4); later rounds: the eighths, ...
     const int den = 2 << round;
-    const int p0 = round == 0 ? sl.y - 1 : (int)(((long long)sl.y) / den);
-    const int p1 = round == 0 ? sl.y >> 1 : (int)(((long long)sl.y * (den - 1)) / den);
-    int jj[2];
-    jj[0] = __ldg(idx + sl.x + p0);
-    jj[1] = __ldg(idx + sl.x + p1);
-    const unsigned si = __ldg(snap + i);
-    unsigned sj[2];
+    int pos[4];
+    pos[0] = round == 0 ? sl.y - 1 : (int)(((long long)sl.y) / den);
+    pos[1] = round == 0 ? sl.y >> 1 : (int)(((long long)sl.y * (den - 1)) / den);
+    pos[2] = sl.y >> 2;
+    pos[3] = (int)(((long long)sl.y * 3) >> 2);
+    int jj[P];
 #pragma unroll
-    for (int u = 0; u < 2; u++) sj[u] = ((unsigned)jj[u] < (unsigned)N) ? __ldg(snap + jj[u]) : si;
+    for (int u = 0; u < P; u++) jj[u] = __ldg(idx + sl.x + pos[u]);
+    const unsigned si = __ldg(snap + i);
+    unsigned sj[P];
+#pragma unroll
+    for (int u = 0; u < P; u++) sj[u] = ((unsigned)jj[u] < (unsigned)N) ? __ldg(snap + jj[u]) : si;
     int ri = (int)(si & kSnapRoot);
 #pragma unroll
-    for (int u = 0; u < 2; u++) {
+    for (int u = 0; u < P; u++) {
         const int j = jj[u];
         const unsigned x = (si ^ sj[u]) & ~kSnapFull;
         if (x == 0u || x > kSnapRoot) continue;                      // same tree, or different label bits
@@ -223,8 +234,10 @@ __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__r
                                                               const int32_t *__restrict__ last,
                                                               const uint32_t *__restrict__ snap, int32_t N,
                                                               int2 *__restrict__ pend, unsigned pend_cap,
-                                                              unsigned long long *scalars) {
+                                                              unsigned long long *scalars, int use_list_count) {
     constexpr int kGroups = kVerThreads / G;
+    // lists to sweep: all N of them in `order`, or the scalars[8] the cell pass left over (grid-assisted mode)
+    const long long NL = use_list_count ? (long long)scalars[8] : (long long)N;
     constexpr int kChunk = kGroups * 8 > kVerThreads ? kVerThreads : kGroups * 8;   // lists per claim (<= one per thread)
     constexpr int kU = 4;
     __shared__ int4 hdr[2][kChunk];              // (point, start, length, snapshot word) per list of a chunk
@@ -239,7 +252,7 @@ __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__r
     auto fetch_header = [&](long long base, int4 &h) {
         h = make_int4(0, 0, 0, 0);
         const long long p = base + tid;
-        if (tid < kChunk && p < N) {
+        if (tid < kChunk && p < NL) {
             const int i = (int)__ldg(order + p);
             const int2 sl = __ldg(start_len + i);
             h = make_int4(i, sl.x, sl.y, (int)__ldg(snap + i));
@@ -261,8 +274,8 @@ __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__r
     for (int round = 0;; round++) {
         const int cur = round & 1;
         const long long base = s_base[cur];
-        if (base >= N) break;
-        const int nl = (int)(N - base < kChunk ? N - base : kChunk);
+        if (base >= NL) break;
+        const int nl = (int)(NL - base < kChunk ? NL - base : kChunk);
         // one step ahead: headers of the next chunk (its base was claimed a round ago), claim of the one after
         const long long base1 = s_base[cur ^ 1];
         int4 h1;
@@ -360,6 +373,160 @@ __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__r
         if ((threadIdx.x & 31) == 0 && chk) atomicAdd(&scalars[0], chk);
         if (bad) atomicMax(&scalars[1], 1ULL);
     }
+}
+
+
+// ---- grid-assisted sweep (trusted lists + the producing ball query's workspace) --------------------------
+// The ball query's uniform grid is still in its workspace: cells, each cell's points, each cell's 27 neighbour
+// cells; every list of a point of cell A is a subset of the points of those 27 cells.  After the sampling rounds
+// almost every component is one tree plus a few stray twigs.  Each cell gets a main pair (M, R): the label and
+// snapshot root most of its points carry.  Call a point with label M and another root a STRAY of that pair.
+//     A is SETTLED  <=>  every stray of (M_A, R_A) in A's 27 cells has a complete (< 1000 entries) list and is
+//                        itself swept.
+// A point i of a settled cell with label M_A and root R_A then has nothing to tell the sweep.  Take j in list(i)
+// with label(j) = M_A (other labels are ignored by the sweep anyway).  Root R_A: already i's set -- equal snapshot
+// roots stay equal, sets only merge -- so the edge neither unites nor, if it is one-way, needs parking.  A stray:
+// its list is complete and d(i, j) < r, so it holds i; j is swept, and from j's side the pair is classified
+// exactly as from i's (two-way iff j <= last(i) when list(i) is full, which holds because j is IN list(i)).  So
+// list(i) is never read.  "Itself swept" is what the rules below guarantee: a point is kept for the sweep unless
+// its cell is settled AND it carries the cell's main pair, and of two adjacent cells with the same label and
+// different roots only the one with the SMALLER root may lean on the other (the larger one then cannot be
+// settled, so all its points are swept).  Per neighbour B of A, from per-cell summaries alone:
+//     M_B = M_A, R_B = R_A :  fine unless B holds a full stray                        (flag F1_B)
+//     M_B = M_A, R_B != R_A:  fine iff R_A < R_B and B holds no full M_B point         (flag F2_B)
+//     M_B != M_A           :  M_A points are the minority in B and always swept; fine if B holds no full point
+//                             (flag F3_B), otherwise B's points are looked at one by one (recheck pass).
+// Passes (none with a long dependent chain):  main per cell -> flags per point -> settle per cell -> recheck per
+// queued cell (one warp) -> work list per point in query order (lists sharing entries stay together).
+// Cost: a few loads per point and 27 per cell, instead of one snapshot read per EDGE (~330 per point on
+// shifted coordinates).
+constexpr unsigned kCellF1 = 0x80000000u, kCellF2 = 0x40000000u, kCellF3 = 0x20000000u;
+
+__global__ void k_cl_cell_main(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cstart,
+                               const int32_t *__restrict__ ccnt, const int64_t *__restrict__ bq_scalars,
+                               const uint2 *__restrict__ pl, const uint32_t *__restrict__ snap, uint2 *__restrict__ cellsum) {
+    const int64_t nCells = bq_scalars[0];
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += (int64_t)gridDim.x * blockDim.x) {
+        const int nq = __ldg(ccnt + c), qs = __ldg(cstart + c);
+        const uint32_t p0 = __ldg(sorted_pt + qs);
+        unsigned M = pl[p0].y, R = __ldg(snap + p0) & kSnapRoot;
+        if (nq >= 3) {                       // majority of three: one noisy label or one stray does not name the cell
+            const uint32_t p1 = __ldg(sorted_pt + qs + 1), p2 = __ldg(sorted_pt + qs + 2);
+            const unsigned l1 = pl[p1].y, l2 = pl[p2].y;
+            const unsigned r1 = __ldg(snap + p1) & kSnapRoot, r2 = __ldg(snap + p2) & kSnapRoot;
+            if (l1 == l2 && r1 == r2 && (l1 != M || r1 != R)) { M = l1; R = r1; }
+        }
+        cellsum[c] = make_uint2(M, R);
+    }
+}
+
+__global__ void k_cl_cell_flags(const int32_t *__restrict__ cell, const uint2 *__restrict__ pl, const uint32_t *__restrict__ snap,
+                                int32_t N, uint2 *cellsum) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const unsigned sv = __ldg(snap + i);
+    if (!(sv & kSnapFull)) return;           // only full lists raise flags
+    const int c = __ldg(cell + i);
+    const uint2 cs = cellsum[c];             // .x never changes; .y only gains flag bits
+    unsigned f = kCellF3;
+    if (pl[i].y == cs.x) f |= kCellF2 | (((sv & kSnapRoot) != (cs.y & kSnapRoot)) ? kCellF1 : 0u);
+    if ((cs.y & f) != f) atomicOr(&cellsum[c].y, f);
+}
+
+// cstate[c]: 1 settled, 0 not; cells that need the point-level recheck are appended to `queue`
+__global__ void k_cl_cell_settle(const int32_t *__restrict__ nbr, const int64_t *__restrict__ bq_scalars,
+                                 const uint2 *__restrict__ cellsum, uint32_t *__restrict__ cstate, int32_t *__restrict__ queue,
+                                 unsigned long long *scalars) {
+    const int64_t nCells = bq_scalars[0];
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += (int64_t)gridDim.x * blockDim.x) {
+        const uint2 me = cellsum[c];
+        const unsigned R = me.y & kSnapRoot;
+        bool ok = !(me.y & kCellF1), recheck = false;
+        if (ok) {
+            const int32_t *nb = nbr + c * 27;
+#pragma unroll 9
+            for (int j = 0; j < 27; j++) {
+                const int b = __ldg(nb + j);
+                if (b < 0 || b == (int)c) continue;
+                const uint2 o = cellsum[b];
+                const unsigned Rb = o.y & kSnapRoot;
+                if (o.x == me.x) {
+                    if (Rb == R ? !(o.y & kCellF1) : (R < Rb && !(o.y & kCellF2))) continue;
+                    ok = false;
+                    break;
+                }
+                if (o.y & kCellF3) recheck = true;
+            }
+        }
+        if (ok && recheck) queue[atomicAdd(&scalars[9], 1ULL)] = (int32_t)c;
+        cstate[c] = ok && !recheck ? 1u : 0u;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_cl_cell_recheck(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cstart,
+                                                         const int32_t *__restrict__ ccnt, const int32_t *__restrict__ nbr,
+                                                         const uint2 *__restrict__ pl, const uint32_t *__restrict__ snap,
+                                                         const uint2 *__restrict__ cellsum, const int32_t *__restrict__ queue,
+                                                         uint32_t *__restrict__ cstate, const unsigned long long *scalars) {
+    const int lane = threadIdx.x & 31;
+    const int64_t nQ = (int64_t)scalars[9];
+    const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < nQ; t += nWarps) {
+        const int c = __ldg(queue + t);
+        const uint2 me = cellsum[c];
+        const unsigned M = me.x, R = me.y & kSnapRoot;
+        // lane j < 27 owns neighbour j; cells with another main label and a full point are scanned point by point
+        int b = -1;
+        if (lane < 27) b = __ldg(nbr + (int64_t)c * 27 + lane);
+        bool need = false;
+        if (b >= 0 && b != c) { const uint2 o = cellsum[b]; need = o.x != M && (o.y & kCellF3); }
+        unsigned todo = __ballot_sync(0xffffffffu, need);
+        bool viol = false;
+        while (todo && !viol) {
+            const int j = __ffs((int)todo) - 1;
+            todo &= todo - 1u;
+            const int bb = __shfl_sync(0xffffffffu, b, j);
+            const int s0 = __ldg(cstart + bb), l0 = __ldg(ccnt + bb);
+            for (int e = lane; e < l0 && !viol; e += 32) {
+                const uint32_t pt = __ldg(sorted_pt + s0 + e);
+                const unsigned sv = __ldg(snap + pt);
+                // a full stray of (M, R): full bit, label bits of M, another root, and really label M
+                if ((sv & kSnapFull) && (sv & kSnapLabel) == ((M & 31u) << 26) && (sv & kSnapRoot) != R && pl[pt].y == M) viol = true;
+            }
+            viol = __any_sync(0xffffffffu, viol);
+        }
+        if (lane == 0) cstate[c] = viol ? 0u : 1u;
+    }
+}
+
+__global__ void k_cl_cell_worklist(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cell,
+                                   const uint2 *__restrict__ pl, const uint32_t *__restrict__ snap,
+                                   const uint2 *__restrict__ cellsum, const uint32_t *__restrict__ cstate, int32_t N,
+                                   uint32_t *__restrict__ worklist, unsigned long long *scalars) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    bool keep = false;
+    uint32_t i = 0;
+    if (q < N) {
+        i = __ldg(sorted_pt + q);
+        const int c = __ldg(cell + i);
+        const uint2 cs = cellsum[c];
+        keep = !(__ldg(cstate + c) && pl[i].y == cs.x && (__ldg(snap + i) & kSnapRoot) == (cs.y & kSnapRoot));
+    }
+    // blocks append in whatever order they run; inside a block the query order is kept (a cell's lists share
+    // their entries, and cells rarely straddle blocks)
+    __shared__ unsigned long long s_base;
+    __shared__ int s_warp[8];
+    const unsigned km = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(km);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; w++) { const int t = s_warp[w]; s_warp[w] = tot; tot += t; }
+        s_base = tot ? atomicAdd(&scalars[8], (unsigned long long)tot) : 0ULL;
+    }
+    __syncthreads();
+    if (keep) worklist[s_base + s_warp[warp] + __popc(km & lanemask_lt())] = i;
 }
 
 // Roots go to their own array: writing them back into the forest would race with the path-halving
@@ -501,17 +668,20 @@ __global__ void k_cl_emit(const uint32_t *__restrict__ keys, const uint32_t *__r
 using namespace pg;
 
 // diagnostics of the most recent pg_bfs_cluster_count on this thread: {checksum != 0, bad, pending, sweeps}
-static thread_local long long g_cl_dbg[4] = {0, 0, 0, 0};
-extern "C" void pg_bfs_cluster_debug(long long *out) { for (int i = 0; i < 4; i++) out[i] = g_cl_dbg[i]; }
+// [4] lists the edge sweep read (N unless the grid-assisted mode settled whole cells first)
+static thread_local long long g_cl_dbg[5] = {0, 0, 0, 0, 0};
+extern "C" void pg_bfs_cluster_debug(long long *out) { for (int i = 0; i < 5; i++) out[i] = g_cl_dbg[i]; }
 
 extern "C" size_t pg_bfs_cluster_workspace_bytes(int64_t N) {
     if (N < 0) N = 0;
     return cl_layout(nullptr, 0, N).used + 256;
 }
 
-extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t *ball_query_idxs,
-                                    const int32_t *start_len, int32_t N, int64_t nActive, int32_t threshold,
-                                    int mode, void *ws, size_t ws_bytes, int32_t *host_sizes, void *stream) {
+// `bq_ws` (optional, trusted mode only): the workspace of the pg_ballquery_* calls that produced the lists,
+// untouched since -- its grid lets whole cells skip the edge sweep (k_cl_cells)
+static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_query_idxs, const int32_t *start_len, int32_t N,
+                          int64_t nActive, int32_t threshold, int mode, void *ws, size_t ws_bytes, void *bq_ws,
+                          size_t bq_ws_bytes, int32_t *host_sizes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     PG_CHECK_ARG(host_sizes, "null host_sizes");
     host_sizes[0] = host_sizes[1] = host_sizes[2] = 0;
@@ -527,7 +697,7 @@ extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t
     const unsigned nb = (unsigned)div_up(N, 256);
     const bool wide = nActive / N >= 12;          // lanes per neighbour list: 32 for long lists, 8 for short
     const unsigned eg = kNumSM * 8;
-    PG_CUDA(cudaMemsetAsync(w.scalars, 0, 8 * sizeof(unsigned long long), st));
+    PG_CUDA(cudaMemsetAsync(w.scalars, 0, 12 * sizeof(unsigned long long), st));
     PG_CUDA(cudaMemsetAsync(w.size, 0, ((size_t)N + 1) * sizeof(int32_t), st));
     // sweep order = ascending segment start, on the top 16 bits of the position (two radix passes)
     int abits = 0;
@@ -536,25 +706,52 @@ extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t
     k_cl_prep<<<(unsigned)div_up((int64_t)N + 32, 256), 256, 0, st>>>(semantic_label, ball_query_idxs, sl, N, nActive,
                                                                      generic ? 0 : 1, w.pl, w.trunc, w.last, w.root, w.lab,
                                                                      w.key0, shift, w.scalars);
-    unsigned long long h[4] = {0, 0, 0, 0};
+    unsigned long long h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     bool use_generic = generic != 0;
     const bool trusted = mode == PG_BFS_TRUSTED;
+    const bool grid = trusted && bq_ws != nullptr;
+    BqWs g{};
+    if (grid) {
+        g = bq_layout(bq_ws, bq_ws_bytes, N);
+        if (!g.ok) { set_error("pg_bfs_cluster_count_grid: ball-query workspace too small for N = %d", N); return PG_EWORKSPACE; }
+    }
     if (!use_generic) {
-        int res = 0;
-        PG_TRY(radix_sort_pairs(w.key0, nullptr, w.kA, w.vA, w.kB, w.vB, N, abits - shift < 1 ? 1 : abits - shift, w.hist,
-                                w.scan_tmp, st, &res));
-        const uint32_t *order = res == 0 ? w.vA : w.vB;
+        // the cell pass pays off on long lists only: it reads ~27 cells' worth of candidates per cell, which on
+        // short lists (raw coordinates, ~5 neighbours per point) is more than the edges themselves
+        const bool use_cells = grid && wide;
+        const uint32_t *order;
+        if (use_cells) {
+            order = w.vA;               // the work list k_cl_cells leaves: query order minus the settled lists
+        } else if (grid) {
+            order = bq_sorted(g, N);    // the ball query's own query order IS the segment order
+        } else {
+            int res = 0;
+            PG_TRY(radix_sort_pairs(w.key0, nullptr, w.kA, w.vA, w.kB, w.vB, N, abits - shift < 1 ? 1 : abits - shift, w.hist,
+                                    w.scan_tmp, st, &res));
+            order = res == 0 ? w.vA : w.vB;
+        }
         k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
         for (int round = 0; round < kSampleRounds; round++) {
             { PG_KTIME("k_cl_sample", st);
-            k_cl_sample<<<nb, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.last, w.snap, N, round); }
+            k_cl_sample<2><<<nb, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.last, w.snap, N, round); }
             PG_KTIME("k_cl_flatten", st);
             k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
+        }
+        if (use_cells) {
+            PG_KTIME("k_cl_cells", st);      // the five passes of the cell pre-pass, timed as one
+            const uint32_t *sp = bq_sorted(g, N);
+            const unsigned cg = kNumSM * 8;
+            k_cl_cell_main<<<cg, 256, 0, st>>>(sp, g.cstart, g.ccnt, g.scalars, w.pl, w.snap, w.cellsum);
+            k_cl_cell_flags<<<nb, 256, 0, st>>>(g.cell, w.pl, w.snap, N, w.cellsum);
+            k_cl_cell_settle<<<cg, 256, 0, st>>>(g.nbr, g.scalars, w.cellsum, w.cstate, w.cqueue, w.scalars);
+            k_cl_cell_recheck<<<cg, 256, 0, st>>>(sp, g.cstart, g.ccnt, g.nbr, w.pl, w.snap, w.cellsum, w.cqueue, w.cstate,
+                                                  w.scalars);
+            k_cl_cell_worklist<<<nb, 256, 0, st>>>(sp, g.cell, w.pl, w.snap, w.cellsum, w.cstate, N, w.vA, w.scalars);
         }
         const unsigned vg = kNumSM * 3;
 #define PG_VERIFY(G, T)                                                                                              \
     k_cl_verify<G, T><<<vg, kVerThreads, 0, st>>>(ball_query_idxs, sl, order, w.pl, w.last, w.snap, N, w.pend,     \
-                                                  (unsigned)w.pend_cap, w.scalars)
+                                                  (unsigned)w.pend_cap, w.scalars, use_cells ? 1 : 0)
         { PG_KTIME(trusted ? "k_cl_verify<trusted>" : "k_cl_verify<validating>", st);
         if (trusted) { if (wide) PG_VERIFY(32, true); else PG_VERIFY(8, true); }
         else { if (wide) PG_VERIFY(32, false); else PG_VERIFY(8, false); } }
@@ -574,6 +771,7 @@ extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t
     }
     const unsigned long long n_pend = use_generic ? 0 : h[2];
     g_cl_dbg[0] = h[0] != 0; g_cl_dbg[1] = (long long)h[1]; g_cl_dbg[2] = (long long)h[2]; g_cl_dbg[3] = 0;
+    g_cl_dbg[4] = (grid && h[8]) ? (long long)h[8] : (long long)N;
     const bool sweep = use_generic || n_pend > w.pend_cap;
     if (sweep || n_pend > 0) {
         for (int it = 0; it < 1000000; it++) {
@@ -609,6 +807,22 @@ extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t
     host_sizes[1] = (int32_t)r[1];
     host_sizes[2] = use_generic ? 1 : 0;
     return PG_OK;
+}
+
+extern "C" int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t *ball_query_idxs,
+                                    const int32_t *start_len, int32_t N, int64_t nActive, int32_t threshold,
+                                    int mode, void *ws, size_t ws_bytes, int32_t *host_sizes, void *stream) {
+    return bfs_count_impl(semantic_label, ball_query_idxs, start_len, N, nActive, threshold, mode, ws, ws_bytes, nullptr, 0,
+                          host_sizes, stream);
+}
+
+extern "C" int pg_bfs_cluster_count_grid(const int32_t *semantic_label, const int32_t *ball_query_idxs,
+                                         const int32_t *start_len, int32_t N, int64_t nActive, int32_t threshold,
+                                         void *ws, size_t ws_bytes, void *ballquery_ws, size_t ballquery_ws_bytes,
+                                         int32_t *host_sizes, void *stream) {
+    PG_CHECK_ARG(ballquery_ws != nullptr, "null ballquery_ws");
+    return bfs_count_impl(semantic_label, ball_query_idxs, start_len, N, nActive, threshold, PG_BFS_TRUSTED, ws, ws_bytes,
+                          ballquery_ws, ballquery_ws_bytes, host_sizes, stream);
 }
 
 extern "C" int pg_bfs_cluster_fill(int32_t N, int32_t nCluster, int32_t sumNPoint, void *ws, size_t ws_bytes,

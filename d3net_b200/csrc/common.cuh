@@ -58,6 +58,18 @@ struct KTimer {
 #define PG_KT_CAT(a, b) PG_KT_CAT2(a, b)
 #define PG_KTIME(name, st) pg::KTimer PG_KT_CAT(_pg_kt_, __LINE__)(name, st)
 
+// Resident blocks per SM of `kernel` at (threads, dynamic smem), asked of the runtime once per call site.
+// Statically partitioned grid-stride kernels size their grid as kNumSM * resident * k: a grid that is not a
+// multiple of what fits leaves a second, mostly empty wave (k_bq_fill_mask: 40 registers -> 6 blocks of 256
+// per SM, so a grid of 8 per SM ran as one full wave plus a third of one, 51 % achieved occupancy).
+template <typename K>
+inline int resident_blocks(K kernel, int threads, size_t smem = 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+    return nb;
+}
+#define PG_RESIDENT(kernel, threads, smem) ([&]() { static const int _n = pg::resident_blocks(kernel, threads, smem); return _n; }())
+
 inline int64_t div_up(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t a, size_t b = 256) { return (a + b - 1) / b * b; }
 

@@ -149,6 +149,7 @@ class BallQueryBatchP(Function):
         t = _sub("fill")
         PG_OP.ballquery_fill_impl(coords, radius, start_len, idx, ws)
         _end(t)
+        BallQueryBatchP._last_ws = ws[0]
         ctx.mark_non_differentiable(idx, start_len)
         return idx, start_len
 
@@ -157,11 +158,19 @@ class BallQueryBatchP(Function):
         return None, None, None, None, None
 
 
-def _stamp(idx, start_len):
+BallQueryBatchP._last_ws = None
+
+# bfs_cluster on stamped lists also gets the ball query's uniform grid (its workspace tensor, kept alive by the
+# stamp): cells that are already one component are not swept (pg_bfs_cluster_count_grid).  Results are identical.
+USE_GRID_SWEEP = True
+
+
+def _stamp(idx, start_len, grid_ws=None):
     """Provenance of a neighbour-list pair: the two tensors, as produced here and never written since
     (torch bumps ``_version`` on every in-place write).  bfs_cluster may then skip the validation it
     runs on foreign lists."""
     idx._pg_lists = (start_len.data_ptr(), start_len._version, idx._version, tuple(start_len.shape))
+    idx._pg_grid = grid_ws
 
 
 def _stamped(idx, start_len):
@@ -172,7 +181,8 @@ def _stamped(idx, start_len):
 
 def ballquery_batch_p(coords, batch_idxs, batch_offsets, radius, meanActive):
     idx, start_len = BallQueryBatchP.apply(coords, batch_idxs, batch_offsets, radius, meanActive)
-    _stamp(idx, start_len)
+    ws, BallQueryBatchP._last_ws = BallQueryBatchP._last_ws, None
+    _stamp(idx, start_len, ws)
     return idx, start_len
 
 
@@ -191,8 +201,10 @@ class BFSCluster(Function):
         assert ball_query_idxs.is_contiguous()
         assert start_len.is_contiguous()
         dev = PG_OP._compute_device(semantic_label)
+        trusted = _stamped(ball_query_idxs, start_len)
+        grid_ws = getattr(ball_query_idxs, "_pg_grid", None) if (trusted and USE_GRID_SWEEP) else None
         ci, co, _ = PG_OP.bfs_cluster_impl(semantic_label.to(dev), ball_query_idxs.to(dev), start_len.to(dev),
-                                           threshold, trusted=_stamped(ball_query_idxs, start_len))
+                                           threshold, trusted=trusted, grid_ws=grid_ws)
         if not semantic_label.is_cuda:
             ci, co = ci.cpu(), co.cpu()
         ctx.mark_non_differentiable(ci, co)
@@ -352,3 +364,24 @@ def cluster_voxel_coords(coords, cluster_idxs, cluster_offsets, fullscale, scale
     voxelization_idx, center [nC,3], size [nC,3]); not differentiable (the reference's `.long()` is not either)."""
     return PG_OP.cluster_coords(coords.contiguous(), cluster_idxs.contiguous(), cluster_offsets.contiguous(), fullscale,
                                 scale, rand6.contiguous())
+
+
+def cross_iou(proposals_idx, num_proposals, N, want_npoint=False):
+    """Not part of the reference's operator API: the proposal-vs-proposal IoU matrix of the instance NMS in
+    PointGroup.test (model/pointgroup.py:577-590) without the dense [nProposal, N] mask and its matmul.
+    ``proposals_idx`` int32 [sumNPoint, 2] rows (proposal id, point id) as bfs_cluster returns them (CPU
+    tensors are staged through the current CUDA device); returns fp32 [num_proposals, num_proposals],
+    bit-identical to ``inter / (n_h + n_v - inter)`` of the reference."""
+    dev = PG_OP._compute_device(proposals_idx)
+    res = PG_OP.cross_iou(proposals_idx.to(dev).contiguous(), num_proposals, N, want_npoint)
+    if proposals_idx.is_cuda:
+        return res
+    return tuple(r.cpu() for r in res) if want_npoint else res.cpu()
+
+
+def nms_instances(cross_ious, scores, threshold):
+    """get_nms_instances (lib/utils/eval.py:75-97) on the device; torch tensors in, int32 pick indices out
+    (the reference takes and returns numpy arrays after copying the matrix to the host)."""
+    dev = PG_OP._compute_device(scores)
+    pick = PG_OP.nms_instances(cross_ious.to(dev).float().contiguous(), scores.to(dev).float().contiguous(), threshold)
+    return pick if scores.is_cuda else pick.cpu()

@@ -129,6 +129,18 @@ size_t pg_bfs_cluster_workspace_bytes(int64_t N);
 int pg_bfs_cluster_count(const int32_t *semantic_label, const int32_t *ball_query_idxs,
                          const int32_t *start_len, int32_t N, int64_t nActive, int32_t threshold, int mode,
                          void *ws, size_t ws_bytes, int32_t *host_sizes, void *stream);
+/* Trusted lists together with the workspace of the pg_ballquery_prepare/count/fill calls that produced them
+ * (same n = N, not written since): the ball query's uniform grid is still in there, and a cell whose whole
+ * 27-cell neighbourhood already sits in one component after the sampling rounds has nothing left to tell the
+ * edge sweep -- its lists are not read at all.  Results are identical to
+ * pg_bfs_cluster_count; phase 2 is the same pg_bfs_cluster_fill. */
+int pg_bfs_cluster_count_grid(const int32_t *semantic_label, const int32_t *ball_query_idxs,
+                              const int32_t *start_len, int32_t N, int64_t nActive, int32_t threshold, void *ws,
+                              size_t ws_bytes, void *ballquery_ws, size_t ballquery_ws_bytes, int32_t *host_sizes,
+                              void *stream);
+/* Diagnostics of this thread's last count phase (no reference counterpart): out[5] = {list checksum failed,
+ * malformed lists, parked one-way edges, propagation sweeps, neighbour lists the edge sweep read}. */
+void pg_bfs_cluster_debug(long long *out);
 int pg_bfs_cluster_fill(int32_t N, int32_t nCluster, int32_t sumNPoint, void *ws, size_t ws_bytes,
                         int32_t *cluster_idxs, int32_t *cluster_offsets, void *stream);
 
@@ -199,6 +211,27 @@ int pg_pack_proposals(const int32_t *proposals_idx, const int32_t *proposals_off
                       const int64_t *semantic_preds, const float *center, const float *size, const float *feats,
                       const float *score, int32_t nProposal, int32_t C, int32_t B, int32_t P, int32_t *ws, float *out,
                       void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * cross_iou / nms_instances     (no native counterpart: the instance NMS of PointGroup.test)
+ * cross_iou replaces model/pointgroup.py:577-590 -- a dense int mask [nProposal, N] scattered from the
+ * (proposal, point) rows of proposals_idx, its product with its own transpose (torch.mm) and
+ * inter / (n_p + n_q - inter) -- by a sparse count over the rows themselves.  proposals_idx int32
+ * [nPairs, 2] in any order, repeated rows count once (as in the mask); cross_ious fp32 [nProposal, nProposal],
+ * bit-identical to the torch sequence (0/0 = NaN for proposals without points); npoint int32 [nProposal]
+ * (optional) = distinct points per proposal (proposals_mask.sum(1), :582).  Synchronises `stream` once
+ * (rows outside [0, nProposal) x [0, N) are reported as PG_EINVAL).
+ * nms_instances replaces lib/utils/eval.py:75-97 (get_nms_instances, numpy on the host after a D2H copy of
+ * the matrix): proposals in descending score order (ties: lower index first; NaN scores last), a proposal
+ * is dropped when a kept one has cross_iou > threshold with it.  pick int32 [n] receives the kept
+ * proposals in pick order, *host_n_pick their number.
+ * ---------------------------------------------------------------------------------------------- */
+size_t pg_cross_iou_workspace_bytes(int64_t nPairs, int64_t nProposal, int64_t N);
+int pg_cross_iou(const int32_t *proposals_idx, int32_t nPairs, int32_t nProposal, int32_t N, void *ws,
+                 size_t ws_bytes, float *cross_ious, int32_t *npoint, void *stream);
+size_t pg_nms_instances_workspace_bytes(int32_t n);
+int pg_nms_instances(const float *cross_ious, const float *scores, int32_t n, float threshold, void *ws,
+                     size_t ws_bytes, int32_t *pick, int32_t *host_n_pick, void *stream);
 
 #ifdef __cplusplus
 }

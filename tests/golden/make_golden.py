@@ -4,6 +4,7 @@ built by oracle/build_ref.py from the unmodified sources under /root/reference).
 
     python tests/golden/make_golden.py cpu     # this container: voxelize_idx, bfs_cluster (the reference's CPU ops)
     python tests/golden/make_golden.py gpu OUT # on the B200 box (gpurun): the nine CUDA kernels -> OUT/ref_gpu.npz
+    python tests/golden/make_golden.py nms     # this container: instance NMS (reference Python, torch CPU) -> ref_nms.npz
 
 Inputs are NOT stored: golden_inputs(case) regenerates them from fixed seeds, so the fixtures stay small.
 The reference ships no tests or vectors of its own; these files are what pins the
@@ -54,6 +55,20 @@ def golden_inputs(case):
                 "grad": rng.standard_normal((len(lens), 16)).astype(np.float32),
                 "pidx": rng.integers(0, N, int(off[-1])).astype(np.int32), "labels": labels,
                 "pointnum": np.bincount(labels[labels >= 0], minlength=nI).astype(np.int32)}
+    if case == "nms":
+        # two overlapping partitions of a point set (what the raw and the shifted clustering produce), a few
+        # repeated rows, one proposal without points, distinct scores
+        N, nA, nB = 6000, 23, 19
+        la = rng.integers(-1, nA, N)
+        stick = (np.maximum(la, 0) + 1) / nA              # per-cluster overlap: IoUs from ~0.03 to ~0.9
+        lb = np.where(rng.random(N) < stick, la % nB, rng.integers(-1, nB, N))
+        rows = [(a, p) for p, a in enumerate(la) if a >= 0] + [(nA + b, p) for p, b in enumerate(lb) if b >= 0]
+        rows += rows[:50]
+        pidx = np.array(rows, np.int32)
+        pidx = pidx[np.argsort(pidx[:, 0], kind="stable")]
+        nP = nA + nB + 1                                  # the last proposal has no rows
+        scores = rng.permutation(nP).astype(np.float32) / nP
+        return {"proposals_idx": pidx, "num_proposals": nP, "N": N, "scores": scores, "threshold": 0.3}
     raise KeyError(case)
 
 
@@ -86,6 +101,41 @@ def make_cpu():
         out["bfs_ci_t%d" % thr], out["bfs_co_t%d" % thr] = ci.numpy(), co.numpy()
     np.savez_compressed(os.path.join(HERE, "ref_cpu.npz"), **out)
     print("wrote ref_cpu.npz:", {k: v.shape for k, v in out.items()})
+
+
+def _reference_function(path, name):
+    """The reference's own source of one top-level function, compiled in place (the module around it imports
+    packages that are not installed here)."""
+    import ast
+    src = open(path).read()
+    node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == name)
+    ns = {"np": np}
+    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    return ns[name]
+
+
+def make_nms():
+    """cross_ious: the statements of model/pointgroup.py:577-590 executed by torch on the CPU; picks: the
+    reference's get_nms_instances (lib/utils/eval.py:75-97) run on that matrix."""
+    import torch
+    g = golden_inputs("nms")
+    pidx = torch.from_numpy(g["proposals_idx"])
+    nP, N = g["num_proposals"], g["N"]
+    mask = torch.zeros((nP, N), dtype=torch.int)
+    mask[pidx[:, 0].long(), pidx[:, 1].long()] = 1
+    npoint_int = mask.sum(1)
+    mf = mask.float()
+    inter = torch.mm(mf, mf.t())
+    npoint = mf.sum(1)
+    h = npoint.unsqueeze(-1).repeat(1, nP)
+    v = npoint.unsqueeze(0).repeat(nP, 1)
+    cross = inter / (h + v - inter)
+    nms = _reference_function("/root/reference/lib/utils/eval.py", "get_nms_instances")
+    out = {"cross_ious": cross.numpy(), "npoint": npoint_int.numpy().astype(np.int32)}
+    for thr in (0.3, 0.1, 0.6):
+        out["pick_%g" % thr] = nms(cross.numpy(), g["scores"], thr)
+    np.savez_compressed(os.path.join(HERE, "ref_nms.npz"), **out)
+    print("wrote ref_nms.npz:", {k: v.shape for k, v in out.items()})
 
 
 def make_gpu(outdir):
@@ -149,5 +199,7 @@ def make_gpu(outdir):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "gpu":
         make_gpu(sys.argv[2] if len(sys.argv) > 2 else HERE)
+    elif len(sys.argv) > 1 and sys.argv[1] == "nms":
+        make_nms()
     else:
         make_cpu()

@@ -355,6 +355,70 @@ def test_bfs_trusted_lists_by_provenance(ops, oracle):
     assert not pgo._stamped(idx, sl)
 
 
+def _grid_vs_oracle(ops, oracle, xyz, bi, bo, sem, r, thr):
+    """bfs_cluster with the ball query's grid (cells already in one component are not swept), the plain
+    trusted sweep and the validating sweep must all give the oracle's clusters."""
+    from d3net_b200 import PG_OP, pointgroup_ops as pgo
+    idx, sl = ops.ballquery_batch_p(cu(xyz), cu(bi), cu(bo), r, 50)
+    assert pgo._stamped(idx, sl) and idx._pg_grid is not None
+    ridx, rsl = oracle.ballquery_batch_p(xyz, bi, bo, r)
+    rci, rco = oracle.bfs_cluster(sem, ridx, rsl, thr)
+    want = oracle.canonical_clusters(rci, rco)
+    swept = {}
+    for name, kw in (("grid", dict(trusted=True, grid_ws=idx._pg_grid)), ("trusted", dict(trusted=True)), ("auto", {})):
+        ci, co, generic = PG_OP.bfs_cluster_impl(cu(sem), idx, sl, thr, **kw)
+        assert not generic
+        np.testing.assert_array_equal(npy(co), rco)
+        got = oracle.canonical_clusters(npy(ci), npy(co))
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)
+        swept[name] = PG_OP.bfs_cluster_debug()[4]
+    ci, co = ops.bfs_cluster(cu(sem), idx, sl, thr)               # the operator picks the grid sweep itself
+    np.testing.assert_array_equal(npy(co), rco)
+    assert swept["trusted"] == len(xyz) and swept["grid"] <= len(xyz)
+    return swept["grid"]
+
+
+def test_bfs_grid_sweep_scene(ops, oracle):
+    """Scene-shaped input, noisy labels, raw and shifted coordinates (the shifted blobs are where whole
+    cells settle before the sweep)."""
+    s = object_subset(small_batch(3, 15000))
+    n = len(s["sem"])
+    for key in ("coords", "shifted"):
+        swept = _grid_vs_oracle(ops, oracle, s[key], s["batch_idxs"], s["batch_offsets"], s["sem"], 0.03, 50)
+        if key == "shifted":
+            assert swept < n // 2, "the cell pass should settle most of the shifted blobs (%d of %d lists swept)" % (swept, n)
+
+
+def test_bfs_grid_sweep_truncated_and_bridged(ops, oracle):
+    """Blobs dense enough to cut lists at 1000 (one-way edges, cells the ball query left early), joined by a
+    thin bridge and surrounded by clutter, two interleaved labels."""
+    rng = np.random.default_rng(21)
+    blobs = [rng.normal(c, 0.006, (1800, 3)) for c in ([0, 0, 0], [0.05, 0, 0], [0.3, 0.3, 0])]
+    bridge = np.linspace([0, 0, 0], [0.3, 0.3, 0], 40)
+    xyz = np.concatenate(blobs + [bridge, rng.uniform(-1, 1, (2500, 3))]).astype(np.float32)
+    xyz = xyz[rng.permutation(len(xyz))]
+    n = len(xyz)
+    bi, bo = np.zeros(n, np.int32), np.array([0, n], np.int32)
+    for labels in (np.ones(n, np.int32), rng.integers(1, 3, n).astype(np.int32),
+                   np.where(rng.random(n) < 0.05, 7, 1).astype(np.int32)):
+        _grid_vs_oracle(ops, oracle, xyz, bi, bo, labels, 0.03, 5)
+
+
+@pytest.mark.parametrize("r", [0.0, 5.0, 0.012])
+def test_bfs_grid_sweep_radius_extremes(ops, oracle, r):
+    """r = 0 (one cell per scene, only duplicates are neighbours), a radius that makes each scene a clique,
+    and a radius below the point pitch (isolated points)."""
+    rng = np.random.default_rng(5)
+    xyz = rng.uniform(0, 1, (1500, 3)).astype(np.float32)
+    xyz[100:110] = xyz[100]                                       # duplicates
+    bi = np.repeat(np.arange(3, dtype=np.int32), 500)
+    bo = np.array([0, 500, 1000, 1500], np.int32)
+    sem = rng.integers(1, 4, 1500).astype(np.int32)
+    _grid_vs_oracle(ops, oracle, xyz, bi, bo, sem, r, 2)
+
+
 def test_bfs_empty(ops):
     z = torch.zeros(0, dtype=torch.int32).cuda()
     ci, co = ops.bfs_cluster(z, z, torch.zeros((0, 2), dtype=torch.int32).cuda(), 50)

@@ -12,5 +12,5 @@ for it in range(3):
     torch.cuda.synchronize(); t=time.time()
     ci, co, g = PG_OP.bfs_cluster_impl(sem_, idx, sl, 50)
     torch.cuda.synchronize(); dt=time.time()-t
-    d=(ctypes.c_longlong*4)(); _native.lib().pg_bfs_cluster_debug(d)
+    d=(ctypes.c_longlong*5)(); _native.lib().pg_bfs_cluster_debug(d)
     print('bfs ms', dt*1e3, 'generic', g, 'dbg', list(d), 'nC', co.numel()-1)
