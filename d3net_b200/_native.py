@@ -100,6 +100,7 @@ SIGNATURES = {
     "pg_cross_iou": (_int, [_vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
     "pg_nms_instances_workspace_bytes": (_sz, [_i32]),
     "pg_nms_instances": (_int, [_vp, _vp, _i32, _f32, _vp, _sz, _vp, _vp, _vp]),
+    "pg_collate_points": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "pg_cluster_coords_workspace_bytes": (_sz, [_i32]),
     "pg_cluster_coords": (_int, [_vp, _vp, _vp, _i32, _i32, _i32, _f32, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
 }

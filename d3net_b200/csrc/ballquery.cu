@@ -484,6 +484,7 @@ __global__ void k_bq_start_len(const uint32_t *__restrict__ sorted_pt, const int
 
 // ---- fill -------------------------------------------------------------------------------------------
 constexpr int kFillQ = 4;
+constexpr int kFillShortK = 96;          // candidate lists this short are decoded without the 8-block pipeline
 
 // without masks: a warp per query re-evaluates the predicate over the cell's sorted candidates
 __global__ void __launch_bounds__(256) k_bq_fill(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
@@ -523,6 +524,76 @@ __global__ void __launch_bounds__(256) k_bq_fill(const float *__restrict__ xyz, 
 
 // fill from hit masks: no coordinates, no predicate -- a word of 32 outcomes per (query, block); the
 // lane whose bit is set writes its candidate's index at (hits so far) + (set bits below it).
+// One call handles a RUN of L <= 4 consecutive queries of the same cell (queries q_first .. q_first + L - 1 of
+// the sorted order).  Eight blocks per trip: ONE load brings the 8 x 4 mask words (lane = block * 4 + query) and
+// eight independent loads the 256 candidate indices, so nine loads per lane are in flight together and
+// their latency is paid once per eight blocks.
+__device__ __forceinline__ void bq_fill_run(int64_t q_first, int L, int cc, const uint32_t *__restrict__ sorted_pt,
+                                            const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
+                                            const int32_t *__restrict__ cand_start, const int32_t *__restrict__ kb,
+                                            const uint32_t *__restrict__ cand_idx, const int32_t *__restrict__ mbase,
+                                            const uint32_t *__restrict__ masks, const int2 *__restrict__ start_len,
+                                            int32_t *__restrict__ idx, int lane, unsigned lt) {
+    const int K = __ldg(kb + cc);
+    const int nq = __ldg(ccnt + cc);
+    const uint32_t *cp = cand_idx + __ldg(cand_start + cc) + lane;
+    int wpos[kFillQ], wend[kFillQ];
+#pragma unroll
+    for (int u = 0; u < kFillQ; u++) {
+        wpos[u] = wend[u] = 0;
+        if (u < L) {
+            const int2 sl = __ldg(start_len + __ldg(sorted_pt + q_first + u));
+            wpos[u] = sl.x; wend[u] = sl.x + sl.y;
+        }
+    }
+    const int nb = (K + 31) >> 5;
+    const bool mine = (lane & 3) < L;              // this lane's (block, query) slot holds a query of the run
+    const uint32_t *mp8 = masks + __ldg(mbase + cc) + (int)(q_first - __ldg(cstart + cc)) + (int64_t)(lane >> 2) * nq + (lane & 3);
+    const unsigned lanebit = 1u << lane;
+    // A list shorter than the cap holds every hit of its query, so the recorded bits ARE the list: no
+    // position needs checking against the segment's end.  Only a run with a full list (kCap entries:
+    // later hits are dropped, and words past the last one may not have been written) takes the checked loop.
+    const bool capped = wend[0] - wpos[0] >= kCap || wend[1] - wpos[1] >= kCap || wend[2] - wpos[2] >= kCap ||
+                        wend[3] - wpos[3] >= kCap;
+    if (!capped) {
+        for (int b0 = 0; b0 < nb; b0 += 8) {
+            const unsigned mw = (mine && b0 + (lane >> 2) < nb) ? __ldg(mp8 + (int64_t)b0 * nq) : 0u;
+            int cidr[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) cidr[j] = ((b0 + j) * 32 + lane < K) ? (int)__ldg(cp + (b0 + j) * 32) : 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+#pragma unroll
+                for (int u = 0; u < kFillQ; u++) {
+                    const unsigned m = __shfl_sync(0xffffffffu, mw, j * 4 + u);
+                    if (m & lanebit) idx[wpos[u] + __popc(m & lt)] = cidr[j];
+                    wpos[u] += __popc(m);
+                }
+            }
+        }
+        return;
+    }
+    bool done = false;
+    for (int b0 = 0; b0 < nb && !done; b0 += 8) {
+        const unsigned mw = (mine && b0 + (lane >> 2) < nb) ? __ldg(mp8 + (int64_t)b0 * nq) : 0u;
+        int cidr[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) cidr[j] = ((b0 + j) * 32 + lane < K) ? (int)__ldg(cp + (b0 + j) * 32) : 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+#pragma unroll
+            for (int u = 0; u < kFillQ; u++) {
+                const unsigned m = __shfl_sync(0xffffffffu, mw, j * 4 + u);
+                const int pos = wpos[u] + __popc(m & lt);
+                if ((m & lanebit) && pos < wend[u]) idx[pos] = cidr[j];
+                wpos[u] = min(wpos[u] + __popc(m), wend[u]);   // words past a full list may be unwritten: stay put
+            }
+        }
+        done = wpos[0] >= wend[0] && wpos[1] >= wend[1] && wpos[2] >= wend[2] && wpos[3] >= wend[3];
+    }
+}
+
+// short candidate lists (a handful of 32-candidate blocks): nothing to pipeline, one query at a time
 __device__ __forceinline__ void bq_fill_mask_one(uint32_t k, const uint32_t *__restrict__ ci, int K,
                                                  const uint32_t *__restrict__ mrow, int nq,
                                                  const int2 *__restrict__ start_len, int32_t *__restrict__ idx, int lane,
@@ -539,7 +610,9 @@ __device__ __forceinline__ void bq_fill_mask_one(uint32_t k, const uint32_t *__r
     }
 }
 
-__global__ void __launch_bounds__(256) k_bq_fill_mask(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cell,
+// A warp takes four consecutive queries of the sorted order at a time and cuts them into runs of equal cell
+// (one run when the cell has at least four queries left, which is the common case on dense data).
+__global__ void __launch_bounds__(256, 5) k_bq_fill_mask(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cell,
                                                       const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
                                                       const int32_t *__restrict__ cand_start, const int32_t *__restrict__ kb,
                                                       const uint32_t *__restrict__ cand_idx, const int32_t *__restrict__ mbase,
@@ -550,81 +623,28 @@ __global__ void __launch_bounds__(256) k_bq_fill_mask(const uint32_t *__restrict
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t q0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kFillQ; q0 < n; q0 += nWarps * kFillQ) {
         const int nqr = (int)((n - q0) < kFillQ ? (n - q0) : kFillQ);
-        uint32_t k[kFillQ];
         int c[kFillQ];
-        bool same = nqr == kFillQ;
 #pragma unroll
-        for (int u = 0; u < kFillQ; u++) {
-            k[u] = u < nqr ? sorted_pt[q0 + u] : 0u;
-            c[u] = u < nqr ? __ldg(cell + k[u]) : -1;
-            same = same && c[u] == c[0];
-        }
-        if (!same) {
-            for (int u = 0; u < nqr; u++) {
-                const int cc = c[u];
-                bq_fill_mask_one(k[u], cand_idx + __ldg(cand_start + cc), __ldg(kb + cc),
-                                 masks + __ldg(mbase + cc) + (int)(q0 + u - __ldg(cstart + cc)), __ldg(ccnt + cc), start_len,
-                                 idx, lane, lt);
+        for (int u = 0; u < kFillQ; u++) c[u] = u < nqr ? __ldg(cell + __ldg(sorted_pt + q0 + u)) : -1;
+        // bit u of `ends`: a run of equal cell ends with query u (warp-uniform)
+        unsigned ends = 0;
+#pragma unroll
+        for (int u = 0; u < kFillQ; u++)
+            if (u < nqr && (u == nqr - 1 || c[(u + 1) % kFillQ] != c[u])) ends |= 1u << u;
+        int u0 = 0;
+        while (u0 < nqr) {
+            const int L = __ffs((int)(ends >> u0));
+            const int cc = u0 == 0 ? c[0] : __ldg(cell + __ldg(sorted_pt + q0 + u0));
+            const int K = __ldg(kb + cc);
+            if (K <= kFillShortK) {
+                for (int u = 0; u < L; u++)
+                    bq_fill_mask_one(__ldg(sorted_pt + q0 + u0 + u), cand_idx + __ldg(cand_start + cc), K,
+                                     masks + __ldg(mbase + cc) + (int)(q0 + u0 + u - __ldg(cstart + cc)), __ldg(ccnt + cc), start_len,
+                                     idx, lane, lt);
+            } else {
+                bq_fill_run(q0 + u0, L, cc, sorted_pt, cstart, ccnt, cand_start, kb, cand_idx, mbase, masks, start_len, idx, lane, lt);
             }
-            continue;
-        }
-        const int cc = c[0];
-        const int K = __ldg(kb + cc);
-        const int nq = __ldg(ccnt + cc);
-        // running pointers, 32-bit output positions: the loop body is ~10 instructions per (query, block)
-        const uint32_t *cp = cand_idx + __ldg(cand_start + cc) + lane;
-        int wpos[kFillQ], wend[kFillQ];
-#pragma unroll
-        for (int u = 0; u < kFillQ; u++) {
-            const int2 sl = __ldg(start_len + k[u]);
-            wpos[u] = sl.x; wend[u] = sl.x + sl.y;
-        }
-        // Eight blocks per trip: ONE load brings the 8 x 4 mask words (lane = block * 4 + query) and eight
-        // independent loads the 256 candidate indices, so nine loads per lane are in flight together
-        // and their latency is paid once per eight blocks.
-        const int nb = (K + 31) >> 5;
-        const uint32_t *mp8 = masks + __ldg(mbase + cc) + (int)(q0 - __ldg(cstart + cc)) + (int64_t)(lane >> 2) * nq + (lane & 3);
-        const unsigned lanebit = 1u << lane;
-        // A list shorter than the cap holds every hit of its query, so the recorded bits ARE the list: no
-        // position needs checking against the segment's end.  Only a group with a full list (kCap entries:
-        // later hits are dropped, and words past the last one may not have been written) takes the checked loop.
-        const bool capped = wend[0] - wpos[0] >= kCap || wend[1] - wpos[1] >= kCap || wend[2] - wpos[2] >= kCap ||
-                            wend[3] - wpos[3] >= kCap;
-        if (!capped) {
-            for (int b0 = 0; b0 < nb; b0 += 8) {
-                const unsigned mw = (b0 + (lane >> 2) < nb) ? __ldg(mp8 + (int64_t)b0 * nq) : 0u;
-                int cidr[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) cidr[j] = ((b0 + j) * 32 + lane < K) ? (int)__ldg(cp + (b0 + j) * 32) : 0;
-#pragma unroll
-                for (int j = 0; j < 8; j++) {
-#pragma unroll
-                    for (int u = 0; u < kFillQ; u++) {
-                        const unsigned m = __shfl_sync(0xffffffffu, mw, j * 4 + u);
-                        if (m & lanebit) idx[wpos[u] + __popc(m & lt)] = cidr[j];
-                        wpos[u] += __popc(m);
-                    }
-                }
-            }
-            continue;
-        }
-        bool done = false;
-        for (int b0 = 0; b0 < nb && !done; b0 += 8) {
-            const unsigned mw = (b0 + (lane >> 2) < nb) ? __ldg(mp8 + (int64_t)b0 * nq) : 0u;
-            int cidr[8];
-#pragma unroll
-            for (int j = 0; j < 8; j++) cidr[j] = ((b0 + j) * 32 + lane < K) ? (int)__ldg(cp + (b0 + j) * 32) : 0;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-#pragma unroll
-                for (int u = 0; u < kFillQ; u++) {
-                    const unsigned m = __shfl_sync(0xffffffffu, mw, j * 4 + u);
-                    const int pos = wpos[u] + __popc(m & lt);
-                    if ((m & lanebit) && pos < wend[u]) idx[pos] = cidr[j];
-                    wpos[u] = min(wpos[u] + __popc(m), wend[u]);   // words past a full list may be unwritten: stay put
-                }
-            }
-            done = wpos[0] >= wend[0] && wpos[1] >= wend[1] && wpos[2] >= wend[2] && wpos[3] >= wend[3];
+            u0 += L;
         }
     }
 }

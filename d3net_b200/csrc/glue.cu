@@ -206,6 +206,31 @@ __global__ void k_pack_rows(const int2 *__restrict__ proposals_idx, const int32_
     out[((int64_t)b * P + s) * kPackWidth + j] = v;
 }
 
+// ---- collate_points: the per-point part of sparse_collate_fn (lib/dataset/pipeline.py:937-985) ----------
+// One thread per point of the concatenated batch: its scene b (binary search in batch_offsets) becomes column 0
+// of locs_scaled (:939-943, the float coordinates truncated toward zero like .long()), sem_labels widen to
+// int64 (:982) and instance ids other than -1 move up by the instances of the scenes before (:963-964,983).
+__global__ void k_collate_points(const float *__restrict__ locs_scaled, const int32_t *__restrict__ sem_labels,
+                                 const int32_t *__restrict__ instance_ids, const int32_t *__restrict__ batch_offsets,
+                                 const int32_t *__restrict__ instance_offsets, int32_t N, int32_t B,
+                                 int64_t *__restrict__ out_locs, int64_t *__restrict__ out_sem, int64_t *__restrict__ out_inst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    int lo = 0, hi = B;                       // last b with batch_offsets[b] <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(batch_offsets + mid) <= i) lo = mid; else hi = mid;
+    }
+    const float *q = locs_scaled + 3 * (int64_t)i;
+    reinterpret_cast<longlong4 *>(out_locs)[i] =
+        make_longlong4((long long)lo, (long long)__ldg(q), (long long)__ldg(q + 1), (long long)__ldg(q + 2));
+    if (out_sem) out_sem[i] = (int64_t)__ldg(sem_labels + i);
+    if (out_inst) {
+        const int id = __ldg(instance_ids + i);
+        out_inst[i] = id == -1 ? -1 : (int64_t)id + (int64_t)__ldg(instance_offsets + lo);
+    }
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -257,6 +282,25 @@ extern "C" int pg_cluster_coords(const float *coords, const int32_t *cluster_idx
                                                      rand6, params, center, size); }
     k_glue_cluster_coords<<<(unsigned)div_up(sumNPoint, 256), 256, 0, st>>>(coords, (const int2 *)cluster_idxs, params, sumNPoint,
                                                                             out_coords);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
+extern "C" int pg_collate_points(const float *locs_scaled, const int32_t *sem_labels, const int32_t *instance_ids,
+                                 const int32_t *batch_offsets, const int32_t *instance_offsets, int32_t N, int32_t B,
+                                 int64_t *out_locs_scaled, int64_t *out_sem_labels, int64_t *out_instance_ids, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PG_CHECK_ARG(N >= 0 && B >= 0, "negative size");
+    if (N == 0) return PG_OK;
+    PG_CHECK_ARG(B >= 1, "points without a scene");
+    PG_CHECK_ARG(locs_scaled && batch_offsets && out_locs_scaled, "null pointer");
+    PG_CHECK_ARG((out_sem_labels == nullptr) == (sem_labels == nullptr), "sem_labels in / out must come together");
+    PG_CHECK_ARG((out_instance_ids == nullptr) == (instance_ids == nullptr) && (instance_ids == nullptr || instance_offsets),
+                 "instance_ids in / out / offsets must come together");
+    PG_CHECK_ARG(((uintptr_t)out_locs_scaled & 31u) == 0, "out_locs_scaled not 32-byte aligned");
+    k_collate_points<<<(unsigned)div_up(N, 256), 256, 0, st>>>(locs_scaled, sem_labels, instance_ids, batch_offsets,
+                                                               instance_offsets, N, B, out_locs_scaled, out_sem_labels,
+                                                               out_instance_ids);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

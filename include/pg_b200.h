@@ -233,6 +233,18 @@ size_t pg_nms_instances_workspace_bytes(int32_t n);
 int pg_nms_instances(const float *cross_ious, const float *scores, int32_t n, float threshold, void *ws,
                      size_t ws_bytes, int32_t *pick, int32_t *host_n_pick, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * collate_points     (no native counterpart: the per-point part of sparse_collate_fn,
+ *                    lib/dataset/pipeline.py:937-985, which the reference runs in forked CPU workers)
+ * For the concatenated points of B scenes (batch_offsets int32 [B+1]): out_locs_scaled int64 [N,4] =
+ * (scene, trunc(x), trunc(y), trunc(z)) of the fp32 voxel-scale coordinates (:939-943) -- the input of
+ * voxelize_idx --, out_sem_labels = int64 copy (:982), out_instance_ids = int64 ids with every id other
+ * than -1 moved up by instance_offsets[scene] (:963-964,983).  The sem / instance pairs may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+int pg_collate_points(const float *locs_scaled, const int32_t *sem_labels, const int32_t *instance_ids,
+                      const int32_t *batch_offsets, const int32_t *instance_offsets, int32_t N, int32_t B,
+                      int64_t *out_locs_scaled, int64_t *out_sem_labels, int64_t *out_instance_ids, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,6 +4,7 @@ built by oracle/build_ref.py from the unmodified sources under /root/reference).
 
     python tests/golden/make_golden.py cpu     # this container: voxelize_idx, bfs_cluster (the reference's CPU ops)
     python tests/golden/make_golden.py gpu OUT # on the B200 box (gpurun): the nine CUDA kernels -> OUT/ref_gpu.npz
+    python tests/golden/make_golden.py collate # this container: the reference's sparse_collate_fn -> ref_collate.npz
     python tests/golden/make_golden.py nms     # this container: instance NMS (reference Python, torch CPU) -> ref_nms.npz
 
 Inputs are NOT stored: golden_inputs(case) regenerates them from fixed seeds, so the fixtures stay small.
@@ -69,6 +70,20 @@ def golden_inputs(case):
         nP = nA + nB + 1                                  # the last proposal has no rows
         scores = rng.permutation(nP).astype(np.float32) / nP
         return {"proposals_idx": pidx, "num_proposals": nP, "N": N, "scores": scores, "threshold": 0.3}
+    if case == "collate":
+        # three scenes as PipelineDataset.__getitem__ hands them to the collate function (pipeline.py:180-187)
+        batch = []
+        for n, ninst in ((1500, 7), (2200, 11), (900, 3)):
+            locs = rng.uniform(0, 0.45, (n, 3)).astype(np.float32)     # ~22^3 voxels: points share voxels
+            scaled = ((locs - locs.min(0)) * 50).astype(np.float32)
+            inst = rng.integers(-1, ninst, n).astype(np.int32)
+            batch.append({"locs": locs, "locs_scaled": scaled, "feats": rng.standard_normal((n, 3)).astype(np.float32),
+                          "sem_labels": rng.integers(-1, 20, n).astype(np.int32), "instance_ids": inst,
+                          "num_instance": np.array(ninst).astype(np.int32),
+                          "instance_info": rng.standard_normal((n, 12)).astype(np.float32),
+                          "instance_num_point": np.bincount(inst[inst >= 0], minlength=ninst).astype(np.int32),
+                          "scene_id": "scene%04d_00" % n})
+        return {"batch": batch}
     raise KeyError(case)
 
 
@@ -138,6 +153,31 @@ def make_nms():
     print("wrote ref_nms.npz:", {k: v.shape for k, v in out.items()})
 
 
+def make_collate():
+    """The reference's own sparse_collate_fn / scannet_collate_fn (lib/dataset/pipeline.py:892-995) executed in
+    place on the golden scenes, with its voxelization_idx bound to the reference's compiled op (oracle/_ref)."""
+    import copy
+    import torch
+    from oracle.ops_adapter import OracleOps
+    ops = OracleOps(use_ref=True)
+    assert ops.ref is not None, "oracle/_ref/PG_OP.so is not built (needs /root/reference)"
+    path = "/root/reference/lib/dataset/pipeline.py"
+    ns = {"np": np, "torch": torch, "pointgroup_ops": ops, "batched_coordinates": None}
+    import ast
+    tree = ast.parse(open(path).read())
+    for name in ("scannet_collate_fn", "sparse_collate_fn"):
+        node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == name)
+        exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    g = golden_inputs("collate")
+    data = ns["sparse_collate_fn"](copy.deepcopy(g["batch"]))           # the reference shifts instance ids in place
+    out = {k: v.numpy() for k, v in data.items() if torch.is_tensor(v)}
+    cat = lambda k: np.concatenate([b[k] for b in g["batch"]], 0)
+    for k in ("locs", "feats", "instance_info"):       # pure concatenations: checked here, not stored
+        assert out[k].dtype == np.float32 and np.array_equal(out.pop(k), cat(k))
+    np.savez_compressed(os.path.join(HERE, "ref_collate.npz"), **out)
+    print("wrote ref_collate.npz:", {k: (v.shape, str(v.dtype)) for k, v in out.items()})
+
+
 def make_gpu(outdir):
     import torch
     ref = _load_ref()
@@ -201,5 +241,7 @@ if __name__ == "__main__":
         make_gpu(sys.argv[2] if len(sys.argv) > 2 else HERE)
     elif len(sys.argv) > 1 and sys.argv[1] == "nms":
         make_nms()
+    elif len(sys.argv) > 1 and sys.argv[1] == "collate":
+        make_collate()
     else:
         make_cpu()
