@@ -576,6 +576,37 @@ __global__ void k_cl_pending(const int2 *__restrict__ pend, unsigned long long n
     if (changed) scalars[3] = 1;
 }
 
+// The same fixed point without the host in the loop, for the trusted path: the parked edges are a few dozen to a
+// few thousand, so ONE block settles them -- the count phase then synchronises the stream once (for the sizes)
+// instead of twice.  More than kPendBlockMax parked edges: raise scalars[10]; the host reruns the two-sync path.
+constexpr unsigned long long kPendBlockMax = 1u << 16;
+
+__global__ void __launch_bounds__(1024) k_cl_pending_block(const int2 *__restrict__ pend, unsigned long long pend_cap,
+                                                           const int32_t *__restrict__ root, int32_t *lab,
+                                                           unsigned long long *scalars) {
+    const unsigned long long n_pend = scalars[2];
+    if (n_pend == 0) return;
+    if (n_pend > pend_cap || n_pend > kPendBlockMax) {
+        if (threadIdx.x == 0) scalars[10] = 1;
+        return;
+    }
+    __shared__ int s_changed;
+    for (int it = 0; it < (1 << 24); it++) {
+        if (threadIdx.x == 0) s_changed = 0;
+        __syncthreads();
+        bool changed = false;
+        for (unsigned long long t = threadIdx.x; t < n_pend; t += blockDim.x) {
+            const int2 e = pend[t];
+            if (root[e.x] != root[e.y]) changed |= propagate_edge(root, lab, e.x, e.y);
+        }
+        if (changed) s_changed = 1;
+        __syncthreads();
+        const int again = s_changed;
+        __syncthreads();
+        if (!again) break;
+    }
+}
+
 // Full sweep: the generic path (ALL same-label edges) or, with ONE_WAY_ONLY, the fall-back when the
 // pending list overflowed.
 template <int G, bool ONE_WAY_ONLY>
@@ -681,7 +712,7 @@ extern "C" size_t pg_bfs_cluster_workspace_bytes(int64_t N) {
 // untouched since -- its grid lets whole cells skip the edge sweep (k_cl_cells)
 static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_query_idxs, const int32_t *start_len, int32_t N,
                           int64_t nActive, int32_t threshold, int mode, void *ws, size_t ws_bytes, void *bq_ws,
-                          size_t bq_ws_bytes, int32_t *host_sizes, void *stream) {
+                          size_t bq_ws_bytes, int32_t *host_sizes, void *stream, bool one_sync = true) {
     cudaStream_t st = (cudaStream_t)stream;
     PG_CHECK_ARG(host_sizes, "null host_sizes");
     host_sizes[0] = host_sizes[1] = host_sizes[2] = 0;
@@ -759,8 +790,15 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
         k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
         PG_LAUNCH_CHECK();
     }
-    PG_CUDA(cudaMemcpyAsync(h, w.scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
-    PG_CUDA(cudaStreamSynchronize(st));
+    // Trusted lists need no verdict from the sweep (no checksum, no range flags): the parked one-way edges are
+    // settled on the device and the host reads everything back once, together with the sizes.
+    const bool fast = trusted && !use_generic && one_sync;
+    if (fast) {
+        k_cl_pending_block<<<1, 1024, 0, st>>>(w.pend, (unsigned long long)w.pend_cap, w.root, w.lab, w.scalars);
+    } else {
+        PG_CUDA(cudaMemcpyAsync(h, w.scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+    }
     if (h[1] == 2) {   // the reference would read out of bounds here (bfs_cluster.cpp:40-42)
         set_error("pg_bfs_cluster_count: start_len has a row outside ball_query_idxs[0..%lld)", (long long)nActive);
         return PG_EINVAL;
@@ -800,11 +838,22 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
     PG_TRY(scan_exclusive_i32(w.cid, w.cid, (int64_t)N + 1, (int64_t *)(w.scalars + 4), w.scan_tmp, st));
     k_cl_sizes<<<nb, 256, 0, st>>>(w.size, w.cid, N, w.csize, w.scalars);
     PG_LAUNCH_CHECK();
-    unsigned long long r[2];
-    PG_CUDA(cudaMemcpyAsync(r, w.scalars + 4, sizeof(r), cudaMemcpyDeviceToHost, st));
+    unsigned long long all[12];
+    PG_CUDA(cudaMemcpyAsync(all, w.scalars, sizeof(all), cudaMemcpyDeviceToHost, st));
     PG_CUDA(cudaStreamSynchronize(st));
-    host_sizes[0] = (int32_t)r[0];
-    host_sizes[1] = (int32_t)r[1];
+    if (fast) {
+        if (all[1] == 2) {
+            set_error("pg_bfs_cluster_count: start_len has a row outside ball_query_idxs[0..%lld)", (long long)nActive);
+            return PG_EINVAL;
+        }
+        if (all[10] != 0)     // too many parked edges for the one-block settle: take the host-driven loop instead
+            return bfs_count_impl(semantic_label, ball_query_idxs, start_len, N, nActive, threshold, mode, ws, ws_bytes, bq_ws,
+                                  bq_ws_bytes, host_sizes, stream, false);
+        g_cl_dbg[0] = 0; g_cl_dbg[1] = (long long)all[1]; g_cl_dbg[2] = (long long)all[2]; g_cl_dbg[3] = 0;
+        g_cl_dbg[4] = (grid && all[8]) ? (long long)all[8] : (long long)N;
+    }
+    host_sizes[0] = (int32_t)all[4];
+    host_sizes[1] = (int32_t)all[5];
     host_sizes[2] = use_generic ? 1 : 0;
     return PG_OK;
 }

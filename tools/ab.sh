@@ -1,4 +1,4 @@
-for v in "" old; do
+for v in ""; do
   if [ -n "$v" ]; then export PG_B200_LIB=$PWD/d3net_b200/variants/libpg_$v.so; else unset PG_B200_LIB; fi
   python bench.py --no-cpu-baseline --steps 10 > gpurun_out/ab_$v.json 2>/dev/null
   python - <<P
