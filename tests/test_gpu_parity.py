@@ -86,7 +86,7 @@ def test_voxelize_idx_cpu_input_roundtrip(ops, oracle):
 # ------------------------------------------------------------------------------------------------
 # voxelization (fp / bp) and point_recover
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("C", [1, 2, 3, 7, 16, 134])
+@pytest.mark.parametrize("C", [1, 2, 3, 7, 16, 40, 134, 600])
 @pytest.mark.parametrize("mode", [4, 3])
 def test_voxelize_fp_bp(ops, oracle, C, mode):
     rng = np.random.default_rng(100 + C)

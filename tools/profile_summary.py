@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """profiles/<tag>_ncu_summary.md, profiles/<tag>_launches.csv and profiles/traffic.json from one gpurun capture:
-    python tools/profile_summary.py TAG gpurun_out/launches_X.csv gpurun_out/prof_X.ncu-rep
+    python tools/profile_summary.py TAG gpurun_out/launches_X.csv gpurun_out/prof_X.ncu-rep|gpurun_out/prof_X_raw.csv
 The launch list is `ncu --metrics gpu__time_duration.sum --clock-control none --csv` of
 `bench.py --profile-mode --steps 1 --warmup 1` (its second half is one step); the report is `ncu --set full` of the
 library's main kernels in the same command.  traffic.json = DRAM bytes (read + write) per STEP and kernel."""
@@ -45,7 +45,10 @@ for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
     out.append("| `%s` | %d | %.1f | %.1f%% |" % (k.replace("|", "/"), v[0], v[1], 100 * v[1] / tot))
 out.append("| total (library kernels %.1f us = %.1f%%) | %d | %.1f | |" % (mine, 100 * mine / tot, len(rows) - half, tot))
 
-txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+# `rep` is the .ncu-rep itself or its `ncu -i X.ncu-rep --page raw --csv` dump (a full-step report exceeds what
+# gpurun copies back, so the dump is made on the GPU box and the report left there)
+txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"],
+                                                                    capture_output=True, text=True).stdout
 r = list(csv.reader(txt.splitlines()))
 hdr, units, data = r[0], r[1], r[2:]
 ix = {h: i for i, h in enumerate(hdr)}
