@@ -227,12 +227,24 @@ __global__ void __launch_bounds__(kMeanThreads) k_sec_mean(const float *__restri
                 if (c < C) {
                     const float *b = &buf[cur][c];
                     float a = acc[j];
+                    // the add chain is the critical path (4 cycles per row): the next eight operands are
+                    // fetched from shared memory while the current eight are being added
                     int r = 0;
-                    for (; r + 8 <= rows; r += 8) {
-                        float q0 = b[(r + 0) * C], q1 = b[(r + 1) * C], q2 = b[(r + 2) * C], q3 = b[(r + 3) * C];
-                        float q4 = b[(r + 4) * C], q5 = b[(r + 5) * C], q6 = b[(r + 6) * C], q7 = b[(r + 7) * C];
-                        a = __fadd_rn(a, q0); a = __fadd_rn(a, q1); a = __fadd_rn(a, q2); a = __fadd_rn(a, q3);
-                        a = __fadd_rn(a, q4); a = __fadd_rn(a, q5); a = __fadd_rn(a, q6); a = __fadd_rn(a, q7);
+                    float q[8], nx[8];
+                    if (rows >= 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) q[u] = b[u * C];
+                        for (; r + 16 <= rows; r += 8) {
+#pragma unroll
+                            for (int u = 0; u < 8; u++) nx[u] = b[(r + 8 + u) * C];
+#pragma unroll
+                            for (int u = 0; u < 8; u++) a = __fadd_rn(a, q[u]);
+#pragma unroll
+                            for (int u = 0; u < 8; u++) q[u] = nx[u];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) a = __fadd_rn(a, q[u]);
+                        r += 8;
                     }
                     for (; r < rows; r++) a = __fadd_rn(a, b[r * C]);
                     acc[j] = a;

@@ -61,6 +61,19 @@ __global__ void k_max_i32(const int32_t *__restrict__ v, const int64_t *__restri
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax((unsigned long long *)out, (unsigned long long)m);
 }
 
+// flat index -> (row, column): a 32-bit division when the index fits (the 64-bit one is a ~80-instruction
+// subroutine, and these kernels do little else per element)
+__device__ __forceinline__ void row_col(int64_t t, int32_t width, int64_t &row, int &col) {
+    if (t <= 0xffffffffLL) {
+        const unsigned q = (unsigned)t / (unsigned)width;
+        row = q;
+        col = (int)((unsigned)t - q * (unsigned)width);
+    } else {
+        row = t / width;
+        col = (int)(t - row * width);
+    }
+}
+
 // output_map rows [cnt, p0 < p1 < ..., 0-pad] (voxelize.cpp:139-149; modes 0/1/2: :121-138) and
 // output_coords = coords row of rule[1] (voxelize.cpp:39-47)
 __device__ __forceinline__ int vox_map_entry(const uint32_t *__restrict__ sorted, int mode, int j, int n, int off) {
@@ -86,7 +99,10 @@ __global__ void k_vox_fill(const int64_t *__restrict__ coords, const int32_t *__
         }
         for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (int64_t)gridDim.x * blockDim.x) {
             const int64_t t = q << 2;
-            int v = (int)(t / W), j = (int)(t - (int64_t)v * W);
+            int64_t v64;
+            int j;
+            row_col(t, W, v64, j);
+            int v = (int)v64;
             int n = cnt[v], off = voff[v];
             int val[4];
 #pragma unroll
@@ -160,8 +176,10 @@ __global__ void __launch_bounds__(256) k_voxelize_fp(const float *__restrict__ f
     const int64_t total = (int64_t)M * Cv;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += (int64_t)gridDim.x * blockDim.x) {
-        const int v = (int)(t / Cv), c = (int)(t - (int64_t)v * Cv);
-        const int32_t *r = rules + (int64_t)v * W;
+        int64_t v;
+        int c;
+        row_col(t, Cv, v, c);
+        const int32_t *r = rules + v * W;
         const int n = __ldg(r);
         const float mult = (average && n > 0) ? __fdiv_rn(1.0f, (float)n) : 1.0f;
         T acc;
@@ -232,8 +250,9 @@ __global__ void __launch_bounds__(256) k_gather_rows(const float *__restrict__ s
     T *__restrict__ d = reinterpret_cast<T *>(dst);
     const int64_t total = nIdx * Cv;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = t / Cv;
-        const int c = (int)(t - row * Cv);
+        int64_t row;
+        int c;
+        row_col(t, Cv, row, c);
         __stcs(d + t, __ldg(s + (int64_t)__ldg(idx + row) * Cv + c));
     }
 }
