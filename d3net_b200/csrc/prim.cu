@@ -172,51 +172,66 @@ __global__ void __launch_bounds__(kRadixThreads) k_radix_hist(const uint32_t *__
     hist[(int64_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
 }
 
+// Each warp owns a contiguous 256-element slice of the tile (8 rounds of 32 consecutive elements), so the stable
+// order inside the tile is (warp, round, lane): a warp ranks its own slice with nothing but warp-level
+// primitives -- `__match_any_sync` groups equal digits, a per-warp counter row in shared memory carries the
+// running count from round to round -- and the block meets only twice per tile: once to turn the eight counter
+// rows into per-warp bases, once before the rows are reused.  Keys, values and ranks stay in registers.
 __global__ void __launch_bounds__(kRadixThreads)
 k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
                 const int32_t *__restrict__ hist, int nb) {
-    __shared__ int base_s[256];                       // global base of this tile's run for each digit
-    __shared__ int wcnt[kRadixThreads / 32][256];     // per-warp digit counts of the current round
+    constexpr int kWarps = kRadixThreads / 32;
+    __shared__ int wcnt[kWarps][256];                 // per-warp digit counts, then exclusive bases across warps
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    base_s[threadIdx.x] = hist[(int64_t)threadIdx.x * nb + blockIdx.x];
-    for (int k = 0; k < kRadixThreads / 32; k++) wcnt[k][threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t tile = (int64_t)blockIdx.x * kRadixTile;
-    for (int r = 0; r < kRadixRounds; r++) {
-        const int64_t i0 = tile + r * kRadixThreads;
-        if (i0 >= n) break;
-        const int64_t i = i0 + threadIdx.x;
-        const bool live = i < n;
-        uint32_t key = 0, val = 0;
-        unsigned d = 256;                             // dead lanes never match a real digit
-        if (live) {
-            key = keys_in[i];
-            val = vals_in ? vals_in[i] : (uint32_t)i;
-            d = (key >> shift) & 255u;
-        }
-        unsigned peers = __match_any_sync(0xffffffffu, d);
-        int rank = __popc(peers & lanemask_lt());
-        if (live && rank == 0) wcnt[w][d] = __popc(peers);
-        __syncthreads();
-        if (live) {
-            int before = 0;
-            for (int k = 0; k < w; k++) before += wcnt[k][d];
-            int pos = base_s[d] + before + rank;
-            keys_out[pos] = key;
-            vals_out[pos] = val;
-        }
-        __syncthreads();
-        {
-            int all = 0;
+    const unsigned lt = lanemask_lt();
+    const int gbase = hist[(int64_t)threadIdx.x * nb + blockIdx.x];   // global base of this tile's run of digit tid
 #pragma unroll
-            for (int k = 0; k < kRadixThreads / 32; k++) {
-                all += wcnt[k][threadIdx.x];
-                wcnt[k][threadIdx.x] = 0;
-            }
-            base_s[threadIdx.x] += all;
+    for (int k = 0; k < kWarps; k++) wcnt[k][threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t slice = (int64_t)blockIdx.x * kRadixTile + (int64_t)w * (kRadixRounds * 32);
+    uint32_t key[kRadixRounds], val[kRadixRounds];
+    int rank[kRadixRounds];                           // position inside the warp's slice among equal digits
+    unsigned dig[kRadixRounds];
+#pragma unroll
+    for (int r = 0; r < kRadixRounds; r++) {
+        const int64_t i = slice + r * 32 + lane;
+        const bool live = i < n;
+        key[r] = live ? keys_in[i] : 0u;
+        val[r] = live ? (vals_in ? vals_in[i] : (uint32_t)i) : 0u;
+        dig[r] = live ? ((key[r] >> shift) & 255u) : 256u;   // dead lanes never match a real digit
+    }
+#pragma unroll
+    for (int r = 0; r < kRadixRounds; r++) {
+        const unsigned peers = __match_any_sync(0xffffffffu, dig[r]);
+        const int before = __popc(peers & lt);
+        int run = 0;
+        if (dig[r] < 256u) {
+            run = wcnt[w][dig[r]];                    // equal digits read the same counter, then the leader bumps it
         }
-        __syncthreads();
+        __syncwarp();
+        if (dig[r] < 256u && before == 0) wcnt[w][dig[r]] = run + __popc(peers);
+        __syncwarp();
+        rank[r] = run + before;
+    }
+    __syncthreads();
+    {   // digit `tid`: exclusive prefix of the eight warp counts, shifted by the tile's global base
+        int acc = gbase;
+#pragma unroll
+        for (int k = 0; k < kWarps; k++) {
+            const int c = wcnt[k][threadIdx.x];
+            wcnt[k][threadIdx.x] = acc;
+            acc += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRadixRounds; r++) {
+        if (dig[r] < 256u) {
+            const int pos = wcnt[w][dig[r]] + rank[r];
+            keys_out[pos] = key[r];
+            vals_out[pos] = val[r];
+        }
     }
 }
 
