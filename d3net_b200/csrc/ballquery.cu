@@ -484,7 +484,7 @@ __global__ void k_bq_start_len(const uint32_t *__restrict__ sorted_pt, const int
 
 // ---- fill -------------------------------------------------------------------------------------------
 constexpr int kFillQ = 4;
-constexpr int kFillShortK = 96;          // candidate lists this short are decoded without the 8-block pipeline
+constexpr int kFillShortK = 128;         // = kSmallK: the cells of the warp-per-cell count kernel, at most four mask words per query
 
 // without masks: a warp per query re-evaluates the predicate over the cell's sorted candidates
 __global__ void __launch_bounds__(256) k_bq_fill(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
@@ -593,20 +593,39 @@ __device__ __forceinline__ void bq_fill_run(int64_t q_first, int L, int cc, cons
     }
 }
 
-// short candidate lists (a handful of 32-candidate blocks): nothing to pipeline, one query at a time
-__device__ __forceinline__ void bq_fill_mask_one(uint32_t k, const uint32_t *__restrict__ ci, int K,
-                                                 const uint32_t *__restrict__ mrow, int nq,
-                                                 const int2 *__restrict__ start_len, int32_t *__restrict__ idx, int lane,
-                                                 unsigned lt) {
+// Short candidate lists (K <= kFillShortK: at most three mask words per query, never a full list) -- the bulk of
+// a sparse set such as raw scene coordinates, ~9 neighbours per point.  A warp per four queries spends its time
+// waiting on one short dependent chain after another there (0.20 ms for 9 M outputs); with a THREAD per query a
+// million chains are in flight at once.  k_bq_fill_mask skips the queries this kernel has written.
+__global__ void __launch_bounds__(256) k_bq_fill_short(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cell,
+                                                       const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
+                                                       const int32_t *__restrict__ cand_start, const int32_t *__restrict__ kb,
+                                                       const uint32_t *__restrict__ cand_idx, const int32_t *__restrict__ mbase,
+                                                       const uint32_t *__restrict__ masks, const int2 *__restrict__ start_len,
+                                                       int32_t n, int32_t *__restrict__ idx) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint32_t k = __ldg(sorted_pt + q);
+    const int c = __ldg(cell + k);
+    const int K = __ldg(kb + c);
+    if (K > kFillShortK) return;
     const int2 sl = __ldg(start_len + k);
+    const int nq = __ldg(ccnt + c);
+    const uint32_t *mrow = masks + __ldg(mbase + c) + (q - __ldg(cstart + c));
+    const uint32_t *ci = cand_idx + __ldg(cand_start + c);
+    unsigned m[(kFillShortK + 31) / 32];
+#pragma unroll
+    for (int w = 0; w < (kFillShortK + 31) / 32; w++) m[w] = (w * 32 < K) ? __ldg(mrow + (int64_t)w * nq) : 0u;
     int32_t *out = idx + sl.x;
-    int written = 0;
-    for (int base = 0; base < K && written < sl.y; base += 32) {
-        const unsigned m = __ldg(mrow + (int64_t)(base >> 5) * nq);
-        if (m == 0u) continue;
-        const int pos = written + __popc(m & lt);
-        if (((m >> lane) & 1u) && pos < sl.y) out[pos] = (int)__ldg(ci + base + lane);
-        written += __popc(m);
+    int pos = 0;
+#pragma unroll
+    for (int w = 0; w < (kFillShortK + 31) / 32; w++) {
+        unsigned mm = m[w];
+        while (mm) {
+            const int b = __ffs((int)mm) - 1;
+            mm &= mm - 1u;
+            out[pos++] = (int)__ldg(ci + w * 32 + b);
+        }
     }
 }
 
@@ -635,15 +654,8 @@ __global__ void __launch_bounds__(256, 5) k_bq_fill_mask(const uint32_t *__restr
         while (u0 < nqr) {
             const int L = __ffs((int)(ends >> u0));
             const int cc = u0 == 0 ? c[0] : __ldg(cell + __ldg(sorted_pt + q0 + u0));
-            const int K = __ldg(kb + cc);
-            if (K <= kFillShortK) {
-                for (int u = 0; u < L; u++)
-                    bq_fill_mask_one(__ldg(sorted_pt + q0 + u0 + u), cand_idx + __ldg(cand_start + cc), K,
-                                     masks + __ldg(mbase + cc) + (int)(q0 + u0 + u - __ldg(cstart + cc)), __ldg(ccnt + cc), start_len,
-                                     idx, lane, lt);
-            } else {
+            if (__ldg(kb + cc) > kFillShortK)               // shorter candidate lists were decoded by k_bq_fill_short
                 bq_fill_run(q0 + u0, L, cc, sorted_pt, cstart, ccnt, cand_start, kb, cand_idx, mbase, masks, start_len, idx, lane, lt);
-            }
             u0 += L;
         }
     }
@@ -749,6 +761,11 @@ extern "C" int pg_ballquery_fill(const float *xyz, int32_t n, float radius, cons
     if (!w.ok) { set_error("pg_ballquery_fill: workspace too small"); return PG_EWORKSPACE; }
     const uint32_t *sorted_pt = bq_sorted(w, n);
     const float r2 = radius * radius;
+    if (masks) {
+        PG_KTIME("k_bq_fill_short", st);
+        k_bq_fill_short<<<(unsigned)div_up(n, 256), 256, 0, st>>>(sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx,
+                                                                  w.mbase, masks, (const int2 *)start_len, n, idx);
+    }
     PG_KTIME(masks ? "k_bq_fill_mask" : "k_bq_fill", st);
     if (masks)
         k_bq_fill_mask<<<kNumSM * PG_RESIDENT(k_bq_fill_mask, 256, 0) * 4, 256, 0, st>>>(sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx, w.mbase,
