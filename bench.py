@@ -105,6 +105,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+KERNEL_NOTES = {
+    "k_bq_cells_dense": "ball-query count over dense cells: 0.8 G exact fp32 distance tests per step (9 SASS instructions each) "
+                        "on coordinates that stay in shared memory -- FP32-issue / barrier bound, so its share of the HBM roofline "
+                        "says little; the streaming kernels are listed under hbm_kernels (DESIGN.md section 5)",
+    "k_bq_fill_mask": "decodes 1 bit per (query, candidate) into the neighbour index lists: writes 4 B per neighbour, instruction-bound "
+                      "on the bit -> position arithmetic",
+    "k_cl_verify<trusted>": "edge sweep of the union-find; algorithmic bytes count every list once although settled cells are never read",
+}
+
 # ----------------------------------------------------------------------------------------------------
 # algorithmic bytes per op (restated in DESIGN.md)
 # ----------------------------------------------------------------------------------------------------
@@ -419,7 +428,11 @@ def run_b200(args, rank, world, local):
                          "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)" if peak_kind == "measured" else peak_kind,
                          "algorithmic_bytes_per_launch": int(kalgo.get(dom, 0) / dom_launches),
                          "ms_per_launch": dom_ms / dom_launches, "launches_per_step": dom_launches,
-                         "timing": "CUDA events on the launching stream around every launch of the kernel, %d steps" % args.steps},
+                         "timing": "CUDA events on the launching stream around every launch of the kernel, %d steps" % args.steps,
+                         "note": KERNEL_NOTES.get(dom, "")},
+            # the kernels that stream their operands once (the ones an HBM roofline is the right yardstick for)
+            "hbm_kernels": {k: {"GBps": v["GBps"], "frac": v["frac"]} for k, v in per_kernel.items()
+                            if k in ("k_voxelize_fp", "k_vox_fill", "k_bq_fill_mask") and "GBps" in v},
             "per_kernel": per_kernel,
             "per_op": per_op,
             "top_kernels": [{"name": k[:80], "calls": c, "us": round(t, 1)} for k, c, t in top[:8]],

@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """How much of the edge sweep the cell pass (k_cl_cells) saves on the bench batch (8 x 150k points), and what
-the kernels of bfs_cluster cost with it:  python tools/grid_stats.py   (env: PG_SAMPLE_ROUNDS, PG_NO_CELLS)"""
+the kernels of bfs_cluster cost with it:  python tools/grid_stats.py
+(set d3net_b200.pointgroup_ops.USE_GRID_SWEEP = False for the plain trusted sweep)"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from d3net_b200 import chain, scenes, pointgroup_ops as ops, PG_OP, _native
