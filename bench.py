@@ -200,7 +200,7 @@ def cpu_chain_rate(budget_s, steps, warmup):
     return rate, dt * 1e3, desc, cores, kind
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, emit=print):
     if rank != 0:
         return
     rate, ms, desc, cores, kind = cpu_chain_rate(150.0, args.steps, args.warmup)
@@ -214,7 +214,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -233,7 +233,7 @@ def count_pg_kernels(fn):
         return None, [("profiler unavailable: %r" % (e,), 0, 0)]
 
 
-def run_b200(args, rank, world, local):
+def run_b200(args, rank, world, local, emit=print):
     import torch.distributed as dist
     from d3net_b200 import pointgroup_ops as ops, dist as pgdist, _native
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -241,9 +241,7 @@ def run_b200(args, rank, world, local):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's banner / warnings belong on stderr
         dist.init_process_group("nccl", device_id=dev)
 
     n_scenes = args.scenes
@@ -440,7 +438,7 @@ def run_b200(args, rank, world, local):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -459,10 +457,25 @@ def main():
                     help="only W warm-up + K device-resident steps, no JSON line (for runs under ncu)")
     args = ap.parse_args()
     rank, world, local = dist_env()
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        run_b200(args, rank, world, local)
+    # stdout carries exactly one JSON line: while the run is going, file descriptor 1 points at stderr, so
+    # nothing a library prints (NCCL's version banner, for one) can land in front of it
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    emit = lines.append
+    try:
+        if args.impl == "reference":
+            run_reference(args, rank, world, emit)
+        else:
+            run_b200(args, rank, world, local, emit)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines:
+        print(ln)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":
