@@ -15,6 +15,8 @@ def short(name):
     if not m:
         return None
     k = m.group(1)
+    if k == "k_voxelize_fp_rows":        # the wide-row variant runs under the same timer name as the flat one
+        k = "k_voxelize_fp"
     if k == "k_cl_verify":
         k += "<trusted>" if re.search(r"k_cl_verify<[^>]*(true|\(bool\)1|, 1)", name) else "<validating>"
     return k
