@@ -89,7 +89,7 @@ def voxelize_idx_impl(coords, mode):
 # Hit masks cost 1 bit per tested (query, candidate) pair -- about 25 words per point at 330 neighbours per
 # point.  The buffer is sized from n alone (no round trip to learn the exact need); a batch that needs more
 # runs without masks (the fill phase then evaluates the predicates again).
-BALLQUERY_MASK_WORDS_PER_POINT = 48
+BALLQUERY_MASK_WORDS_PER_POINT = 512
 BALLQUERY_MASK_BUDGET_BYTES = 4 << 30
 
 
@@ -150,7 +150,9 @@ def bfs_cluster_impl(semantic_label, ball_query_idxs, start_len, threshold, gene
     dev = semantic_label.device
     with torch.cuda.device(dev):
         L = _L()
-        nws = L.pg_bfs_cluster_workspace_bytes(N)
+        # whatever the buffer holds beyond the minimum becomes parking room for one-way edges (lists cut at 1000
+        # entries): one 8-byte slot per 8 neighbours, at most 512 MB
+        nws = L.pg_bfs_cluster_workspace_bytes(N) + 8 * min(ball_query_idxs.numel() // 8, 64 << 20)
         ws = _ws(nws, dev)
         sizes = (ctypes.c_int32 * 3)()
         if trusted and not generic and grid_ws is not None and N > 0:

@@ -68,8 +68,6 @@ static ClWs cl_layout(void *ws, size_t ws_bytes, int64_t N_) {
     w.size = a.take<int32_t>(n + 1);
     w.cid = a.take<int32_t>(n + 1);
     w.csize = a.take<int32_t>(n + 1);
-    w.pend_cap = n + 1024;
-    w.pend = a.take<int2>(w.pend_cap);
     w.cellsum = a.take<uint2>(n);
     w.cstate = a.take<uint32_t>(n);
     w.cqueue = a.take<int32_t>(n);
@@ -81,6 +79,11 @@ static ClWs cl_layout(void *ws, size_t ws_bytes, int64_t N_) {
     w.hist = a.take<int32_t>(radix_tmp_count(N_));
     w.scan_tmp = a.take<int64_t>(scan_tmp_count((int64_t)(n + radix_tmp_count(N_))));
     w.scalars = a.take<unsigned long long>(12);
+    // the parking lot for one-way edges comes last and takes whatever the caller's buffer holds beyond the minimum:
+    // a scene with hundreds of thousands of truncated lists parks millions of them
+    w.pend_cap = n + 1024;
+    if (ws && ws_bytes > a.used + (w.pend_cap + 64) * sizeof(int2)) w.pend_cap = (ws_bytes - a.used) / sizeof(int2) - 64;
+    w.pend = a.take<int2>(w.pend_cap);
     w.ok = a.ok;
     w.used = a.used;
     return w;
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__r
                                                               const uint32_t *__restrict__ order, uint2 *pl,
                                                               const int32_t *__restrict__ last,
                                                               const uint32_t *__restrict__ snap, int32_t N,
-                                                              int2 *__restrict__ pend, unsigned pend_cap,
+                                                              int2 *__restrict__ pend, unsigned long long pend_cap,
                                                               unsigned long long *scalars, int use_list_count) {
     constexpr int kGroups = kVerThreads / G;
     // lists to sweep: all N of them in `order`, or the scalars[8] the cell pass left over (grid-assisted mode)
@@ -247,6 +250,7 @@ __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__r
     const unsigned gmask = G == 32 ? 0xffffffffu : (((1u << G) - 1u) << ((tid & 31) / G * G));
     unsigned long long chk = 0, chk_rev = 0;
     bool bad = false;
+    int park_a = -1, park_b = -1;                // the pair of sets this lane parked last
     const bool any_full = scalars[7] != 0;       // some list holds kCap entries: reverse edges may be missing
 
     auto fetch_header = [&](long long base, int4 &h) {
@@ -349,10 +353,14 @@ __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__r
                     if (a == b) continue;
                     if (twoway) {
                         ri = uf_union_roots(pl, a, b);
-                    } else {
-                        // one-way edge i -> j whose ends are not connected (yet): park it
+                    } else if (a != park_a || b != park_b) {
+                        // one-way edge between two sets that are not connected (yet): park it as (a, b) -- the
+                        // propagation only looks at the sets of its ends -- unless this lane has just parked the
+                        // same pair (a truncated list points at the same few sets a thousand times)
+                        park_a = a;
+                        park_b = b;
                         const unsigned long long slot = atomicAdd(&scalars[2], 1ULL);
-                        if (slot < pend_cap) pend[slot] = make_int2(i, j);
+                        if (slot < pend_cap) pend[slot] = make_int2(a, b);
                     }
                 }
                 if (!more) break;
@@ -579,7 +587,7 @@ __global__ void k_cl_pending(const int2 *__restrict__ pend, unsigned long long n
 // The same fixed point without the host in the loop, for the trusted path: the parked edges are a few dozen to a
 // few thousand, so ONE block settles them -- the count phase then synchronises the stream once (for the sizes)
 // instead of twice.  More than kPendBlockMax parked edges: raise scalars[10]; the host reruns the two-sync path.
-constexpr unsigned long long kPendBlockMax = 1u << 16;
+constexpr unsigned long long kPendBlockMax = 4096;
 
 __global__ void __launch_bounds__(1024) k_cl_pending_block(const int2 *__restrict__ pend, unsigned long long pend_cap,
                                                            const int32_t *__restrict__ root, int32_t *lab,
@@ -712,7 +720,7 @@ extern "C" size_t pg_bfs_cluster_workspace_bytes(int64_t N) {
 // untouched since -- its grid lets whole cells skip the edge sweep (k_cl_cells)
 static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_query_idxs, const int32_t *start_len, int32_t N,
                           int64_t nActive, int32_t threshold, int mode, void *ws, size_t ws_bytes, void *bq_ws,
-                          size_t bq_ws_bytes, int32_t *host_sizes, void *stream, bool one_sync = true) {
+                          size_t bq_ws_bytes, int32_t *host_sizes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     PG_CHECK_ARG(host_sizes, "null host_sizes");
     host_sizes[0] = host_sizes[1] = host_sizes[2] = 0;
@@ -782,7 +790,7 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
         const unsigned vg = kNumSM * 3;
 #define PG_VERIFY(G, T)                                                                                              \
     k_cl_verify<G, T><<<vg, kVerThreads, 0, st>>>(ball_query_idxs, sl, order, w.pl, w.last, w.snap, N, w.pend,     \
-                                                  (unsigned)w.pend_cap, w.scalars, use_cells ? 1 : 0)
+                                                  (unsigned long long)w.pend_cap, w.scalars, use_cells ? 1 : 0)
         { PG_KTIME(trusted ? "k_cl_verify<trusted>" : "k_cl_verify<validating>", st);
         if (trusted) { if (wide) PG_VERIFY(32, true); else PG_VERIFY(8, true); }
         else { if (wide) PG_VERIFY(32, false); else PG_VERIFY(8, false); } }
@@ -792,7 +800,7 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
     }
     // Trusted lists need no verdict from the sweep (no checksum, no range flags): the parked one-way edges are
     // settled on the device and the host reads everything back once, together with the sizes.
-    const bool fast = trusted && !use_generic && one_sync;
+    const bool fast = trusted && !use_generic;
     if (fast) {
         k_cl_pending_block<<<1, 1024, 0, st>>>(w.pend, (unsigned long long)w.pend_cap, w.root, w.lab, w.scalars);
     } else {
@@ -810,12 +818,15 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
     const unsigned long long n_pend = use_generic ? 0 : h[2];
     g_cl_dbg[0] = h[0] != 0; g_cl_dbg[1] = (long long)h[1]; g_cl_dbg[2] = (long long)h[2]; g_cl_dbg[3] = 0;
     g_cl_dbg[4] = (grid && h[8]) ? (long long)h[8] : (long long)N;
-    const bool sweep = use_generic || n_pend > w.pend_cap;
-    if (sweep || n_pend > 0) {
+    // min-label propagation to a fixed point, one launch + one readback per round (the parked edges, or -- on the
+    // generic path / when the parking lot overflowed -- every edge)
+    auto settle_host = [&](unsigned long long n_parked) -> int {
+        const bool sweep = use_generic || n_parked > w.pend_cap;
+        if (!sweep && n_parked == 0) return PG_OK;
         for (int it = 0; it < 1000000; it++) {
             PG_CUDA(cudaMemsetAsync(w.scalars + 3, 0, sizeof(unsigned long long), st));
             if (!sweep) {
-                k_cl_pending<<<(unsigned)div_up((int64_t)n_pend, 256), 256, 0, st>>>(w.pend, n_pend, w.root, w.lab, w.scalars);
+                k_cl_pending<<<(unsigned)div_up((int64_t)n_parked, 256), 256, 0, st>>>(w.pend, n_parked, w.root, w.lab, w.scalars);
             } else if (use_generic) {
                 if (wide) k_cl_propagate<32, false><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.trunc, w.last, N, w.root, w.lab, w.scalars);
                 else k_cl_propagate<8, false><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.trunc, w.last, N, w.root, w.lab, w.scalars);
@@ -830,27 +841,38 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
             g_cl_dbg[3]++;
             if (!changed) break;
         }
-    }
-    { PG_KTIME("k_cl_label", st);
-    k_cl_label<<<nb, 256, 0, st>>>(w.root, w.lab, N, w.size, w.key0); }
-    k_cl_keep<<<nb, 256, 0, st>>>(w.key0, w.size, N, threshold, w.cid);
-    PG_CUDA(cudaMemsetAsync(w.cid + N, 0, sizeof(int32_t), st));
-    PG_TRY(scan_exclusive_i32(w.cid, w.cid, (int64_t)N + 1, (int64_t *)(w.scalars + 4), w.scan_tmp, st));
-    k_cl_sizes<<<nb, 256, 0, st>>>(w.size, w.cid, N, w.csize, w.scalars);
-    PG_LAUNCH_CHECK();
+        return PG_OK;
+    };
+    // final labels, sizes, kept clusters; everything the host needs comes back in one copy
     unsigned long long all[12];
-    PG_CUDA(cudaMemcpyAsync(all, w.scalars, sizeof(all), cudaMemcpyDeviceToHost, st));
-    PG_CUDA(cudaStreamSynchronize(st));
+    auto finish = [&]() -> int {
+        { PG_KTIME("k_cl_label", st);
+        k_cl_label<<<nb, 256, 0, st>>>(w.root, w.lab, N, w.size, w.key0); }
+        k_cl_keep<<<nb, 256, 0, st>>>(w.key0, w.size, N, threshold, w.cid);
+        PG_CUDA(cudaMemsetAsync(w.cid + N, 0, sizeof(int32_t), st));
+        PG_TRY(scan_exclusive_i32(w.cid, w.cid, (int64_t)N + 1, (int64_t *)(w.scalars + 4), w.scan_tmp, st));
+        k_cl_sizes<<<nb, 256, 0, st>>>(w.size, w.cid, N, w.csize, w.scalars);
+        PG_LAUNCH_CHECK();
+        PG_CUDA(cudaMemcpyAsync(all, w.scalars, sizeof(all), cudaMemcpyDeviceToHost, st));
+        PG_CUDA(cudaStreamSynchronize(st));
+        return PG_OK;
+    };
+    PG_TRY(settle_host(n_pend));
+    PG_TRY(finish());
     if (fast) {
         if (all[1] == 2) {
             set_error("pg_bfs_cluster_count: start_len has a row outside ball_query_idxs[0..%lld)", (long long)nActive);
             return PG_EINVAL;
         }
-        if (all[10] != 0)     // too many parked edges for the one-block settle: take the host-driven loop instead
-            return bfs_count_impl(semantic_label, ball_query_idxs, start_len, N, nActive, threshold, mode, ws, ws_bytes, bq_ws,
-                                  bq_ws_bytes, host_sizes, stream, false);
         g_cl_dbg[0] = 0; g_cl_dbg[1] = (long long)all[1]; g_cl_dbg[2] = (long long)all[2]; g_cl_dbg[3] = 0;
         g_cl_dbg[4] = (grid && all[8]) ? (long long)all[8] : (long long)N;
+        if (all[10] != 0) {
+            // more parked edges than one block settles quickly: the host-driven rounds after all, then the labels again
+            PG_TRY(settle_host(all[2]));
+            PG_CUDA(cudaMemsetAsync(w.size, 0, ((size_t)N + 1) * sizeof(int32_t), st));
+            PG_CUDA(cudaMemsetAsync(w.scalars + 4, 0, 2 * sizeof(unsigned long long), st));
+            PG_TRY(finish());
+        }
     }
     host_sizes[0] = (int32_t)all[4];
     host_sizes[1] = (int32_t)all[5];
