@@ -30,7 +30,16 @@
 namespace pg {
 
 constexpr int kCap = PG_BALLQUERY_CAP;
-constexpr int kSmallK = 128;             // sparse/dense class boundary (candidates per cell)
+constexpr int kSmallK = 256;             // sparse/dense class boundary (candidates per cell): one warp up to here
+constexpr int kSmallSplit = 128;         // the warp kernel runs as two instantiations, K <= 128 (<= 4 keys per lane)
+                                         // and 128 < K <= 256 (8 keys per lane, twice the registers)
+constexpr int kMediumQ = 16;             // ... the latter only for cells with few queries: one warp tests them one
+                                         // after the other, a block shares them out (surfaces of a 1M-point scene:
+                                         // ~9 queries on ~150 candidates per cell, 100k such cells -> warp; the blobs of
+                                         // shifted coordinates: 50+ queries per cell -> block)
+
+// the class of a cell: served by the block-per-cell kernel?
+__host__ __device__ __forceinline__ bool bq_is_dense(int K, int nq) { return K > kSmallK || (K > kSmallSplit && nq > kMediumQ); }
 constexpr int kTile = 1024;              // candidates per shared-memory tile (dense cells)
 constexpr int kWinBits = 160 * 1024;     // index window covered by the rank bitmap (a 150k-point scene in one)
 constexpr int kWinWords = kWinBits / 32;
@@ -86,9 +95,9 @@ __global__ void __launch_bounds__(256) k_bq_neighbours(const int4 *__restrict__ 
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if (lane == 0) {
             kc[c] = cnt;
-            if (cnt > kSmallK) dense[atomicAdd((unsigned long long *)&scalars[3], 1ULL)] = (int32_t)c;
+            if (bq_is_dense(cnt, ccnt[c])) dense[atomicAdd((unsigned long long *)&scalars[3], 1ULL)] = (int32_t)c;
         }
-        if (cnt > kSmallK) {          // a dense cell: the index range of its candidates (lists ascend)
+        if (bq_is_dense(cnt, ccnt[c])) {          // a dense cell: the index range of its candidates (lists ascend)
             uint32_t head = 0xffffffffu, tail = 0u;
             if (id >= 0) {
                 const int s0 = cstart[id], l0 = ccnt[id];
@@ -212,6 +221,7 @@ __device__ __forceinline__ void bq_small_cell(const float *__restrict__ xyz, con
     }
 }
 
+template <int LO, int HI>
 __global__ void __launch_bounds__(256) k_bq_cells_small(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
                                                         const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
                                                         const int32_t *__restrict__ nbr, const int32_t *__restrict__ kc,
@@ -220,15 +230,13 @@ __global__ void __launch_bounds__(256) k_bq_cells_small(const float *__restrict_
                                                         uint32_t *__restrict__ masks, int64_t mask_capacity, float r2,
                                                         uint32_t *__restrict__ cand_idx, int32_t *__restrict__ counts,
                                                         int32_t *__restrict__ kb) {
-    __shared__ uint32_t scratch_all[8][kSmallK];
+    __shared__ uint32_t scratch_all[8][HI];
     uint32_t *scratch = scratch_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int64_t nCells = scalars[0];
     if (scalars[6] > mask_capacity) masks = nullptr;            // the caller's mask buffer is too small: run without
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nCells; c += nWarps) {
-        const int K = __ldg(kc + c);
-        if (K > kSmallK) continue;                                // a dense cell: the block kernel's
+    auto serve = [&](int64_t c, int K) {
         // lane j < 27 owns neighbour list j and copies it to its slot of the scratch row
         int len = 0;
         const uint32_t *L = sorted_pt;
@@ -247,11 +255,33 @@ __global__ void __launch_bounds__(256) k_bq_cells_small(const float *__restrict_
         __syncwarp();
         const int nq = __ldg(ccnt + c), qs = __ldg(cstart + c), cbase = __ldg(cand_start + c);
         const int mb = masks ? __ldg(mbase + c) : 0;
-        if (K <= 32) bq_small_cell<1>(xyz, sorted_pt, scratch, K, nq, qs, cbase, mb, masks, cand_idx, counts, r2, lane);
+        if (HI > kSmallSplit) bq_small_cell<HI / 32>(xyz, sorted_pt, scratch, K, nq, qs, cbase, mb, masks, cand_idx, counts, r2, lane);
+        else if (K <= 32) bq_small_cell<1>(xyz, sorted_pt, scratch, K, nq, qs, cbase, mb, masks, cand_idx, counts, r2, lane);
         else if (K <= 64) bq_small_cell<2>(xyz, sorted_pt, scratch, K, nq, qs, cbase, mb, masks, cand_idx, counts, r2, lane);
         else bq_small_cell<4>(xyz, sorted_pt, scratch, K, nq, qs, cbase, mb, masks, cand_idx, counts, r2, lane);
         if (lane == 0) kb[c] = K;
         __syncwarp();
+    };
+    if (LO == 0) {
+        // nearly every cell of a sparse set is this instantiation's: one warp per cell, strided
+        for (int64_t c = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); c < nCells; c += nWarps) {
+            const int K = __ldg(kc + c);
+            if (K > HI || bq_is_dense(K, __ldg(ccnt + c))) continue;
+            serve(c, K);
+        }
+    } else {
+        // few cells are: a warp looks at 32 consecutive cells at once (lane = cell) and serves the ones of its class
+        // one by one -- skipping the others costs one coalesced load per 32 cells, not a dependent load per cell
+        for (int64_t c0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; c0 < nCells; c0 += nWarps * 32) {
+            const int Kl = (c0 + lane < nCells) ? __ldg(kc + c0 + lane) : 0;
+            const bool wanted = Kl > LO && Kl <= HI && !bq_is_dense(Kl, __ldg(ccnt + c0 + lane));
+            unsigned todo = __ballot_sync(0xffffffffu, wanted);
+            while (todo) {
+                const int bit = __ffs((int)todo) - 1;
+                todo &= todo - 1u;
+                serve(c0 + bit, __shfl_sync(0xffffffffu, Kl, bit));
+            }
+        }
     }
 }
 
@@ -484,7 +514,7 @@ __global__ void k_bq_start_len(const uint32_t *__restrict__ sorted_pt, const int
 
 // ---- fill -------------------------------------------------------------------------------------------
 constexpr int kFillQ = 4;
-constexpr int kFillShortK = 128;         // = kSmallK: the cells of the warp-per-cell count kernel, at most four mask words per query
+constexpr int kFillShortK = kSmallK;     // the cells of the warp-per-cell count kernels: at most eight mask words per query
 
 // without masks: a warp per query re-evaluates the predicate over the cell's sorted candidates
 __global__ void __launch_bounds__(256) k_bq_fill(const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt,
@@ -724,11 +754,18 @@ extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int
     // masks are used when they fit the caller's buffer (and int32 bases): decided on the device, reported below
     const int64_t mask_cap = masks ? (mask_words < 0x7fffffffLL ? mask_words : 0x7ffffffeLL) : -1;
     const int64_t gsmall_want = div_up(n, 8);
-    const int64_t gsmall_max = (int64_t)kNumSM * PG_RESIDENT(k_bq_cells_small, 256, 0) * 4;
+    auto ksmall = k_bq_cells_small<0, kSmallSplit>;
+    auto kmedium = k_bq_cells_small<kSmallSplit, kSmallK>;
+    const int64_t gsmall_max = (int64_t)kNumSM * PG_RESIDENT(ksmall, 256, 0) * 4;
+    const int64_t gmedium_max = (int64_t)kNumSM * PG_RESIDENT(kmedium, 256, 0) * 4;
     const unsigned gsmall = (unsigned)(gsmall_want < gsmall_max ? gsmall_want : gsmall_max);
+    const unsigned gmedium = (unsigned)(gsmall_want < gmedium_max ? gsmall_want : gmedium_max);
     { PG_KTIME("k_bq_cells_small", st);
-    k_bq_cells_small<<<gsmall, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars,
-                                             masks, mask_cap, r2, w.cand_idx, w.counts, w.kb); }
+    ksmall<<<gsmall, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars, masks, mask_cap,
+                                   r2, w.cand_idx, w.counts, w.kb); }
+    { PG_KTIME("k_bq_cells_medium", st);
+    kmedium<<<gmedium, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars, masks, mask_cap,
+                                     r2, w.cand_idx, w.counts, w.kb); }
     { PG_KTIME("k_bq_cells_dense", st);
     k_bq_cells_dense<<<kNumSM * 4, kDenseThreads, sizeof(DenseSmem), st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc,
                                                                             w.cand_start, w.mbase, w.dense, w.crange, w.scalars,
