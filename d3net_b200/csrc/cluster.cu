@@ -41,14 +41,14 @@ struct ClWs {
     int32_t *cid;        // cluster id per kept label (exclusive scan of keep flags)
     int32_t *csize;      // sizes in cluster order -> offsets
     int2 *pend;          // parked one-way edges (i -> j)
-    uint2 *cellsum;      // grid-assisted mode, per ball-query cell: (main label, snapshot root | flags F1 F2 F3)
-    uint32_t *cstate;    //   settled flag per cell
-    int32_t *cqueue;     //   cells queued for the point-level recheck
+    uint2 *cellsum;      // grid-assisted mode, per ball-query cell: (main label, snapshot root)
+    int32_t *cstate;     //   skip threshold L per cell
+    int32_t *cthr;       //   three minima of last(j) over the cell's full points (T1, T2, T3)
     uint32_t *key0, *kA, *vA, *kB, *vB;
     int32_t *hist;
     int64_t *scan_tmp;
     // [0] checksum [1] bad [2] pending count [3] changed [4] nCluster [5] sumNPoint [6] verify work counter
-    // [7] some list is full [8] lists left to the sweep (grid-assisted mode) [9] cells queued for the recheck
+    // [7] some list is full [8] lists left to the sweep (grid-assisted mode)
     unsigned long long *scalars;
     size_t pend_cap;
     bool ok;
@@ -69,8 +69,8 @@ static ClWs cl_layout(void *ws, size_t ws_bytes, int64_t N_) {
     w.cid = a.take<int32_t>(n + 1);
     w.csize = a.take<int32_t>(n + 1);
     w.cellsum = a.take<uint2>(n);
-    w.cstate = a.take<uint32_t>(n);
-    w.cqueue = a.take<int32_t>(n);
+    w.cstate = a.take<int32_t>(n);
+    w.cthr = a.take<int32_t>(3 * n);
     w.key0 = a.take<uint32_t>(n);
     w.kA = a.take<uint32_t>(n);
     w.vA = a.take<uint32_t>(n);
@@ -389,30 +389,32 @@ __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__r
 // cells; every list of a point of cell A is a subset of the points of those 27 cells.  After the sampling rounds
 // almost every component is one tree plus a few stray twigs.  Each cell gets a main pair (M, R): the label and
 // snapshot root most of its points carry.  Call a point with label M and another root a STRAY of that pair.
-//     A is SETTLED  <=>  every stray of (M_A, R_A) in A's 27 cells has a complete (< 1000 entries) list and is
-//                        itself swept.
-// A point i of a settled cell with label M_A and root R_A then has nothing to tell the sweep.  Take j in list(i)
-// with label(j) = M_A (other labels are ignored by the sweep anyway).  Root R_A: already i's set -- equal snapshot
-// roots stay equal, sets only merge -- so the edge neither unites nor, if it is one-way, needs parking.  A stray:
-// its list is complete and d(i, j) < r, so it holds i; j is swept, and from j's side the pair is classified
-// exactly as from i's (two-way iff j <= last(i) when list(i) is full, which holds because j is IN list(i)).  So
-// list(i) is never read.  "Itself swept" is what the rules below guarantee: a point is kept for the sweep unless
-// its cell is settled AND it carries the cell's main pair, and of two adjacent cells with the same label and
-// different roots only the one with the SMALLER root may lean on the other (the larger one then cannot be
-// settled, so all its points are swept).  Per neighbour B of A, from per-cell summaries alone:
-//     M_B = M_A, R_B = R_A :  fine unless B holds a full stray                        (flag F1_B)
-//     M_B = M_A, R_B != R_A:  fine iff R_A < R_B and B holds no full M_B point         (flag F2_B)
-//     M_B != M_A           :  M_A points are the minority in B and always swept; fine if B holds no full point
-//                             (flag F3_B), otherwise B's points are looked at one by one (recheck pass).
-// Passes (none with a long dependent chain):  main per cell -> flags per point -> settle per cell -> recheck per
-// queued cell (one warp) -> work list per point in query order (lists sharing entries stay together).
+// A point i of cell A carrying (M_A, R_A) has nothing to tell the sweep -- its list is never read -- when
+//     every stray j of (M_A, R_A) in A's 27 cells lists i back and is itself swept.
+// Proof.  Take j in list(i) with label(j) = M_A (other labels are ignored by the sweep anyway).  Root R_A: already
+// i's set -- equal snapshot roots stay equal, sets only merge -- so the edge neither unites nor, if it is one-way,
+// needs parking.  A stray: it lists i, it is swept, and from its side the pair is classified exactly as from i's
+// (two-way iff j <= last(i) when list(i) is full, which holds because j is IN list(i)).
+// "Lists i back": d(i, j) < r, so a complete list of j holds i, and a full one (the first 1000 of j's ball by
+// index) holds i iff i <= last(j).  Hence a per-cell THRESHOLD L_A = min last(j) over the full strays around A
+// (INT_MAX without any): points of A carrying the main pair are skipped iff their index is <= L_A.
+// "Is itself swept": a point is kept for the sweep unless it carries its own cell's main pair and passes its cell's
+// threshold; a stray of (M_A, R_A) either has another root than its cell's main pair, or another label, or sits in
+// a cell B with M_B = M_A and R_B != R_A -- and of two such adjacent cells only the one with the SMALLER root may
+// lean on the other: the larger one gets L = -1, all its points are swept.
+// Per neighbour B of A, from three per-cell minima of last(j) over B's full points -- T1: strays of B's own main
+// pair, T2: points with label M_B, T3: all --
+//     M_B = M_A, R_B = R_A :  L_A = min(L_A, T1_B)
+//     M_B = M_A, R_B != R_A:  L_A = min(L_A, T2_B) if R_A < R_B, else L_A = -1
+//     M_B != M_A           :  L_A = min(L_A, T3_B)      (label-M_A points are the minority in B and always swept)
+// Four small passes, none with a long dependent chain: main per cell -> thresholds per (full) point -> L per cell
+// -> work list per point in query order (lists sharing entries stay together).
 // Cost: a few loads per point and 27 per cell, instead of one snapshot read per EDGE (~330 per point on
 // shifted coordinates).
-constexpr unsigned kCellF1 = 0x80000000u, kCellF2 = 0x40000000u, kCellF3 = 0x20000000u;
-
 __global__ void k_cl_cell_main(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cstart,
                                const int32_t *__restrict__ ccnt, const int64_t *__restrict__ bq_scalars,
-                               const uint2 *__restrict__ pl, const uint32_t *__restrict__ snap, uint2 *__restrict__ cellsum) {
+                               const uint2 *__restrict__ pl, const uint32_t *__restrict__ snap, uint2 *__restrict__ cellsum,
+                               int32_t *__restrict__ cthr) {
     const int64_t nCells = bq_scalars[0];
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += (int64_t)gridDim.x * blockDim.x) {
         const int nq = __ldg(ccnt + c), qs = __ldg(cstart + c);
@@ -425,91 +427,55 @@ __global__ void k_cl_cell_main(const uint32_t *__restrict__ sorted_pt, const int
             if (l1 == l2 && r1 == r2 && (l1 != M || r1 != R)) { M = l1; R = r1; }
         }
         cellsum[c] = make_uint2(M, R);
+        cthr[3 * c] = cthr[3 * c + 1] = cthr[3 * c + 2] = 0x7fffffff;
     }
 }
 
-__global__ void k_cl_cell_flags(const int32_t *__restrict__ cell, const uint2 *__restrict__ pl, const uint32_t *__restrict__ snap,
-                                int32_t N, uint2 *cellsum) {
+__global__ void k_cl_cell_thresholds(const int32_t *__restrict__ cell, const uint2 *__restrict__ pl,
+                                     const uint32_t *__restrict__ snap, const int32_t *__restrict__ last, int32_t N,
+                                     const uint2 *__restrict__ cellsum, int32_t *cthr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const unsigned sv = __ldg(snap + i);
-    if (!(sv & kSnapFull)) return;           // only full lists raise flags
+    if (!(sv & kSnapFull)) return;           // only full lists can fail to list a neighbour back
     const int c = __ldg(cell + i);
-    const uint2 cs = cellsum[c];             // .x never changes; .y only gains flag bits
-    unsigned f = kCellF3;
-    if (pl[i].y == cs.x) f |= kCellF2 | (((sv & kSnapRoot) != (cs.y & kSnapRoot)) ? kCellF1 : 0u);
-    if ((cs.y & f) != f) atomicOr(&cellsum[c].y, f);
-}
-
-// cstate[c]: 1 settled, 0 not; cells that need the point-level recheck are appended to `queue`
-__global__ void k_cl_cell_settle(const int32_t *__restrict__ nbr, const int64_t *__restrict__ bq_scalars,
-                                 const uint2 *__restrict__ cellsum, uint32_t *__restrict__ cstate, int32_t *__restrict__ queue,
-                                 unsigned long long *scalars) {
-    const int64_t nCells = bq_scalars[0];
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += (int64_t)gridDim.x * blockDim.x) {
-        const uint2 me = cellsum[c];
-        const unsigned R = me.y & kSnapRoot;
-        bool ok = !(me.y & kCellF1), recheck = false;
-        if (ok) {
-            const int32_t *nb = nbr + c * 27;
-#pragma unroll 9
-            for (int j = 0; j < 27; j++) {
-                const int b = __ldg(nb + j);
-                if (b < 0 || b == (int)c) continue;
-                const uint2 o = cellsum[b];
-                const unsigned Rb = o.y & kSnapRoot;
-                if (o.x == me.x) {
-                    if (Rb == R ? !(o.y & kCellF1) : (R < Rb && !(o.y & kCellF2))) continue;
-                    ok = false;
-                    break;
-                }
-                if (o.y & kCellF3) recheck = true;
-            }
-        }
-        if (ok && recheck) queue[atomicAdd(&scalars[9], 1ULL)] = (int32_t)c;
-        cstate[c] = ok && !recheck ? 1u : 0u;
+    const uint2 cs = cellsum[c];
+    const int lst = __ldg(last + i);
+    int32_t *t = cthr + 3 * (int64_t)c;
+    if (t[2] > lst) atomicMin(t + 2, lst);
+    if (pl[i].y == cs.x) {
+        if (t[1] > lst) atomicMin(t + 1, lst);
+        if ((sv & kSnapRoot) != cs.y && t[0] > lst) atomicMin(t, lst);
     }
 }
 
-__global__ void __launch_bounds__(256) k_cl_cell_recheck(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cstart,
-                                                         const int32_t *__restrict__ ccnt, const int32_t *__restrict__ nbr,
-                                                         const uint2 *__restrict__ pl, const uint32_t *__restrict__ snap,
-                                                         const uint2 *__restrict__ cellsum, const int32_t *__restrict__ queue,
-                                                         uint32_t *__restrict__ cstate, const unsigned long long *scalars) {
-    const int lane = threadIdx.x & 31;
-    const int64_t nQ = (int64_t)scalars[9];
-    const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    for (int64_t t = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); t < nQ; t += nWarps) {
-        const int c = __ldg(queue + t);
+// cstate[c] = L_c: points of c carrying its main pair are skipped iff their index is <= L_c (-1: none)
+__global__ void k_cl_cell_settle(const int32_t *__restrict__ nbr, const int64_t *__restrict__ bq_scalars,
+                                 const uint2 *__restrict__ cellsum, const int32_t *__restrict__ cthr,
+                                 int32_t *__restrict__ cstate) {
+    const int64_t nCells = bq_scalars[0];
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += (int64_t)gridDim.x * blockDim.x) {
         const uint2 me = cellsum[c];
-        const unsigned M = me.x, R = me.y & kSnapRoot;
-        // lane j < 27 owns neighbour j; cells with another main label and a full point are scanned point by point
-        int b = -1;
-        if (lane < 27) b = __ldg(nbr + (int64_t)c * 27 + lane);
-        bool need = false;
-        if (b >= 0 && b != c) { const uint2 o = cellsum[b]; need = o.x != M && (o.y & kCellF3); }
-        unsigned todo = __ballot_sync(0xffffffffu, need);
-        bool viol = false;
-        while (todo && !viol) {
-            const int j = __ffs((int)todo) - 1;
-            todo &= todo - 1u;
-            const int bb = __shfl_sync(0xffffffffu, b, j);
-            const int s0 = __ldg(cstart + bb), l0 = __ldg(ccnt + bb);
-            for (int e = lane; e < l0 && !viol; e += 32) {
-                const uint32_t pt = __ldg(sorted_pt + s0 + e);
-                const unsigned sv = __ldg(snap + pt);
-                // a full stray of (M, R): full bit, label bits of M, another root, and really label M
-                if ((sv & kSnapFull) && (sv & kSnapLabel) == ((M & 31u) << 26) && (sv & kSnapRoot) != R && pl[pt].y == M) viol = true;
-            }
-            viol = __any_sync(0xffffffffu, viol);
+        int L = cthr[3 * c];
+        const int32_t *nb = nbr + c * 27;
+#pragma unroll 9
+        for (int j = 0; j < 27; j++) {
+            const int b = __ldg(nb + j);
+            if (b < 0 || b == (int)c) continue;
+            const uint2 o = cellsum[b];
+            const int32_t *t = cthr + 3 * (int64_t)b;
+            if (o.x != me.x) L = min(L, t[2]);
+            else if (o.y == me.y) L = min(L, t[0]);
+            else if (me.y < o.y) L = min(L, t[1]);
+            else { L = -1; break; }
         }
-        if (lane == 0) cstate[c] = viol ? 0u : 1u;
+        cstate[c] = L;
     }
 }
 
 __global__ void k_cl_cell_worklist(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cell,
                                    const uint2 *__restrict__ pl, const uint32_t *__restrict__ snap,
-                                   const uint2 *__restrict__ cellsum, const uint32_t *__restrict__ cstate, int32_t N,
+                                   const uint2 *__restrict__ cellsum, const int32_t *__restrict__ cstate, int32_t N,
                                    uint32_t *__restrict__ worklist, unsigned long long *scalars) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     bool keep = false;
@@ -518,7 +484,7 @@ __global__ void k_cl_cell_worklist(const uint32_t *__restrict__ sorted_pt, const
         i = __ldg(sorted_pt + q);
         const int c = __ldg(cell + i);
         const uint2 cs = cellsum[c];
-        keep = !(__ldg(cstate + c) && pl[i].y == cs.x && (__ldg(snap + i) & kSnapRoot) == (cs.y & kSnapRoot));
+        keep = !((int)i <= __ldg(cstate + c) && pl[i].y == cs.x && (__ldg(snap + i) & kSnapRoot) == cs.y);
     }
     // blocks append in whatever order they run; inside a block the query order is kept (a cell's lists share
     // their entries, and cells rarely straddle blocks)
@@ -777,14 +743,12 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
             k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
         }
         if (use_cells) {
-            PG_KTIME("k_cl_cells", st);      // the five passes of the cell pre-pass, timed as one
+            PG_KTIME("k_cl_cells", st);      // the four passes of the cell pre-pass, timed as one
             const uint32_t *sp = bq_sorted(g, N);
             const unsigned cg = kNumSM * 8;
-            k_cl_cell_main<<<cg, 256, 0, st>>>(sp, g.cstart, g.ccnt, g.scalars, w.pl, w.snap, w.cellsum);
-            k_cl_cell_flags<<<nb, 256, 0, st>>>(g.cell, w.pl, w.snap, N, w.cellsum);
-            k_cl_cell_settle<<<cg, 256, 0, st>>>(g.nbr, g.scalars, w.cellsum, w.cstate, w.cqueue, w.scalars);
-            k_cl_cell_recheck<<<cg, 256, 0, st>>>(sp, g.cstart, g.ccnt, g.nbr, w.pl, w.snap, w.cellsum, w.cqueue, w.cstate,
-                                                  w.scalars);
+            k_cl_cell_main<<<cg, 256, 0, st>>>(sp, g.cstart, g.ccnt, g.scalars, w.pl, w.snap, w.cellsum, w.cthr);
+            k_cl_cell_thresholds<<<nb, 256, 0, st>>>(g.cell, w.pl, w.snap, w.last, N, w.cellsum, w.cthr);
+            k_cl_cell_settle<<<cg, 256, 0, st>>>(g.nbr, g.scalars, w.cellsum, w.cthr, w.cstate);
             k_cl_cell_worklist<<<nb, 256, 0, st>>>(sp, g.cell, w.pl, w.snap, w.cellsum, w.cstate, N, w.vA, w.scalars);
         }
         const unsigned vg = kNumSM * 3;
