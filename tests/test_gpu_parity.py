@@ -419,6 +419,18 @@ def test_bfs_grid_sweep_radius_extremes(ops, oracle, r):
     _grid_vs_oracle(ops, oracle, xyz, bi, bo, sem, r, 2)
 
 
+def test_bfs_grid_sweep_density_gradient(ops, oracle):
+    """A blob whose density falls off over several radii: last(j) differs from point to point, so the per-cell
+    index thresholds of the grid-assisted sweep are what keeps it exact (tests/test_grid_rule.py shows the rule
+    without them is violated on this very input)."""
+    from test_grid_rule import _gradient_blob
+    g = _gradient_blob()
+    n = len(g["xyz"])
+    rng = np.random.default_rng(2)
+    for labels in (np.ones(n, np.int32), g["sem"], np.where(rng.random(n) < 0.05, 7, 1).astype(np.int32)):
+        _grid_vs_oracle(ops, oracle, g["xyz"], g["batch_idxs"], g["batch_offsets"], labels, 0.03, 5)
+
+
 def test_bfs_empty(ops):
     z = torch.zeros(0, dtype=torch.int32).cuda()
     ci, co = ops.bfs_cluster(z, z, torch.zeros((0, 2), dtype=torch.int32).cuda(), 50)
