@@ -396,3 +396,18 @@ def nms_instances(cross_ious, scores, threshold):
         check(L.pg_nms_instances(_p(cross_ious), _p(scores), n, float(threshold), _p(ws), nws, _p(pick),
                                  ctypes.byref(cnt), _stream()), "nms_instances")
     return pick[:cnt.value]
+
+
+def pick_masks(proposals_idx, proposals_offset, pick, N):
+    """clusters_mask = proposals_mask[pick_idxs] (model/pointgroup.py:593) without the dense [nProposal, N] mask:
+    int32 [nPick, N], row k = membership of proposal pick[k] (ids in the numbering of proposals_offset)."""
+    _need(proposals_idx, "proposals_idx", torch.int32)
+    _need(proposals_offset, "proposals_offset", torch.int32)
+    _need(pick, "pick", torch.int32)
+    dev = proposals_idx.device
+    out = torch.empty((pick.numel(), int(N)), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        ws = _ws(8, dev)
+        check(_L().pg_pick_masks(_p(proposals_idx), _p(proposals_offset), proposals_offset.numel() - 1, _p(pick),
+                                 pick.numel(), int(N), _p(ws), _p(out), _stream()), "pick_masks")
+    return out

@@ -98,6 +98,7 @@ SIGNATURES = {
     "pg_pack_proposals": (_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "pg_cross_iou_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "pg_cross_iou": (_int, [_vp, _i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
+    "pg_pick_masks": (_int, [_vp, _vp, _i32, _vp, _i32, _i32, _vp, _vp, _vp]),
     "pg_nms_instances_workspace_bytes": (_sz, [_i32]),
     "pg_nms_instances": (_int, [_vp, _vp, _i32, _f32, _vp, _sz, _vp, _vp, _vp]),
     "pg_collate_points": (_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),

@@ -188,9 +188,45 @@ __global__ void __launch_bounds__(1024) k_nms_greedy(const float *__restrict__ c
     if (threadIdx.x == 0) *n_pick = s_count;
 }
 
+// clusters_mask = proposals_mask[pick_idxs] (model/pointgroup.py:593) without the dense [nProposal, N] mask: only
+// the picked rows are materialised.  One block per picked row scatters the members of its proposal.
+__global__ void __launch_bounds__(256) k_pick_masks(const int2 *__restrict__ pairs, const int32_t *__restrict__ offsets,
+                                                    const int32_t *__restrict__ pick, int32_t nPick, int32_t nP, int32_t N,
+                                                    int32_t *__restrict__ out, unsigned long long *bad) {
+    for (int k = blockIdx.x; k < nPick; k += gridDim.x) {
+        const int p = __ldg(pick + k);
+        if ((unsigned)p >= (unsigned)nP) { if (threadIdx.x == 0) *bad = 1; continue; }
+        const int s0 = __ldg(offsets + p), s1 = __ldg(offsets + p + 1);
+        int32_t *row = out + (int64_t)k * N;
+        for (int e = s0 + threadIdx.x; e < s1; e += blockDim.x) {
+            const int pt = __ldg(&pairs[e].y);
+            if ((unsigned)pt < (unsigned)N) row[pt] = 1; else *bad = 1;
+        }
+    }
+}
+
 }  // namespace pg
 
 using namespace pg;
+
+extern "C" int pg_pick_masks(const int32_t *proposals_idx, const int32_t *proposals_offset, int32_t nProposal,
+                             const int32_t *pick, int32_t nPick, int32_t N, void *ws, int32_t *out, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    PG_CHECK_ARG(nProposal >= 0 && nPick >= 0 && N >= 0, "negative size");
+    if (nPick == 0 || N == 0) return PG_OK;
+    PG_CHECK_ARG(proposals_idx && proposals_offset && pick && out && ws, "null pointer");
+    unsigned long long *d_bad = (unsigned long long *)ws;          // 8 bytes: out-of-range flag
+    PG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), st));
+    PG_CUDA(cudaMemsetAsync(out, 0, (size_t)nPick * (size_t)N * sizeof(int32_t), st));
+    k_pick_masks<<<(unsigned)(nPick < kNumSM * 8 ? nPick : kNumSM * 8), 256, 0, st>>>((const int2 *)proposals_idx, proposals_offset, pick,
+                                                                                   nPick, nProposal, N, out, d_bad);
+    PG_LAUNCH_CHECK();
+    unsigned long long bad = 0;
+    PG_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, st));
+    PG_CUDA(cudaStreamSynchronize(st));
+    if (bad) { set_error("pg_pick_masks: a picked proposal or one of its points is out of range"); return PG_EINVAL; }
+    return PG_OK;
+}
 
 extern "C" size_t pg_cross_iou_workspace_bytes(int64_t nPairs, int64_t nProposal, int64_t N) {
     return nms_layout(nullptr, 0, nPairs, N, nProposal).used + 256;

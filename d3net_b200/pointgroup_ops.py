@@ -385,3 +385,14 @@ def nms_instances(cross_ious, scores, threshold):
     dev = PG_OP._compute_device(scores)
     pick = PG_OP.nms_instances(cross_ious.to(dev).float().contiguous(), scores.to(dev).float().contiguous(), threshold)
     return pick if scores.is_cuda else pick.cpu()
+
+
+def pick_masks(proposals_idx, proposals_offset, pick_idxs, N):
+    """Not part of the reference's operator API: ``proposals_mask[pick_idxs]`` of PointGroup.test
+    (model/pointgroup.py:579-580,593) for the picked proposals only -- int32 [nPick, N] on the inputs' device.
+    ``pick_idxs`` are proposal ids in the numbering of ``proposals_offset`` (after a score / size filter:
+    ``keep[pick]``)."""
+    dev = PG_OP._compute_device(proposals_idx)
+    out = PG_OP.pick_masks(proposals_idx.to(dev).contiguous(), proposals_offset.to(dev).int().contiguous(),
+                           torch.as_tensor(pick_idxs).to(dev).int().contiguous(), N)
+    return out if proposals_idx.is_cuda else out.cpu()

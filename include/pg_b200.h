@@ -229,6 +229,11 @@ int pg_pack_proposals(const int32_t *proposals_idx, const int32_t *proposals_off
 size_t pg_cross_iou_workspace_bytes(int64_t nPairs, int64_t nProposal, int64_t N);
 int pg_cross_iou(const int32_t *proposals_idx, int32_t nPairs, int32_t nProposal, int32_t N, void *ws,
                  size_t ws_bytes, float *cross_ious, int32_t *npoint, void *stream);
+/* pick_masks replaces clusters_mask = proposals_mask[pick_idxs] (model/pointgroup.py:593): out int32 [nPick, N], row k
+ * = 0/1 membership of proposal pick[k], whose members are rows proposals_offset[p] .. proposals_offset[p+1] of
+ * proposals_idx (bfs_cluster's layout).  ws: 8 bytes.  Synchronises `stream` once (out-of-range ids: PG_EINVAL). */
+int pg_pick_masks(const int32_t *proposals_idx, const int32_t *proposals_offset, int32_t nProposal,
+                  const int32_t *pick, int32_t nPick, int32_t N, void *ws, int32_t *out, void *stream);
 size_t pg_nms_instances_workspace_bytes(int32_t n);
 int pg_nms_instances(const float *cross_ious, const float *scores, int32_t n, float threshold, void *ws,
                      size_t ws_bytes, int32_t *pick, int32_t *host_n_pick, void *stream);

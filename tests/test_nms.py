@@ -109,3 +109,25 @@ def test_gpu_chain_proposals_and_edge_cases():
     assert ops.nms_instances(torch.zeros((0, 0)).cuda(), torch.zeros(0).cuda(), 0.3).numel() == 0
     with pytest.raises(_native.PgError):
         ops.cross_iou(torch.tensor([[0, 10]], dtype=torch.int32).cuda(), 1, 10)
+
+
+@pytest.mark.gpu
+def test_gpu_pick_masks_equal_dense_mask_rows():
+    """model/pointgroup.py:579-580,593: rows of the dense mask for the picked proposals (repeats and an empty
+    proposal included); out-of-range picks are an error."""
+    from d3net_b200 import pointgroup_ops as ops, _native
+    rng = np.random.default_rng(9)
+    N, nP = 4000, 37
+    lens = rng.integers(0, 300, nP)
+    lens[5] = 0
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+    rows = np.concatenate([np.stack([np.full(l, p), rng.choice(N, l, replace=False)], 1) for p, l in enumerate(lens)]).astype(np.int32)
+    mask = np.zeros((nP, N), np.int32)
+    mask[rows[:, 0], rows[:, 1]] = 1
+    pick = np.array([3, 36, 5, 3, 0, 20], np.int32)
+    got = ops.pick_masks(torch.from_numpy(rows).cuda(), torch.from_numpy(off).cuda(), torch.from_numpy(pick).cuda(), N)
+    assert got.dtype == torch.int32 and got.is_cuda
+    np.testing.assert_array_equal(got.cpu().numpy(), mask[pick])
+    assert tuple(ops.pick_masks(torch.from_numpy(rows).cuda(), torch.from_numpy(off).cuda(), torch.zeros(0, dtype=torch.int32).cuda(), N).shape) == (0, N)
+    with pytest.raises(_native.PgError):
+        ops.pick_masks(torch.from_numpy(rows).cuda(), torch.from_numpy(off).cuda(), torch.tensor([nP], dtype=torch.int32).cuda(), N)
