@@ -203,7 +203,7 @@ def cpu_chain_rate(budget_s, steps, warmup):
 def run_reference(args, rank, world, emit=print):
     if rank != 0:
         return
-    rate, ms, desc, cores, kind = cpu_chain_rate(150.0, args.steps, args.warmup)
+    rate, ms, desc, cores, kind = cpu_chain_rate(args.cpu_budget_s, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
@@ -453,6 +453,8 @@ def main():
     ap.add_argument("--points", type=int, default=POINTS)
     ap.add_argument("--max-proposals", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0,
+                    help="--impl reference: CPU seconds the whole run may take (sizes the sample of the workload)")
     ap.add_argument("--profile-mode", action="store_true",
                     help="only W warm-up + K device-resident steps, no JSON line (for runs under ncu)")
     args = ap.parse_args()
