@@ -32,6 +32,17 @@ def test_golden_is_consistent(gold):
     np.testing.assert_array_equal(gold["voxel_locs"][gold["p2v_map"]], gold["locs_scaled"])
 
 
+def test_oracle_reproduces_reference_collate(gold, oracle):
+    """oracle/collate_oracle.py (numpy restatement, with the C oracle's voxelization_idx) against the dictionary the
+    reference's own sparse_collate_fn produced."""
+    from oracle import collate_oracle
+    g = golden_inputs("collate")["batch"]
+    data = collate_oracle.sparse_collate(g)
+    for k in gold.files:
+        assert data[k].dtype == gold[k].dtype, (k, data[k].dtype, gold[k].dtype)
+        np.testing.assert_array_equal(data[k], gold[k], err_msg=k)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("to_cpu", [False, True])
 def test_gpu_collate_equals_reference(gold, to_cpu):
