@@ -1,7 +1,9 @@
-"""BASELINE.json's full sizes on the GPU, checked through size-independent properties and independent
-re-computations (torch / scipy), since the CPU oracle does not finish in seconds there:
+"""BASELINE.json's full sizes on the GPU:
   configs[1]  the whole chain on 8 x 150k-point scenes
   configs[3]  one 1M-point dense scene through both clusterings (truncated lists, one giant component)
+Each is checked twice: bit-exact against the CPU oracle (the C restatement, plus the reference's own compiled
+voxelize_idx / bfs_cluster from oracle/_ref when it was built) by replaying the trace of every op call, and
+through size-independent properties and independent re-computations (torch / scipy).
 """
 import numpy as np
 import pytest
@@ -201,3 +203,70 @@ def test_config4_one_million_point_scene(ops):
             # same partition: component id <-> cluster id is a bijection on the kept points
             pairs = torch.stack([comp[kept], cl[kept]], 1).unique(dim=0)
             assert pairs.size(0) == co.numel() - 1 == pairs[:, 0].unique().numel() == pairs[:, 1].unique().numel()
+
+
+# ---- bit-exact oracle replay at BASELINE sizes --------------------------------------------------------------------
+def _ref_module():
+    from oracle import build_ref
+    return build_ref.load()          # None when oracle/_ref was never built (needs /root/reference at build time)
+
+
+def test_config2_chain_oracle_replay(ops, full_batch):
+    """configs[1]: every op call of the 8 x 150k chain replayed through the oracle on the same inputs --
+    voxel maps, every neighbour list (338 M + 9 M entries), both clusterings, segment reductions, roipool, IoU."""
+    from oracle import replay
+    nb, batch = full_batch
+    trace = {}
+    chain.proposal_chain(ops, batch, trace=trace)
+    torch.cuda.synchronize()
+    checked = replay.check_trace(trace, ref=_ref_module(), big=True)
+    assert len(checked) == 12
+
+
+def _one_million_scene(dev):
+    s = scenes.make_scene(1_000_000, seed=4000)
+    sem_all = torch.from_numpy(s["semantic_preds"]).to(dev)
+    obj = torch.nonzero(sem_all > 0).view(-1)
+    xyz = torch.from_numpy(s["locs"]).to(dev)[obj].contiguous()
+    shifted = (xyz + torch.from_numpy(s["pt_offsets"]).to(dev)[obj]).contiguous()
+    sem = sem_all[obj].int().contiguous()
+    n = xyz.size(0)
+    bi = torch.zeros(n, dtype=torch.int32, device=dev)
+    bo = torch.tensor([0, n], dtype=torch.int32, device=dev)
+    return xyz, shifted, sem, bi, bo
+
+
+def test_config4_one_million_point_scene_oracle_replay(ops):
+    """configs[3]: both clusterings of the 1M-point dense room against the oracle, bit for bit, through the
+    operator API (trusted, grid-assisted sweep) -- with hundreds of thousands of lists cut at the 1000 cap."""
+    from oracle import replay
+    dev = torch.device("cuda")
+    xyz, shifted, sem, bi, bo = _one_million_scene(dev)
+    ref = _ref_module()
+    for tag, pts in (("raw", xyz), ("shift", shifted)):
+        idx, sl = ops.ballquery_batch_p(pts, bi, bo, 0.03, 300)
+        ci, co = ops.bfs_cluster(sem, idx, sl, 50)
+        if tag == "shift":
+            assert int((sl[:, 1] == 1000).sum()) > 100_000                     # the cap really is exercised
+        trace = {"ballquery(%s)" % tag: (pts, bi, bo, idx, sl), "bfs_cluster(%s)" % tag: (sem, idx, sl, ci, co)}
+        replay.check_trace(trace, ref=ref, big=True)
+        del idx, sl, trace
+        torch.cuda.empty_cache()
+
+
+def test_config2_maskless_fill_matches(ops, full_batch):
+    """The fill path taken when the hit-mask buffer does not fit (it re-evaluates the predicates): same lists,
+    same layout as the masked path on the full 8 x 150k shifted set."""
+    from d3net_b200 import PG_OP
+    nb, batch = full_batch
+    obj = torch.nonzero(batch["semantic_preds"] > 0).view(-1)
+    bi = batch["locs_scaled"][:, 0].int()[obj].contiguous()
+    bo = chain.get_batch_offsets(bi, 8)
+    shifted = (batch["locs"][obj] + batch["pt_offsets"][obj]).contiguous()
+    idx, sl = ops.ballquery_batch_p(shifted, bi, bo, 0.03, 300)
+    for kw in ({"use_masks": False}, {"mask_words": 1 << 20}):                 # no buffer / a buffer that is too small
+        sl2, total, state = PG_OP.ballquery_count_impl(shifted, bi, bo, 0.03, **kw)
+        assert state[1] is None and total == idx.numel()
+        idx2 = torch.empty(total, dtype=torch.int32, device=idx.device)
+        PG_OP.ballquery_fill_impl(shifted, 0.03, sl2, idx2, state)
+        assert torch.equal(sl, sl2) and torch.equal(idx, idx2)

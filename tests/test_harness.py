@@ -1,0 +1,106 @@
+"""The reference's own caller (model/pointgroup.py, staged unmodified under baseline/_ref) against this repo's
+restatement of it (d3net_b200/chain.py):
+
+  CPU  (-m "not gpu")  both run over the ORACLE dressed as the operator API (oracle/ops_adapter.py), with `.cuda()`
+                       patched to a no-op -- checks the harness, the stand-in backbone and that chain.py issues the same
+                       op calls with the same tensors as the real `PointGroup.forward` / `clusters_voxelization`;
+  GPU  (-m gpu)        the real caller over d3net_b200.pointgroup_ops with its own CPU-tensor call pattern
+                       (model/pointgroup.py:297,305,167-169), compared with chain.py's device-resident pass.
+Skipped when baseline/_ref is absent (it is staged by harness/stage_ref.py where /root/reference exists).
+"""
+import numpy as np
+import pytest
+import torch
+
+from d3net_b200 import chain, scenes
+from harness import d3net_stub as H
+
+needs_staged = pytest.mark.skipif(not H.available(), reason="baseline/_ref not staged (harness/stage_ref.py)")
+
+
+def _chain_batch(np_batch, data_dict, captured, device):
+    """The tensors chain.proposal_chain takes as inputs, taken from what the real caller computed."""
+    return {
+        "locs": data_dict["locs"], "locs_scaled": data_dict["locs_scaled"],
+        "feats": torch.cat((data_dict["feats"], data_dict["locs"]), 1).contiguous(),
+        "pt_feats": captured["pt_feats"].contiguous(),
+        "semantic_preds": captured["semantic_preds"], "pt_offsets": captured["pt_offsets"].contiguous(),
+        "instance_ids": data_dict["instance_ids"], "instance_pointnum": data_dict["instance_num_point"],
+        "n_scenes": int(np_batch["n_scenes"]),
+    }
+
+
+def _run_both(ops, device, n_scenes, n_points, seed=1234):
+    cfg = H.load_cfg()
+    model = H.build_detector(cfg, device)
+    nb = scenes.make_batch(n_scenes, n_points, config_id=5, geometry_points=n_points)
+    dd = H.collate(nb, device)
+    captured = {}
+    hook = model.backbone.register_forward_hook(
+        lambda mod, inp, out: captured.__setitem__("pt_feats", out.features[dd["p2v_map"].long()]))
+    out = H.run_feed(model, dd, epoch=1, seed=seed)
+    hook.remove()
+    captured["semantic_preds"] = out["semantic_scores"].max(1)[1]
+    captured["pt_offsets"] = out["pt_offsets"]
+    batch = _chain_batch(nb, dd, captured, device)
+    mine = chain.proposal_chain(ops, batch, rand6=H.rand6_for(seed).to(device))
+    return cfg, model, nb, out, mine, captured, dd
+
+
+def _compare(cfg, out, mine, captured, nb, dd):
+    scores, proposals_idx, proposals_offset = out["proposal_scores"]
+    nP = proposals_offset.numel() - 1
+    assert nP > 10
+    # the planted labels / offsets came back through the reference's own heads
+    planted = H.planted_labels(nb, dd["p2v_map"].cpu(), dd["v2p_map"].cpu())
+    assert (captured["semantic_preds"].cpu().numpy() == planted).all()
+    assert torch.equal(proposals_idx.cpu().int(), mine["proposals_idx"].cpu().int())
+    assert torch.equal(proposals_offset.cpu().int(), mine["proposals_offset"].cpu().int())
+    mask = out["proposal_thres_mask"].cpu()
+    crop = out["proposal_crop_bbox"].cpu()
+    assert torch.equal(crop[:, :3], mine["proposals_center"].cpu()[mask])
+    assert torch.equal(crop[:, 3:6], mine["proposals_size"].cpu()[mask])
+    # score_net is a pass-through with a power-of-two gain: pooled features differ by exactly that factor
+    gain = float(out["proposal_feats"].sum() / mine["proposals_score_feats"].cpu()[mask].sum()) if mask.any() else 1.0
+    if mask.any():
+        assert gain == 2.0 ** round(np.log2(gain))
+        assert torch.equal(out["proposal_feats"].cpu(), mine["proposals_score_feats"].cpu()[mask] * gain)
+    B, P = len(out["batch_offsets"]) - 1, cfg.model.max_num_proposal
+    assert tuple(out["proposal_feats_batched"].shape) == (B, P, cfg.model.m)
+    assert int(out["proposal_batch_mask"].sum()) == min(int(mask.sum()), int(out["proposal_batch_mask"].numel()))
+
+
+@needs_staged
+def test_real_caller_equals_chain_on_cpu_oracle(monkeypatch):
+    from oracle.ops_adapter import OracleOps
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    ops = OracleOps(use_ref=True)
+    H._installed.clear()
+    H.install_stubs(wrapper="d3net_b200")
+    import sys
+    monkeypatch.setitem(sys.modules, "lib.pointgroup_ops.functions.pointgroup_ops", ops)
+    monkeypatch.setitem(H._installed, "ops", ops)
+    sys.modules.pop("model.pointgroup", None)
+    try:
+        cfg, model, nb, out, mine, captured, dd = _run_both(ops, torch.device("cpu"), 2, 9000)
+        _compare(cfg, out, mine, captured, nb, dd)
+    finally:
+        sys.modules.pop("model.pointgroup", None)
+        H._installed.clear()
+
+
+@needs_staged
+@pytest.mark.gpu
+@pytest.mark.parametrize("wrapper", ["d3net_b200", "reference"])
+def test_real_caller_on_gpu(wrapper):
+    """`wrapper="reference"`: the reference's own functions/pointgroup_ops.py over d3net_b200.PG_OP (option A);
+    `"d3net_b200"`: this repo's operator API mirror (option B).  Same caller, same results as chain.py."""
+    from d3net_b200 import pointgroup_ops as ops
+    H._installed.clear()
+    H.install_stubs(wrapper=wrapper)
+    try:
+        cfg, model, nb, out, mine, captured, dd = _run_both(ops, torch.device("cuda"), 2, 20000)
+        _compare(cfg, out, mine, captured, nb, dd)
+        assert not out["proposal_scores"][1].is_cuda            # bfs_cluster got CPU tensors and answered on the CPU
+    finally:
+        H._installed.clear()
