@@ -113,7 +113,10 @@ def ballquery_count_impl(xyz, batch_idxs, batch_offsets, radius, use_masks=True,
         if use_masks and n > 0:
             if mask_words is None:
                 mask_words = min(BALLQUERY_MASK_WORDS_PER_POINT * n + 1024, BALLQUERY_MASK_BUDGET_BYTES // 4)
-            masks = torch.empty(int(mask_words), dtype=torch.int32, device=dev)
+            try:
+                masks = torch.empty(int(mask_words), dtype=torch.int32, device=dev)
+            except torch.cuda.OutOfMemoryError:
+                masks = None          # the kernels run without: the fill phase then evaluates the predicates again
         start_len = torch.empty((n, 2), dtype=torch.int32, device=dev)
         total = ctypes.c_int64(0)
         used = ctypes.c_int(0)

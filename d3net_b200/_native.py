@@ -18,6 +18,8 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
+ABI_VERSION = 2        # must equal pg_abi_version() of the loaded library (bumped with every signature change)
+
 _lib = None
 
 
@@ -54,7 +56,7 @@ def build(force=False, verbose=False):
     with ThreadPoolExecutor(max_workers=8) as ex:
         objs = list(ex.map(compile_one, _sources()))
     tmp = LIB_PATH + ".tmp.%d" % os.getpid()
-    cmd = [nvcc, "-shared", "-o", tmp] + objs
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp] + objs
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
@@ -121,6 +123,10 @@ def lib():
             fn = getattr(L, name)          # AttributeError here = header / library mismatch
             fn.restype = res
             fn.argtypes = args
+        got = L.pg_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError("d3net_b200: %s reports ABI version %d, this package binds version %d -- a stale build; "
+                               "rebuild it (python -c 'import __graft_entry__ as g; g.build()')" % (path, got, ABI_VERSION))
         _lib = L
     return _lib
 

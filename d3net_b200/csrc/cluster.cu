@@ -186,11 +186,14 @@ constexpr int kSampleRounds = 1;
 
 template <int P>
 __global__ void k_cl_sample(const int32_t *__restrict__ idx, const int2 *__restrict__ start_len, uint2 *pl,
-                            const int32_t *__restrict__ last, const uint32_t *__restrict__ snap, int32_t N, int round) {
+                            const int32_t *__restrict__ last, const uint32_t *__restrict__ snap, int32_t N, int64_t nActive,
+                            int round) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int2 sl = start_len[i];
     if (sl.y <= 1) return;
+    // a row outside idx[0, nActive) (foreign lists; k_cl_prep has flagged it, the host raises PG_EINVAL): never read
+    if (sl.x < 0 || (int64_t)sl.x + sl.y > nActive) return;
     // round 0: last and middle entry (P = 2), plus the quarter points (P = 4); later rounds: the eighths, ...
     const int den = 2 << round;
     int pos[4];
@@ -235,7 +238,7 @@ template <int G, bool TRUSTED>
 __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__restrict__ idx, const int2 *__restrict__ start_len,
                                                               const uint32_t *__restrict__ order, uint2 *pl,
                                                               const int32_t *__restrict__ last,
-                                                              const uint32_t *__restrict__ snap, int32_t N,
+                                                              const uint32_t *__restrict__ snap, int32_t N, int64_t nActive,
                                                               int2 *__restrict__ pend, unsigned long long pend_cap,
                                                               unsigned long long *scalars, int use_list_count) {
     constexpr int kGroups = kVerThreads / G;
@@ -258,7 +261,10 @@ __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__r
         const long long p = base + tid;
         if (tid < kChunk && p < NL) {
             const int i = (int)__ldg(order + p);
-            const int2 sl = __ldg(start_len + i);
+            int2 sl = __ldg(start_len + i);
+            // validating sweep: a row outside idx[0, nActive) is swept as an empty list (k_cl_prep has flagged it and
+            // the host answers PG_EINVAL) -- the reference would read out of bounds there (bfs_cluster.cpp:40-42)
+            if (!TRUSTED && (sl.x < 0 || sl.y < 0 || (int64_t)sl.x + sl.y > nActive)) sl.y = 0;
             h = make_int4(i, sl.x, sl.y, (int)__ldg(snap + i));
         }
     };
@@ -738,7 +744,7 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
         k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
         for (int round = 0; round < kSampleRounds; round++) {
             { PG_KTIME("k_cl_sample", st);
-            k_cl_sample<2><<<nb, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.last, w.snap, N, round); }
+            k_cl_sample<2><<<nb, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.last, w.snap, N, nActive, round); }
             PG_KTIME("k_cl_flatten", st);
             k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
         }
@@ -753,7 +759,7 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
         }
         const unsigned vg = kNumSM * 3;
 #define PG_VERIFY(G, T)                                                                                              \
-    k_cl_verify<G, T><<<vg, kVerThreads, 0, st>>>(ball_query_idxs, sl, order, w.pl, w.last, w.snap, N, w.pend,     \
+    k_cl_verify<G, T><<<vg, kVerThreads, 0, st>>>(ball_query_idxs, sl, order, w.pl, w.last, w.snap, N, nActive, w.pend, \
                                                   (unsigned long long)w.pend_cap, w.scalars, use_cells ? 1 : 0)
         { PG_KTIME(trusted ? "k_cl_verify<trusted>" : "k_cl_verify<validating>", st);
         if (trusted) { if (wide) PG_VERIFY(32, true); else PG_VERIFY(8, true); }

@@ -80,12 +80,32 @@ def pack_proposals_torch(out, batch, max_num_proposal=256):
     return packed
 
 
-def all_gather_proposals(packed, group=None):
-    """[b, P, 46] per rank -> [world * b, P, 46] on every rank with one all_gather_into_tensor."""
+def all_gather_proposals(packed, group=None, n_scenes_total=None):
+    """[b, P, 46] per rank -> [sum of b, P, 46] on every rank with one all_gather_into_tensor.
+
+    ``all_gather_into_tensor`` needs the same shape on every rank.  With ``n_scenes_total`` given, the ranks are
+    taken to hold the blocks of ``scene_shard(n_scenes_total, rank, world)`` -- uneven when the batch does not divide
+    -- and every rank pads its block to ceil(n / world) scenes before the collective; the padding is cut out of the
+    result.  Without it the blocks must be equal (checked against the shard rule when it can be)."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return packed
     world = dist.get_world_size(group)
-    gathered = torch.empty((world * packed.size(0),) + tuple(packed.shape[1:]), dtype=packed.dtype,
-                           device=packed.device)
-    dist.all_gather_into_tensor(gathered, packed.contiguous(), group=group)
+    rank = dist.get_rank(group)
+    b = packed.size(0)
+    if n_scenes_total is None:
+        per = b
+        counts = None
+    else:
+        per = -(-int(n_scenes_total) // world)
+        counts = [hi - lo for lo, hi in (scene_shard(int(n_scenes_total), r, world) for r in range(world))]
+        if counts[rank] != b:
+            raise ValueError("rank %d holds %d scenes, scene_shard(%d, %d, %d) says %d"
+                             % (rank, b, n_scenes_total, rank, world, counts[rank]))
+    send = packed.contiguous()
+    if b < per:
+        send = torch.cat([send, send.new_zeros((per - b,) + tuple(send.shape[1:]))], 0)
+    gathered = torch.empty((world * per,) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(gathered, send, group=group)
+    if counts is not None and any(c != per for c in counts):
+        gathered = torch.cat([gathered[r * per:r * per + c] for r, c in enumerate(counts)], 0)
     return gathered

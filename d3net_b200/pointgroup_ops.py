@@ -5,13 +5,25 @@ argument meaning, return conventions, autograd behaviour and assertion behaviour
 model/pointgroup.py, lib/dataset/pipeline.py and lib/solver/pointgroup.py can import this module in
 place of the original.
 
-What changed underneath (none of it visible in results):
+What changed underneath:
   * outputs that the kernels fully overwrite are allocated uninitialised instead of zero-filled;
   * ball query is count -> exact allocation -> fill, so the reference's grow-and-retry loop
     (functions/pointgroup_ops.py:135-142) is gone and ``meanActive`` is only a hint;
   * voxelization_idx and bfs_cluster -- CPU-only in the reference -- run on the GPU.  CPU inputs (what
     the reference's callers pass, model/pointgroup.py:169,297) are staged through the current CUDA
     device and the results come back on the input's device; CUDA inputs stay on the device.
+Two differences ARE visible, both inside what the reference leaves undefined or what its caller never reads:
+  * ``ballquery_batch_p``: every point's list is the reference's (ascending, first 1000), but the SEGMENTS sit in
+    ``idx`` in grid-cell order; the reference places them by ``atomicAdd`` (bfs_cluster.cu:47), differently on
+    every run.  Scene membership is taken from ``batch_idxs``; ``batch_offsets`` (the reference's scan range,
+    bfs_cluster.cu:27-32) is only consulted for the scene count -- the two agree for every input the caller builds
+    (model/pointgroup.py:291-292).
+  * ``bfs_cluster``: clusters, their order and their members are the reference's; inside a cluster the members are
+    listed in ASCENDING point order, the reference lists them in BFS visit order (bfs_cluster.cpp:44-51).  Everything
+    downstream that is integer-valued is unaffected (voxel sets, argmax rows, IoUs); the row order of
+    ``clusters_coords`` changes, hence the first-appearance numbering of the cluster voxels (a consistent relabelling
+    of voxel_coords / p2v_map / v2p_map rows) and the fp32 summation order inside ``sec_mean`` / the voxel means --
+    within the 1e-6 relative contract, not bit-identical to a reference run.
 There is no CPU fallback: without the CUDA library or a GPU these functions raise.
 """
 import torch
@@ -128,13 +140,15 @@ point_recover = PointRecover.apply
 
 class BallQueryBatchP(Function):
     @staticmethod
-    def forward(ctx, coords, batch_idxs, batch_offsets, radius, meanActive):
+    def forward(ctx, coords, batch_idxs, batch_offsets, radius, meanActive, ws_out=None):
         '''
         :param coords: (n, 3) float
         :param batch_idxs: (n) int
         :param batch_offsets: (B+1) int
         :param radius: float
         :param meanActive: int (the reference's initial buffer guess; unused here)
+        :param ws_out: optional list; receives the call's grid workspace tensor (this module's own hand-over to
+                       bfs_cluster -- a per-call object, so concurrent callers cannot see each other's workspace)
         :return: idx (nActive), int -- per point ascending, segments laid out in query (cell) order
         :return: start_len (n, 2), int
         (functions/pointgroup_ops.py:115-150)
@@ -149,40 +163,44 @@ class BallQueryBatchP(Function):
         t = _sub("fill")
         PG_OP.ballquery_fill_impl(coords, radius, start_len, idx, ws)
         _end(t)
-        BallQueryBatchP._last_ws = ws[0]
+        if ws_out is not None:
+            ws_out.append(ws[0])
         ctx.mark_non_differentiable(idx, start_len)
         return idx, start_len
 
     @staticmethod
     def backward(ctx, a=None, b=None):
-        return None, None, None, None, None
+        return None, None, None, None, None, None
 
-
-BallQueryBatchP._last_ws = None
 
 # bfs_cluster on stamped lists also gets the ball query's uniform grid (its workspace tensor, kept alive by the
 # stamp): cells that are already one component are not swept (pg_bfs_cluster_count_grid).  Results are identical.
 USE_GRID_SWEEP = True
 
 
+def _tag(idx, start_len):
+    return (start_len.data_ptr(), start_len._version, idx.data_ptr(), idx._version, tuple(start_len.shape), idx.numel(),
+            str(idx.device), str(start_len.device))
+
+
 def _stamp(idx, start_len, grid_ws=None):
-    """Provenance of a neighbour-list pair: the two tensors, as produced here and never written since
-    (torch bumps ``_version`` on every in-place write).  bfs_cluster may then skip the validation it
+    """Provenance of a neighbour-list pair: the two tensors (storage, shape, device), as produced here and never
+    written since (torch bumps ``_version`` on every in-place write).  bfs_cluster may then skip the validation it
     runs on foreign lists."""
-    idx._pg_lists = (start_len.data_ptr(), start_len._version, idx._version, tuple(start_len.shape))
+    idx._pg_lists = _tag(idx, start_len)
     idx._pg_grid = grid_ws
 
 
 def _stamped(idx, start_len):
     tag = getattr(idx, "_pg_lists", None)
-    return (tag is not None and idx.is_cuda and start_len.is_cuda
-            and tag == (start_len.data_ptr(), start_len._version, idx._version, tuple(start_len.shape)))
+    return (tag is not None and idx.is_cuda and start_len.is_cuda and idx.device == start_len.device
+            and tag == _tag(idx, start_len))
 
 
 def ballquery_batch_p(coords, batch_idxs, batch_offsets, radius, meanActive):
-    idx, start_len = BallQueryBatchP.apply(coords, batch_idxs, batch_offsets, radius, meanActive)
-    ws, BallQueryBatchP._last_ws = BallQueryBatchP._last_ws, None
-    _stamp(idx, start_len, ws)
+    ws = []
+    idx, start_len = BallQueryBatchP.apply(coords, batch_idxs, batch_offsets, radius, meanActive, ws)
+    _stamp(idx, start_len, ws[0] if ws else None)
     return idx, start_len
 
 
@@ -200,9 +218,16 @@ class BFSCluster(Function):
         assert semantic_label.is_contiguous()
         assert ball_query_idxs.is_contiguous()
         assert start_len.is_contiguous()
-        dev = PG_OP._compute_device(semantic_label)
-        trusted = _stamped(ball_query_idxs, start_len)
+        # compute where the lists already are (they are the big operand); otherwise where semantic_label is / the
+        # current device.  Lists that have to be moved are copies: no provenance, no grid.
+        if ball_query_idxs.is_cuda:
+            dev = ball_query_idxs.device
+        else:
+            dev = PG_OP._compute_device(semantic_label)
+        trusted = _stamped(ball_query_idxs, start_len) and ball_query_idxs.device == dev
         grid_ws = getattr(ball_query_idxs, "_pg_grid", None) if (trusted and USE_GRID_SWEEP) else None
+        if grid_ws is not None and grid_ws.device != dev:
+            grid_ws = None
         ci, co, _ = PG_OP.bfs_cluster_impl(semantic_label.to(dev), ball_query_idxs.to(dev), start_len.to(dev),
                                            threshold, trusted=trusted, grid_ws=grid_ws)
         if not semantic_label.is_cuda:

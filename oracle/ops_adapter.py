@@ -59,3 +59,73 @@ class OracleOps:
 
     def sec_max(self, inp, offsets):
         return torch.from_numpy(o.sec_max(_n(inp), _n(offsets)))
+
+
+class RefGpuOps:
+    """The reference's lib/pointgroup_ops as a D3Net user runs it today, on the GPU box: its nine CUDA kernels
+    (compiled unmodified for sm_100a into oracle/_ref) on device tensors and its two CPU ops after the D2H copies its
+    callers make (model/pointgroup.py:167-169,297,305), with the wrapper's protocol (zero-filled outputs, the ball
+    query's grow-and-retry loop, functions/pointgroup_ops.py:135-142).  bench.py's `reference_mixed` leg and the GPU
+    reference tests only; needs a CUDA device."""
+
+    def __init__(self):
+        self.ref = build_ref.load()
+
+    def voxelization_idx(self, coords, batchsize, mode=4):
+        c = coords.cpu().contiguous()                                     # the op is CPU-only in the reference
+        oc, im, om = c.new(), torch.zeros(c.size(0), dtype=torch.int32), torch.zeros(0, dtype=torch.int32)
+        self.ref.voxelize_idx(c, oc, im, om, batchsize, mode)
+        return oc.to(coords.device), im.to(coords.device), om.to(coords.device)
+
+    def voxelization(self, feats, map_rule, mode=4):
+        M, W = map_rule.shape
+        out = torch.zeros((M, feats.size(1)), dtype=torch.float32, device=feats.device)
+        self.ref.voxelize_fp(feats.contiguous(), out, map_rule.contiguous(), mode, M, W - 1, feats.size(1))
+        return out
+
+    def ballquery_batch_p(self, coords, batch_idxs, batch_offsets, radius, meanActive):
+        n = coords.size(0)
+        while True:
+            idx = torch.zeros(n * meanActive, dtype=torch.int32, device=coords.device)
+            start_len = torch.zeros((n, 2), dtype=torch.int32, device=coords.device)
+            nActive = self.ref.ballquery_batch_p(coords, batch_idxs, batch_offsets, idx, start_len, n, meanActive, radius)
+            if nActive <= n * meanActive:
+                break
+            meanActive = int(nActive // n + 1)
+        return idx[:nActive], start_len
+
+    def bfs_cluster(self, semantic_label, ball_query_idxs, start_len, threshold):
+        sem = semantic_label.cpu().contiguous()
+        ci, co = sem.new(), sem.new()
+        self.ref.bfs_cluster(sem, ball_query_idxs.cpu().contiguous(), start_len.cpu().contiguous(), ci, co,
+                             start_len.size(0), threshold)
+        return ci.to(semantic_label.device), co.to(semantic_label.device)
+
+    def roipool(self, feats, proposals_offset):
+        nP, C = proposals_offset.numel() - 1, feats.size(1)
+        out = torch.zeros((nP, C), dtype=torch.float32, device=feats.device)
+        arg = torch.zeros((nP, C), dtype=torch.int32, device=feats.device)
+        self.ref.roipool_fp(feats.contiguous(), proposals_offset.contiguous(), out, arg, nP, C)
+        return out
+
+    def get_iou(self, proposals_idx, proposals_offset, instance_labels, instance_pointnum):
+        nP, nI = proposals_offset.numel() - 1, instance_pointnum.numel()
+        out = torch.zeros((nP, nI), dtype=torch.float32, device=proposals_idx.device)
+        self.ref.get_iou(proposals_idx.contiguous(), proposals_offset.contiguous(), instance_labels.contiguous(),
+                         instance_pointnum.contiguous(), out, nI, nP)
+        return out
+
+    def _sec(self, fn, inp, offsets):
+        nP, C = offsets.numel() - 1, inp.size(1)
+        out = torch.zeros((nP, C), dtype=torch.float32, device=inp.device)
+        fn(inp.contiguous(), offsets.contiguous(), out, nP, C)
+        return out
+
+    def sec_mean(self, inp, offsets):
+        return self._sec(self.ref.sec_mean, inp, offsets)
+
+    def sec_min(self, inp, offsets):
+        return self._sec(self.ref.sec_min, inp, offsets)
+
+    def sec_max(self, inp, offsets):
+        return self._sec(self.ref.sec_max, inp, offsets)

@@ -30,7 +30,7 @@ def test_every_declared_symbol_is_exported_and_bound(lib):
         assert hasattr(lib, n), "libpg_b200.so does not export " + n
         assert n in _native.SIGNATURES, "no ctypes signature for " + n
     assert sorted(_native.SIGNATURES) == names      # nothing bound that the header does not declare
-    assert lib.pg_abi_version() == 1
+    assert lib.pg_abi_version() == _native.ABI_VERSION
 
 
 def test_header_cites_the_reference_interface():

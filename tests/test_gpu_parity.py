@@ -431,6 +431,59 @@ def test_bfs_grid_sweep_density_gradient(ops, oracle):
         _grid_vs_oracle(ops, oracle, g["xyz"], g["batch_idxs"], g["batch_offsets"], labels, 0.03, 5)
 
 
+@pytest.mark.parametrize("bad_row", [(2 ** 30, 700), (-5, 3), (10, 2 ** 30), (0, -1), (2 ** 31 - 8, 16)])
+def test_bfs_malformed_start_len_raises_cleanly(ops, oracle, bad_row):
+    """Rows of start_len that point outside ball_query_idxs: the reference reads out of bounds there
+    (bfs_cluster.cpp:40-42); here the validating sweep never dereferences them and the call fails with a clean error
+    -- and the device stays usable (no sticky fault), which the good call afterwards proves."""
+    from d3net_b200 import PG_OP, _native
+    s = object_subset(small_batch(2, 9000))
+    idx, sl = oracle.ballquery_batch_p(s["shifted"], s["batch_idxs"], s["batch_offsets"], 0.03)
+    bad = sl.copy()
+    rows = np.random.default_rng(1).integers(0, len(bad), 50)
+    bad[rows] = np.array(bad_row, np.int32)
+    for generic in (0, 1):
+        with pytest.raises(_native.PgError, match="start_len"):
+            PG_OP.bfs_cluster_impl(cu(s["sem"]), cu(idx), cu(bad), 50, generic=generic)
+        torch.cuda.synchronize()
+    _check_bfs(ops, oracle, s["sem"], idx, sl, 50, expect_generic=False)
+
+
+def test_bfs_two_threads_do_not_share_grid_workspaces(ops, oracle):
+    """Two threads running ballquery_batch_p + bfs_cluster on different inputs: each bfs_cluster gets the grid of
+    ITS ball query (the hand-over is per call, not a module global)."""
+    import threading
+    sets = [object_subset(small_batch(2, 9000, config_id=11)), object_subset(small_batch(1, 14000, config_id=12))]
+    want = []
+    for s in sets:
+        idx, sl = oracle.ballquery_batch_p(s["shifted"], s["batch_idxs"], s["batch_offsets"], 0.03)
+        want.append(oracle.bfs_cluster(s["sem"], idx, sl, 50))
+    errors = []
+
+    def work(k):
+        try:
+            s = sets[k]
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                x, b, o, sem = cu(s["shifted"]), cu(s["batch_idxs"]), cu(s["batch_offsets"]), cu(s["sem"])
+                for _ in range(6):
+                    idx, sl = ops.ballquery_batch_p(x, b, o, 0.03, 300)
+                    assert idx._pg_grid is not None and idx._pg_grid.numel() >= 0
+                    ci, co = ops.bfs_cluster(sem, idx, sl, 50)
+                    np.testing.assert_array_equal(npy(co), want[k][1])
+                    for a, c in zip(oracle.canonical_clusters(npy(ci), npy(co)), oracle.canonical_clusters(*want[k])):
+                        np.testing.assert_array_equal(a, c)
+        except Exception as e:          # noqa: BLE001  (reported by the main thread)
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_bfs_empty(ops):
     z = torch.zeros(0, dtype=torch.int32).cuda()
     ci, co = ops.bfs_cluster(z, z, torch.zeros((0, 2), dtype=torch.int32).cuda(), 50)

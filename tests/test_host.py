@@ -93,6 +93,14 @@ out = pgdist.all_gather_proposals(packed)
 assert out.shape == (6, 4, pgdist.PACK_WIDTH), out.shape
 assert out[:, 0, 0].tolist() == [0., 1., 2., 3., 4., 5.]
 assert out[:3, :, 1].eq(1).all() and out[3:, :, 1].eq(2).all()
+# uneven split (7 scenes over 2 ranks: 4 + 3): padded to ceil(7 / 2) per rank, padding cut out of the result
+lo, hi = pgdist.scene_shard(7, rank, world)
+packed = torch.full((hi - lo, 4, pgdist.PACK_WIDTH), float(rank + 1))
+packed[:, :, 0] = torch.arange(lo, hi, dtype=torch.float32)[:, None]
+out = pgdist.all_gather_proposals(packed, n_scenes_total=7)
+assert out.shape == (7, 4, pgdist.PACK_WIDTH), out.shape
+assert out[:, 0, 0].tolist() == [0., 1., 2., 3., 4., 5., 6.]
+assert out[:4, :, 1].eq(1).all() and out[4:, :, 1].eq(2).all()
 dist.destroy_process_group()
 print("rank", rank, "ok")
 """
