@@ -144,7 +144,48 @@ def clusters_voxelization(ops, clusters_idx, clusters_offset, feats, coords, ful
                                        trace, (clusters_center, clusters_size))
 
 
-def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=False):
+_pool = None
+
+
+def _run_overlapped(fa, fb):
+    """fa() on a side stream in a worker thread, fb() on another side stream in this thread; both start after the
+    current stream's pending work and the current stream continues after both."""
+    global _pool
+    if _pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pg-chain")
+    dev = torch.cuda.current_device()
+    main = torch.cuda.current_stream()
+    sa, sb = _side_streams(dev)
+    sa.wait_stream(main)
+    sb.wait_stream(main)
+
+    def in_stream(fn, st):
+        torch.cuda.set_device(dev)
+        with torch.cuda.stream(st):
+            r = fn()
+        return r
+
+    fut = _pool.submit(in_stream, fa, sa)
+    rb = in_stream(fb, sb)
+    ra = fut.result()
+    main.wait_stream(sa)
+    main.wait_stream(sb)
+    for t in ra + rb:
+        t.record_stream(main)
+    return ra, rb
+
+
+_streams = {}
+
+
+def _side_streams(dev):
+    if dev not in _streams:
+        _streams[dev] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+    return _streams[dev]
+
+
+def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=False, overlap=False):
     """One pass of the hot path over one collated batch (all tensors on one CUDA device).
 
     batch: locs fp32 [N,3], locs_scaled int64 [N,4], feats fp32 [N,134], pt_feats fp32 [N,16],
@@ -182,33 +223,46 @@ def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=Fa
     sem_ = semantic_preds[object_idxs].int().contiguous()
 
     shifted = (coords_ + pt_offsets_).contiguous()
-    t = timer.start("ballquery(shift)")
-    idx_shift, start_len_shift = ops.ballquery_batch_p(shifted, batch_idxs_, batch_offsets_, scenes.CLUSTER_RADIUS,
-                                                       scenes.CLUSTER_SHIFT_MEANACTIVE)
-    timer.stop(t)
-    t = timer.start("bfs_cluster(shift)")
-    proposals_idx_shift, proposals_offset_shift = ops.bfs_cluster(sem_, idx_shift, start_len_shift,
-                                                                  scenes.CLUSTER_NPOINT_THRE)
-    timer.stop(t)
-    if trace is not None:
-        trace["ballquery(shift)"] = (shifted, batch_idxs_, batch_offsets_, idx_shift, start_len_shift)
-        trace["bfs_cluster(shift)"] = (sem_, idx_shift, start_len_shift, proposals_idx_shift.clone(),
-                                       proposals_offset_shift.clone())
-    out["nActive_shift"] = idx_shift.numel()
-    proposals_idx_shift[:, 1] = object_idxs[proposals_idx_shift[:, 1].long()].int()
 
-    t = timer.start("ballquery(raw)")
-    idx, start_len = ops.ballquery_batch_p(coords_, batch_idxs_, batch_offsets_, scenes.CLUSTER_RADIUS,
-                                           scenes.CLUSTER_MEANACTIVE)
-    timer.stop(t)
-    t = timer.start("bfs_cluster(raw)")
-    proposals_idx, proposals_offset = ops.bfs_cluster(sem_, idx, start_len, scenes.CLUSTER_NPOINT_THRE)
-    timer.stop(t)
-    if trace is not None:
-        trace["ballquery(raw)"] = (coords_, batch_idxs_, batch_offsets_, idx, start_len)
-        trace["bfs_cluster(raw)"] = (sem_, idx, start_len, proposals_idx.clone(), proposals_offset.clone())
-    out["nActive_raw"] = idx.numel()
-    proposals_idx[:, 1] = object_idxs[proposals_idx[:, 1].long()].int()
+    def cluster_shift():
+        t = timer.start("ballquery(shift)")
+        idx_shift, start_len_shift = ops.ballquery_batch_p(shifted, batch_idxs_, batch_offsets_, scenes.CLUSTER_RADIUS,
+                                                           scenes.CLUSTER_SHIFT_MEANACTIVE)
+        timer.stop(t)
+        t = timer.start("bfs_cluster(shift)")
+        pidx, poff = ops.bfs_cluster(sem_, idx_shift, start_len_shift, scenes.CLUSTER_NPOINT_THRE)
+        timer.stop(t)
+        if trace is not None:
+            trace["ballquery(shift)"] = (shifted, batch_idxs_, batch_offsets_, idx_shift, start_len_shift)
+            trace["bfs_cluster(shift)"] = (sem_, idx_shift, start_len_shift, pidx.clone(), poff.clone())
+        out["nActive_shift"] = idx_shift.numel()
+        pidx[:, 1] = object_idxs[pidx[:, 1].long()].int()
+        return pidx, poff
+
+    def cluster_raw():
+        t = timer.start("ballquery(raw)")
+        idx, start_len = ops.ballquery_batch_p(coords_, batch_idxs_, batch_offsets_, scenes.CLUSTER_RADIUS,
+                                               scenes.CLUSTER_MEANACTIVE)
+        timer.stop(t)
+        t = timer.start("bfs_cluster(raw)")
+        pidx, poff = ops.bfs_cluster(sem_, idx, start_len, scenes.CLUSTER_NPOINT_THRE)
+        timer.stop(t)
+        if trace is not None:
+            trace["ballquery(raw)"] = (coords_, batch_idxs_, batch_offsets_, idx, start_len)
+            trace["bfs_cluster(raw)"] = (sem_, idx, start_len, pidx.clone(), poff.clone())
+        out["nActive_raw"] = idx.numel()
+        pidx[:, 1] = object_idxs[pidx[:, 1].long()].int()
+        return pidx, poff
+
+    # The two clusterings (model/pointgroup.py:296-298 and :304-306) share their inputs and nothing else.  Each needs
+    # the host twice (exact output sizes); issued from two host threads on two streams, one's kernels fill the other's
+    # synchronisation bubbles and launch-bound stretches.  Same calls, same results -- scheduling only.
+    if overlap and coords_.is_cuda and timer.enabled is False:
+        (proposals_idx_shift, proposals_offset_shift), (proposals_idx, proposals_offset) = _run_overlapped(
+            cluster_shift, cluster_raw)
+    else:
+        proposals_idx_shift, proposals_offset_shift = cluster_shift()
+        proposals_idx, proposals_offset = cluster_raw()
 
     proposals_idx_shift[:, 0] += (proposals_offset.size(0) - 1)
     proposals_offset_shift = proposals_offset_shift + proposals_offset[-1]

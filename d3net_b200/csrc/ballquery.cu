@@ -40,11 +40,6 @@ constexpr int kMediumQ = 16;             // ... the latter only for cells with f
 
 // the class of a cell: served by the block-per-cell kernel?
 __host__ __device__ __forceinline__ bool bq_is_dense(int K, int nq) { return K > kSmallK || (K > kSmallSplit && nq > kMediumQ); }
-constexpr int kTile = 1024;              // candidates per shared-memory tile (dense cells)
-constexpr int kWinBits = 160 * 1024;     // index window covered by the rank bitmap (a 150k-point scene in one)
-constexpr int kWinWords = kWinBits / 32;
-constexpr int kQMax = 512;               // queries of one dense cell handled per pass
-constexpr int kDenseThreads = 256;
 constexpr int kChunkBlocks = 4;          // 32-candidate blocks per (query group, chunk) work item
 
 // Far coordinates (|x/s| >= 2^30) have an fp32 spacing above the radius, so two of them can only be
@@ -71,8 +66,7 @@ __global__ void __launch_bounds__(256) k_bq_neighbours(const int4 *__restrict__ 
                                                        const uint32_t *__restrict__ sorted_pt,
                                                        const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
                                                        int64_t *scalars, int32_t *__restrict__ nbr,
-                                                       int32_t *__restrict__ kc, int32_t *__restrict__ dense,
-                                                       uint2 *__restrict__ crange) {
+                                                       int32_t *__restrict__ kc, int32_t *__restrict__ dense) {
     const int64_t nc = scalars[0];
     const int lane = threadIdx.x & 31;
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -96,20 +90,6 @@ __global__ void __launch_bounds__(256) k_bq_neighbours(const int4 *__restrict__ 
         if (lane == 0) {
             kc[c] = cnt;
             if (bq_is_dense(cnt, ccnt[c])) dense[atomicAdd((unsigned long long *)&scalars[3], 1ULL)] = (int32_t)c;
-        }
-        if (bq_is_dense(cnt, ccnt[c])) {          // a dense cell: the index range of its candidates (lists ascend)
-            uint32_t head = 0xffffffffu, tail = 0u;
-            if (id >= 0) {
-                const int s0 = cstart[id], l0 = ccnt[id];
-                head = sorted_pt[s0];
-                tail = sorted_pt[s0 + l0 - 1];
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                head = min(head, __shfl_xor_sync(0xffffffffu, head, o));
-                tail = max(tail, __shfl_xor_sync(0xffffffffu, tail, o));
-            }
-            if (lane == 0) crange[c] = make_uint2(head, tail);
         }
     }
 }
@@ -285,118 +265,63 @@ __global__ void __launch_bounds__(256) k_bq_cells_small(const float *__restrict_
     }
 }
 
-// ---- dense cells: one block per cell ----------------------------------------------------------------
-struct DenseSmem {
+// ---- dense cells ----------------------------------------------------------------------------------------
+// Two kernels.  MERGE (a warp per cell, no block barrier anywhere): the cell's 27 ascending point lists are merged
+// through a small per-warp bitmap, window by window over the index range, into the cell's candidate list in
+// ascending original index; the indices go to cand_idx (the fill phase reads them), the coordinates to cand_xy /
+// cand_z in the pair layout of the packed predicate.  TEST (a block per cell, persistent, work claimed from a
+// counter): candidate tiles arrive in shared memory by bulk asynchronous copy (cp.async.bulk, completion on an
+// mbarrier; the next tile is in flight while the current one is tested), lanes are queries, candidates are
+// shared-memory broadcasts, two candidates per FADD2 / FMUL2 / FFMA2.
+__device__ __forceinline__ uint32_t warp_min_u32(uint32_t v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+constexpr int kMergeThreads = 256;
+constexpr int kWinBits = 160 * 1024;       // index window covered by the rank bitmap (a 150k-point scene in one)
+constexpr int kWinWords = kWinBits / 32;
+constexpr int kWordsPerThread = kWinWords / kMergeThreads;     // 20: every thread owns a run of consecutive words
+static_assert(kWordsPerThread % 4 == 0 && kWordsPerThread * kMergeThreads == kWinWords, "window / block shape");
+constexpr int kTestThreads = 128;
+constexpr int kTestTile = 512;             // candidates per shared-memory tile
+constexpr int kTestQ = 256;                // queries of one cell handled per pass
+
+struct MergeSmem {
     uint32_t bm[kWinWords];          // rank bitmap over the index window [s0, s0 + kWinBits)
-    float4 tile[kTile];              // candidates of the current tile, ascending index (w unused)
-    uint32_t tidx[kTile];            // their indices
-    float qx[kQMax], qy[kQMax], qz[kQMax];
-    int32_t qcnt[kQMax];             // hits so far per query
-    uint8_t qsat[kQMax];             // snapshot at the last tile boundary: the query already holds kCap hits
     const uint32_t *lptr[27];
     int32_t llen[27], la[27], lb[27];
-    int32_t wsum[kDenseThreads / 32];
-    uint32_t lo, hi, s0;
+    int32_t wsum[kMergeThreads / 32];
+    uint32_t s0, more;
     int32_t tw, cellslot;
+    long long cb;
 };
 
-// exclusive scan of one int per thread over the block; *total = block sum
-__device__ __forceinline__ int dense_block_exscan(int v, int32_t *wsum, int32_t *total_slot, int *total) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) wsum[w] = inc;
-    __syncthreads();
-    int before = 0, all = 0;
-#pragma unroll
-    for (int i = 0; i < kDenseThreads / 32; i++) {
-        const int t = wsum[i];
-        if (i < w) before += t;
-        all += t;
-    }
-    if (threadIdx.x == 0) *total_slot = all;
-    __syncthreads();
-    *total = all;
-    return before + inc - v;
-}
-
-// Loads the next non-empty index window at or after `from`: sets one bit per candidate whose index
-// falls into it and returns, per thread, its run of bitmap words [w0, w1), the rank (inside the
-// window) of the first bit of that run and the number of bits in it; S.tw = candidates in the window.
-__device__ __forceinline__ void dense_load_window(DenseSmem &S, uint32_t from, int &w0, int &w1, int &tbase, int &tlocal) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (warp == 0) {
-        // first unconsumed element of every list -> the window starts at the smallest one
-        int a = 0;
-        uint32_t nxt = 0xffffffffu;
-        if (lane < 27 && S.llen[lane] > 0) {
-            a = from <= S.lo ? 0 : lower_bound_u32(S.lptr[lane], S.llen[lane], from);
-            if (a < S.llen[lane]) nxt = S.lptr[lane][a];
-        }
-        uint32_t mn = nxt;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-        const uint32_t s0 = mn & ~31u;
-        if (lane < 27) {
-            S.la[lane] = a;
-            int b = S.llen[lane];
-            if (b > 0 && (uint64_t)S.hi >= (uint64_t)s0 + kWinBits) b = lower_bound_u32(S.lptr[lane], b, s0 + (uint32_t)kWinBits);
-            S.lb[lane] = b;
-        }
-        if (lane == 0) S.s0 = s0;
-    }
-    __syncthreads();
-    const uint32_t s0 = S.s0;
-    const uint32_t top = S.hi - s0;                               // hi >= s0 whenever a candidate is left
-    const int W = (int)min((uint32_t)kWinWords, (top >> 5) + 1u);
-    for (int w = tid; w < W; w += kDenseThreads) S.bm[w] = 0u;
-    __syncthreads();
-    for (int j = warp; j < 27; j += kDenseThreads / 32) {
-        const uint32_t *L = S.lptr[j];
-        for (int t = S.la[j] + lane; t < S.lb[j]; t += 32) {
-            const uint32_t v = L[t] - s0;
-            atomicOr(&S.bm[v >> 5], 1u << (v & 31u));
-        }
-    }
-    __syncthreads();
-    const int wpt = (W + kDenseThreads - 1) / kDenseThreads;
-    w0 = min(W, tid * wpt);
-    w1 = min(W, w0 + wpt);
-    int cnt = 0;
-    for (int w = w0; w < w1; w++) cnt += __popc(S.bm[w]);
-    int total;
-    tbase = dense_block_exscan(cnt, S.wsum, &S.tw, &total);
-    tlocal = cnt;
-}
-
-__global__ void __launch_bounds__(kDenseThreads, 4) k_bq_cells_dense(
+// MERGE: rank-select through a shared-memory bitmap.  One bit per candidate over the cell's index window, a block
+// scan of the per-thread popcounts, then every thread walks its words and emits the set bits in order -- ascending
+// candidates without a comparison.  The indices go straight to cand_idx; a second, lane-dense sweep fetches the
+// coordinates (all loads of a warp in flight together) and writes them in the pair layout.
+__global__ void __launch_bounds__(kMergeThreads) k_bq_merge_dense(
     const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cstart,
     const int32_t *__restrict__ ccnt, const int32_t *__restrict__ nbr, const int32_t *__restrict__ kc,
-    const int32_t *__restrict__ cand_start, const int32_t *__restrict__ mbase, const int32_t *__restrict__ dense,
-    const uint2 *__restrict__ crange, int64_t *scalars, uint32_t *__restrict__ masks, int64_t mask_capacity, float r2,
-    uint32_t *__restrict__ cand_idx, int32_t *__restrict__ counts, int32_t *__restrict__ kb) {
-    extern __shared__ uint4 dense_smem_raw[];
-    DenseSmem &S = *reinterpret_cast<DenseSmem *>(dense_smem_raw);
+    const int32_t *__restrict__ cand_start, const int32_t *__restrict__ dense, int64_t *scalars,
+    uint32_t *cand_idx, float4 *__restrict__ cand_xy, float2 *__restrict__ cand_z, int32_t *__restrict__ dbase) {
+    __shared__ __align__(16) MergeSmem S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nDense = scalars[3];
-    if (scalars[6] > mask_capacity) masks = nullptr;            // the caller's mask buffer is too small: run without
-    // hit <=> d2 < r2.  d2 is a sum of squares: +0 .. +inf or the canonical NaN, so the float compare is
-    // the signed compare of the bit patterns, and its outcome is the sign bit of (bits(d2) - bits(r2)).
-    const int thr = (r2 == r2) ? __float_as_int(r2) : 0;         // NaN radius: nothing is a neighbour
-    if (tid == 0) S.cellslot = (int32_t)atomicAdd((unsigned long long *)&scalars[4], 1ULL);
+    float *xy_f = reinterpret_cast<float *>(cand_xy);
+    float *z_f = reinterpret_cast<float *>(cand_z);
+    if (tid == 0) S.cellslot = (int32_t)atomicAdd((unsigned long long *)&scalars[5], 1ULL);
     for (;;) {
         __syncthreads();
         const int64_t slot = S.cellslot;
         if (slot >= nDense) break;
         int32_t next_slot = 0;                                   // claimed now, published after this cell's work
-        if (tid == 0) next_slot = (int32_t)atomicAdd((unsigned long long *)&scalars[4], 1ULL);
+        if (tid == 0) next_slot = (int32_t)atomicAdd((unsigned long long *)&scalars[5], 1ULL);
         const int c = __ldg(dense + slot);
-        const int K = __ldg(kc + c), nq = __ldg(ccnt + c), qs = __ldg(cstart + c), cbase = __ldg(cand_start + c);
-        const int mb = masks ? __ldg(mbase + c) : 0;
+        const int K = __ldg(kc + c), cbase = __ldg(cand_start + c);
+        const int Kpad = (K + 31) & ~31;
         if (warp == 0) {
             int len = 0;
             const uint32_t *L = sorted_pt;
@@ -405,99 +330,311 @@ __global__ void __launch_bounds__(kDenseThreads, 4) k_bq_cells_dense(
                 if (src >= 0) { len = __ldg(ccnt + src); L = sorted_pt + __ldg(cstart + src); }
                 S.lptr[lane] = L;
                 S.llen[lane] = len;
+                S.la[lane] = 0;
             }
-            if (lane == 0) { const uint2 rg = __ldg(crange + c); S.lo = rg.x; S.hi = rg.y; }
+            if (lane == 0) {                                     // where this cell's coordinates go (a multiple of 32)
+                const long long cb = (long long)atomicAdd((unsigned long long *)&scalars[7], (unsigned long long)Kpad);
+                dbase[slot] = (int32_t)(uint32_t)cb;             // < 34 * 2^26 < 2^32
+                S.cb = cb;
+            }
         }
         __syncthreads();
+        const long long cb = S.cb;
+        int rank_base = 0;                                       // candidates emitted by earlier windows
+        for (;;) {
+            // ---- next window: starts at the smallest unconsumed element of the 27 lists
+            if (warp == 0) {
+                uint32_t nxt = 0xffffffffu;
+                int a = 0, len = 0;
+                const uint32_t *L = nullptr;
+                if (lane < 27) {
+                    a = S.la[lane]; len = S.llen[lane]; L = S.lptr[lane];
+                    if (a < len) nxt = __ldg(L + a);
+                }
+                const uint32_t mn = warp_min_u32(nxt);
+                const uint32_t s0 = mn & ~31u;
+                int bnd = len;
+                if (lane < 27 && a < len && __ldg(L + len - 1) - s0 >= (uint32_t)kWinBits)
+                    bnd = a + lower_bound_u32(L + a, len - a, s0 + (uint32_t)kWinBits);
+                if (lane < 27) S.lb[lane] = bnd;
+                const unsigned more = __ballot_sync(0xffffffffu, lane < 27 && bnd < len);
+                if (lane == 0) { S.s0 = s0; S.more = more; }
+            }
+            // the bitmap is all zero here (cleared below by the threads that walked it)
+            if (rank_base == 0) {
+                uint4 *z = reinterpret_cast<uint4 *>(S.bm + tid * kWordsPerThread);
+#pragma unroll
+                for (int k = 0; k < kWordsPerThread / 4; k++) z[k] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            __syncthreads();
+            const uint32_t s0 = S.s0;
+            for (int j = warp; j < 27; j += kMergeThreads / 32) {
+                const uint32_t *L = S.lptr[j];
+                const int b1 = S.lb[j];
+                for (int t = S.la[j] + lane; t < b1; t += 32) {
+                    const uint32_t v = __ldg(L + t) - s0;
+                    atomicOr(&S.bm[v >> 5], 1u << (v & 31u));
+                }
+            }
+            __syncthreads();
+            // ---- popcount of the thread's run of words, block scan -> rank of its first bit
+            uint4 *run = reinterpret_cast<uint4 *>(S.bm + tid * kWordsPerThread);
+            int cnt = 0;
+#pragma unroll
+            for (int k = 0; k < kWordsPerThread / 4; k++) {
+                const uint4 q = run[k];
+                cnt += __popc(q.x) + __popc(q.y) + __popc(q.z) + __popc(q.w);
+            }
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) S.wsum[warp] = inc;
+            __syncthreads();
+            int before = 0, tw = 0;
+#pragma unroll
+            for (int i = 0; i < kMergeThreads / 32; i++) {
+                const int t = S.wsum[i];
+                if (i < warp) before += t;
+                tw += t;
+            }
+            // ---- walk: emit the set bits of the run in order, clear the words for the next window / cell
+            if (cnt) {
+                uint32_t *out = cand_idx + cbase + rank_base + before + inc - cnt;
+                const uint32_t base_id = s0 + (uint32_t)(tid * kWordsPerThread << 5);
+#pragma unroll
+                for (int k = 0; k < kWordsPerThread / 4; k++) {
+                    const uint4 q = run[k];
+                    const uint32_t wv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        uint32_t word = wv[u];
+                        while (word) {
+                            const int b = __ffs((int)word) - 1;
+                            word &= word - 1u;
+                            *out++ = base_id + (uint32_t)((k * 4 + u) << 5) + (uint32_t)b;
+                        }
+                    }
+                    run[k] = make_uint4(0u, 0u, 0u, 0u);
+                }
+            }
+            if (tid < 27) S.la[tid] = S.lb[tid];
+            __syncthreads();                                     // the window's indices are in cand_idx (same block: visible)
+            // ---- coordinates, lane-dense
+            for (int e = tid; e < tw; e += kMergeThreads) {
+                const int pos = rank_base + e;
+                const uint32_t id = __ldcg(cand_idx + cbase + pos);
+                const float *p = xyz + 3 * (int64_t)id;
+                const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+                const long long q = cb + pos;
+                float *pxy = xy_f + ((q >> 1) << 2) + (q & 1);
+                pxy[0] = x;
+                pxy[2] = y;
+                z_f[q] = z;
+            }
+            rank_base += tw;
+            if (S.more == 0u) break;                             // (read before anyone can rewrite it: the next write
+            __syncthreads();                                     //  follows this barrier)
+        }
+        // padding up to a multiple of 32: +inf never passes the predicate
+        if (tid < Kpad - K) {
+            const long long q = cb + K + tid;
+            float *pxy = xy_f + ((q >> 1) << 2) + (q & 1);
+            pxy[0] = INFINITY;
+            pxy[2] = INFINITY;
+            z_f[q] = INFINITY;
+        }
+        if (tid == 0) S.cellslot = next_slot;
+    }
+}
+
+// mbarrier / bulk-copy helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct TestSmem {
+    float4 txy[2][kTestTile / 2];     // two tiles in flight: pair p = candidates (2p, 2p+1): (x0, x1, y0, y1)
+    float2 tz[2][kTestTile / 2];      //                                                        (z0, z1)
+    float qx[kTestQ], qy[kTestQ], qz[kTestQ];
+    int32_t qcnt[kTestQ];             // hits so far per query
+    uint8_t qsat[kTestQ];             // snapshot at the last tile boundary: the query already holds kCap hits
+    uint64_t full[2];                 // mbarriers: tile landed
+    int32_t cellslot;
+};
+
+// One work item: query group g (lane l tests queries g*128 + j*32 + l, j < Q) against the 32-candidate
+// blocks [b0, b1) of the tile in `buf`.  A candidate pair is read from shared memory ONCE (LDS.128 + LDS.64, broadcast)
+// and tested against the lane's Q queries: the shared-memory pipe delivers 512 B per LDS.128 whatever the broadcast, so
+// at Q = 1 it, not the FP32 pipe, bounds the kernel (6 cycles per pair against 2.25 issue cycles).
+template <int Q>
+__device__ __forceinline__ void bq_test_item(TestSmem &S, int buf, int g, int b0, int b1, int nqs, int nq, int sg0, int64_t mrow0,
+                                             uint32_t *__restrict__ masks, int thr, bool can_saturate, int lane) {
+    float ox[Q], oy[Q], oz[Q];
+    bool live[Q];
+    int cnt[Q];
+    bool any_unsat = false;
+#pragma unroll
+    for (int j = 0; j < Q; j++) {
+        const int qi = (g << 7) + j * 32 + lane;
+        live[j] = qi < nqs;
+        ox[j] = live[j] ? S.qx[qi] : NAN; oy[j] = live[j] ? S.qy[qi] : NAN; oz[j] = live[j] ? S.qz[qi] : NAN;
+        cnt[j] = 0;
+        any_unsat |= live[j] && !S.qsat[qi];
+    }
+    if (can_saturate && !__any_sync(0xffffffffu, any_unsat)) return;   // all of them already hold kCap hits
+    for (int b = b0; b < b1; b++) {
+        const float4 *pxy = S.txy[buf] + (b << 4);
+        const float2 *pz = S.tz[buf] + (b << 4);
+        unsigned m[Q];
+#pragma unroll
+        for (int j = 0; j < Q; j++) m[j] = 0u;
+        // Two candidates per instruction (sm_100 packed fp32: FADD2 / FMUL2 / FFMA2, each half rounded to nearest
+        // exactly like the scalar op): d2 = fma(dz, dz, fma(dx, dx, dy * dy)) as compiled from bfs_cluster.cu:36.
+        // hit <=> d2 < r2.  d2 is a sum of squares: +0 .. +inf or the canonical NaN (0x7fffffff), so the float compare
+        // is the signed compare of the bit patterns and its outcome the sign bit of bits(d2) - bits(r2) -- taken on the
+        // integer pipe, which the packed FP32 work leaves idle.
+#pragma unroll
+        for (int u = 15; u >= 0; u--) {           // candidate 31 first: it ends up in bit 31
+            const float4 cxy = pxy[u];
+            const float2 cz = pz[u];
+            const float2 ncx = make_float2(-cxy.x, -cxy.y), ncy = make_float2(-cxy.z, -cxy.w), ncz = make_float2(-cz.x, -cz.y);
+#pragma unroll
+            for (int j = 0; j < Q; j++) {
+                const float2 dx = __fadd2_rn(make_float2(ox[j], ox[j]), ncx);
+                const float2 dy = __fadd2_rn(make_float2(oy[j], oy[j]), ncy);
+                const float2 dz = __fadd2_rn(make_float2(oz[j], oz[j]), ncz);
+                const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+                m[j] = __funnelshift_l((unsigned)(__float_as_int(d2.y) - thr), m[j], 1);
+                m[j] = __funnelshift_l((unsigned)(__float_as_int(d2.x) - thr), m[j], 1);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < Q; j++) {
+            cnt[j] += __popc(m[j]);
+            if (masks && live[j]) masks[mrow0 + (int64_t)b * nq + sg0 + (g << 7) + j * 32 + lane] = m[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < Q; j++)
+        if (live[j] && cnt[j]) atomicAdd(&S.qcnt[(g << 7) + j * 32 + lane], cnt[j]);
+}
+
+__global__ void __launch_bounds__(kTestThreads, 8) k_bq_test_dense(
+    const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cstart,
+    const int32_t *__restrict__ ccnt, const int32_t *__restrict__ kc, const int32_t *__restrict__ mbase,
+    const int32_t *__restrict__ dense, const int32_t *__restrict__ dbase, const float4 *__restrict__ cand_xy,
+    const float2 *__restrict__ cand_z, int64_t *scalars, uint32_t *__restrict__ masks, int64_t mask_capacity, float r2,
+    int32_t *__restrict__ counts, int32_t *__restrict__ kb) {
+    __shared__ __align__(128) TestSmem S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t nDense = scalars[3];
+    if (scalars[6] > mask_capacity) masks = nullptr;            // the caller's mask buffer is too small: run without
+    const int thr = (r2 == r2) ? __float_as_int(r2) : 0;         // NaN radius: nothing is a neighbour
+    if (tid == 0) {
+        mbar_init(&S.full[0], 1);
+        mbar_init(&S.full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        S.cellslot = (int32_t)atomicAdd((unsigned long long *)&scalars[4], 1ULL);
+    }
+    uint32_t uses0 = 0, uses1 = 0;                               // completed uses of each buffer (its mbarrier's phase)
+    for (;;) {
+        __syncthreads();
+        const int64_t slot = S.cellslot;
+        if (slot >= nDense) break;
+        int32_t next_slot = 0;                                   // claimed now, published after this cell's work
+        if (tid == 0) next_slot = (int32_t)atomicAdd((unsigned long long *)&scalars[4], 1ULL);
+        const int c = __ldg(dense + slot);
+        const int K = __ldg(kc + c), nq = __ldg(ccnt + c), qs = __ldg(cstart + c);
+        const int64_t cb = (int64_t)(uint32_t)__ldg(dbase + slot);
+        const int64_t mb = masks ? __ldg(mbase + c) : 0;
+        const int Kpad = (K + 31) & ~31;
+        const int ntiles = (Kpad + kTestTile - 1) / kTestTile;
+        const bool can_saturate = K > kCap;
+        auto issue = [&](int t, int buf) {                       // thread 0: start the copy of tile t into buffer buf
+            const int n = min(kTestTile, Kpad - t * kTestTile);  // a multiple of 32 candidates
+            const int64_t q0 = cb + (int64_t)t * kTestTile;      // a multiple of 32
+            mbar_expect_tx(&S.full[buf], (uint32_t)n * 12u);
+            bulk_g2s(S.txy[buf], cand_xy + (q0 >> 1), (uint32_t)n * 8u, &S.full[buf]);
+            bulk_g2s(S.tz[buf], cand_z + (q0 >> 1), (uint32_t)n * 4u, &S.full[buf]);
+        };
         int built_max = 0;
-        for (int sg0 = 0; sg0 < nq; sg0 += kQMax) {                    // passes over the cell's queries (one, normally)
-            const int nqs = min(kQMax, nq - sg0);
-            for (int t = tid; t < nqs; t += kDenseThreads) {
+        for (int sg0 = 0; sg0 < nq; sg0 += kTestQ) {                 // passes over the cell's queries (one, normally)
+            const int nqs = min(kTestQ, nq - sg0);
+            if (tid == 0) issue(0, 0);
+            for (int t = tid; t < nqs; t += kTestThreads) {
                 const uint32_t k = __ldg(sorted_pt + qs + sg0 + t);
                 S.qx[t] = __ldg(xyz + 3 * (int64_t)k); S.qy[t] = __ldg(xyz + 3 * (int64_t)k + 1); S.qz[t] = __ldg(xyz + 3 * (int64_t)k + 2);
                 S.qcnt[t] = 0;
                 S.qsat[t] = 0;
             }
-            int w0, w1, tbase, tlocal;
-            int rank_base = 0;                                         // rank of the window's first candidate
-            dense_load_window(S, 0u, w0, w1, tbase, tlocal);           // (its barriers also publish the query rows)
+            __syncthreads();
+            // query groups: 128 queries each (four per lane); the last one holds the remainder with as few queries
+            // per lane as it needs (1..4), so the padding is what groups of 32 would give
+            const int G = (nqs + 127) >> 7;
             int built = 0;
-            for (int Rlo = 0; Rlo < K; Rlo += kTile) {
-                const int Rhi = min(Rlo + kTile, K), nt = Rhi - Rlo;
-                for (;;) {                                             // windows that overlap the tile
-                    int r = rank_base + tbase;
-                    if (r < Rhi && r + tlocal > Rlo) {
-                        const uint32_t s0 = S.s0;
-                        for (int w = w0; w < w1 && r < Rhi; w++) {
-                            uint32_t word = S.bm[w];
-                            const int pc = __popc(word);
-                            if (r + pc <= Rlo) { r += pc; continue; }
-                            while (word) {
-                                const int b = __ffs((int)word) - 1;
-                                word &= word - 1u;
-                                if (r >= Rlo && r < Rhi) S.tidx[r - Rlo] = s0 + ((uint32_t)w << 5) + (uint32_t)b;
-                                r++;
-                            }
-                        }
-                    }
-                    const int tw = S.tw;
-                    if (rank_base + tw >= Rhi) break;                  // the tile is complete
-                    rank_base += tw;
-                    const uint32_t nextfrom = S.s0 + (uint32_t)kWinBits;   // < 2^27: indices are below 2^26
-                    __syncthreads();                                   // everyone is done with this bitmap
-                    dense_load_window(S, nextfrom, w0, w1, tbase, tlocal);
-                }
-                const int ntp = (nt + 31) & ~31;
-                __syncthreads();
-                // coordinates: every thread fetches a few candidates, all loads in flight together
-                for (int t = tid; t < ntp; t += kDenseThreads) {
-                    float4 v = make_float4(INFINITY, INFINITY, INFINITY, 0.f);     // padding never passes the predicate
-                    if (t < nt) {
-                        const uint32_t id = S.tidx[t];
-                        const float *p = xyz + 3 * (int64_t)id;
-                        v = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
-                        cand_idx[cbase + Rlo + t] = id;
-                    }
-                    S.tile[t] = v;
-                }
-                __syncthreads();
-                // ---- test: lane = query, the tile's candidates come as shared-memory broadcasts
-                const int nblk = ntp >> 5;
-                const int G = (nqs + 31) >> 5, nch = (nblk + kChunkBlocks - 1) / kChunkBlocks;
-                for (int item = warp; item < G * nch; item += kDenseThreads / 32) {
+            for (int t = 0; t < ntiles; t++) {
+                const int buf = t & 1;
+                // the other buffer was released by the barrier that ended tile t - 1
+                if (tid == 0 && t + 1 < ntiles) issue(t + 1, buf ^ 1);
+                mbar_wait(&S.full[buf], (buf ? uses1 : uses0) & 1u);
+                if (buf) uses1++; else uses0++;
+                const int nt = min(kTestTile, Kpad - t * kTestTile);
+                const int nblk = nt >> 5;
+                // chunks of blocks: at least one item per warp when the tile allows it
+                const int G32 = (nqs + 31) >> 5;
+                const int per = max(1, min(kChunkBlocks, (nblk * G32 + 4 * (kTestThreads / 32) - 1) / (4 * (kTestThreads / 32))));
+                const int nch = (nblk + per - 1) / per;
+                const int64_t mrow0 = mb + (int64_t)t * (kTestTile / 32) * nq;
+                for (int item = warp; item < G * nch; item += kTestThreads / 32) {
                     const int g = item / nch, ch = item - g * nch;
-                    const int qi = (g << 5) + lane;
-                    const bool live = qi < nqs;
-                    if (!__any_sync(0xffffffffu, live && !S.qsat[qi])) continue;   // all 32 already hold kCap hits
-                    const float ox = live ? S.qx[qi] : NAN, oy = live ? S.qy[qi] : NAN, oz = live ? S.qz[qi] : NAN;
-                    int cnt = 0;
-                    const int b1 = min(nblk, (ch + 1) * kChunkBlocks);
-                    for (int b = ch * kChunkBlocks; b < b1; b++) {
-                        const float4 *tp = S.tile + (b << 5);
-                        unsigned m = 0;
-#pragma unroll
-                        for (int u = 31; u >= 0; u--) {           // candidate 31 first: it ends up in bit 31
-                            const float4 cd = tp[u];
-                            const float dx = __fsub_rn(ox, cd.x), dy = __fsub_rn(oy, cd.y), dz = __fsub_rn(oz, cd.z);
-                            const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
-                            m = __funnelshift_l((unsigned)(__float_as_int(d2) - thr), m, 1);
-                        }
-                        cnt += __popc(m);
-                        if (masks && live) masks[mb + (int64_t)((Rlo >> 5) + b) * nq + sg0 + qi] = m;
+                    const int b0 = ch * per, b1 = min(nblk, b0 + per);
+                    const int Qg = min(4, (nqs - (g << 7) + 31) >> 5);
+                    if (Qg == 4) bq_test_item<4>(S, buf, g, b0, b1, nqs, nq, sg0, mrow0, masks, thr, can_saturate, lane);
+                    else if (Qg == 3) bq_test_item<3>(S, buf, g, b0, b1, nqs, nq, sg0, mrow0, masks, thr, can_saturate, lane);
+                    else if (Qg == 2) bq_test_item<2>(S, buf, g, b0, b1, nqs, nq, sg0, mrow0, masks, thr, can_saturate, lane);
+                    else bq_test_item<1>(S, buf, g, b0, b1, nqs, nq, sg0, mrow0, masks, thr, can_saturate, lane);
+                }
+                built = min(K, (t + 1) * kTestTile);
+                if (can_saturate) {
+                    __syncthreads();                              // the tile's counts are complete
+                    int unsat = 0;
+                    for (int q = tid; q < nqs; q += kTestThreads) {
+                        const bool s = S.qcnt[q] >= kCap;
+                        S.qsat[q] = s;
+                        unsat |= !s;
                     }
-                    if (live && cnt) atomicAdd(&S.qcnt[qi], cnt);
+                    if (!__syncthreads_or(unsat)) {               // nobody needs later candidates
+                        if (t + 1 < ntiles) {                     // ... but tile t + 1 is already on its way: let it land
+                            mbar_wait(&S.full[buf ^ 1], (buf ? uses0 : uses1) & 1u);
+                            if (buf) uses0++; else uses1++;
+                        }
+                        break;
+                    }
+                } else {
+                    __syncthreads();                              // everyone is done with this buffer
                 }
-                __syncthreads();
-                built = Rhi;
-                int unsat = 0;
-                for (int t = tid; t < nqs; t += kDenseThreads) {
-                    const bool s = S.qcnt[t] >= kCap;
-                    S.qsat[t] = s;
-                    unsat |= !s;
-                }
-                if (!__syncthreads_or(unsat)) break;                  // nobody needs later candidates
             }
-            for (int t = tid; t < nqs; t += kDenseThreads) counts[qs + sg0 + t] = min(S.qcnt[t], kCap);
+            for (int q = tid; q < nqs; q += kTestThreads) counts[qs + sg0 + q] = min(S.qcnt[q], kCap);
             built_max = max(built_max, built);
             __syncthreads();
         }
@@ -725,7 +862,7 @@ extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs,
     PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
     const unsigned gsm = kNumSM * 8;
     { PG_KTIME("k_bq_neighbours", st);
-    k_bq_neighbours<<<kNumSM * PG_RESIDENT(k_bq_neighbours, 256, 0) * 2, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense, w.crange); }
+    k_bq_neighbours<<<kNumSM * PG_RESIDENT(k_bq_neighbours, 256, 0) * 2, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense); }
     k_bq_clear_tail<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n + 1);   // kc beyond nCells must scan as 0
     PG_TRY(scan_exclusive_i32(w.kc, w.cand_start, (int64_t)n + 1, w.scalars + 1, w.scan_tmp, st));
     k_bq_mask_sizes<<<gsm, 256, 0, st>>>(w.ccnt, w.kc, w.scalars, n + 1, w.mbase);
@@ -749,8 +886,8 @@ extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int
     if (!w.ok) { set_error("pg_ballquery_count: workspace too small (%zu < %zu)", ws_bytes, w.used); return PG_EWORKSPACE; }
     const uint32_t *sorted_pt = bq_sorted(w, n);
     const float r2 = radius * radius;
-    PG_CUDA(cudaFuncSetAttribute(k_bq_cells_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DenseSmem)));
-    PG_CUDA(cudaMemsetAsync(w.scalars + 4, 0, sizeof(int64_t), st));   // the dense kernel's work counter
+    PG_CUDA(cudaMemsetAsync(w.scalars + 4, 0, 2 * sizeof(int64_t), st));   // the dense kernels' work counters
+    PG_CUDA(cudaMemsetAsync(w.scalars + 7, 0, sizeof(int64_t), st));       // ... and the coordinate cursor
     // masks are used when they fit the caller's buffer (and int32 bases): decided on the device, reported below
     const int64_t mask_cap = masks ? (mask_words < 0x7fffffffLL ? mask_words : 0x7ffffffeLL) : -1;
     const int64_t gsmall_want = div_up(n, 8);
@@ -766,10 +903,13 @@ extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int
     { PG_KTIME("k_bq_cells_medium", st);
     kmedium<<<gmedium, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars, masks, mask_cap,
                                      r2, w.cand_idx, w.counts, w.kb); }
-    { PG_KTIME("k_bq_cells_dense", st);
-    k_bq_cells_dense<<<kNumSM * 4, kDenseThreads, sizeof(DenseSmem), st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc,
-                                                                            w.cand_start, w.mbase, w.dense, w.crange, w.scalars,
-                                                                            masks, mask_cap, r2, w.cand_idx, w.counts, w.kb); }
+    { PG_KTIME("k_bq_merge_dense", st);
+    k_bq_merge_dense<<<kNumSM * PG_RESIDENT(k_bq_merge_dense, kMergeThreads, 0), kMergeThreads, 0, st>>>(
+        xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.dense, w.scalars, w.cand_idx, w.cand_xy, w.cand_z, w.dbase); }
+    { PG_KTIME("k_bq_test_dense", st);
+    k_bq_test_dense<<<kNumSM * PG_RESIDENT(k_bq_test_dense, kTestThreads, 0), kTestThreads, 0, st>>>(
+        xyz, sorted_pt, w.cstart, w.ccnt, w.kc, w.mbase, w.dense, w.dbase, w.cand_xy, w.cand_z, w.scalars, masks, mask_cap, r2,
+        w.counts, w.kb); }
     // starts (reuse pslot) in query order, then the interleaved (start, len) rows per point
     PG_TRY(scan_exclusive_i32(w.counts, w.pslot, n, w.scalars + 2, w.scan_tmp, st));
     k_bq_start_len<<<(unsigned)div_up(n, 256), 256, 0, st>>>(sorted_pt, w.counts, w.pslot, n, (int2 *)start_len);

@@ -9,12 +9,18 @@ struct BqWs {
     int4 *keys;
     GroupTable tab;
     int32_t *pslot, *cell, *ccnt, *cstart, *kc, *kb, *cand_start, *counts, *nbr, *mbase, *dense;
-    uint2 *crange;      // dense cells: (smallest, largest) candidate index
+    int32_t *dbase;     // dense cells, by slot of `dense`: where the cell's candidate coordinates start in cand_xy / cand_z
     uint32_t *cand_idx;
+    // dense cells: candidate coordinates in merged (ascending index) order, laid out in PAIRS for the packed f32x2
+    // predicate and padded per cell to a multiple of 32 with +inf:  cand_xy[p] = (x0, x1, y0, y1), cand_z[p] = (z0, z1)
+    float4 *cand_xy;
+    float2 *cand_z;
+    size_t cand_cap;    // capacity of cand_xy / cand_z in candidates
     uint32_t *kA, *vA, *kB, *vB;
     int32_t *hist;
     int64_t *scan_tmp;
-    // [0] nCells [1] total candidates [2] total neighbours [3] nDense [4] dense work counter [6] mask words
+    // [0] nCells [1] total candidates [2] total neighbours [3] nDense [4] test work counter [5] merge work counter
+    // [6] mask words [7] cursor into cand_xy / cand_z
     int64_t *scalars;
     bool ok;
     size_t used;
@@ -38,7 +44,7 @@ inline BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
     w.counts = a.take<int32_t>(n + 1);
     w.nbr = a.take<int32_t>(n * 27);
     w.dense = a.take<int32_t>(n);
-    w.crange = a.take<uint2>(n);
+    w.dbase = a.take<int32_t>(n);
     w.kA = a.take<uint32_t>(n);
     w.vA = a.take<uint32_t>(n);
     w.kB = a.take<uint32_t>(n);
@@ -48,6 +54,11 @@ inline BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
     w.scalars = a.take<int64_t>(8);
     w.cand_idx = a.take<uint32_t>(n * 27);
     w.mbase = a.take<int32_t>(n + 1);
+    // a point is a candidate of at most 27 cells; a dense cell has more than 128 candidates, so at most 27 n / 129 cells
+    // are dense and padding each to a multiple of 32 adds at most 31 entries per dense cell: 27 n + 31 * 27 n / 129 < 34 n
+    w.cand_cap = n * 34 + 64;
+    w.cand_xy = a.take<float4>(w.cand_cap / 2);
+    w.cand_z = a.take<float2>(w.cand_cap / 2);
     w.ok = a.ok;
     w.used = a.used;
     return w;

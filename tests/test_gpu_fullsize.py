@@ -270,3 +270,17 @@ def test_config2_maskless_fill_matches(ops, full_batch):
         idx2 = torch.empty(total, dtype=torch.int32, device=idx.device)
         PG_OP.ballquery_fill_impl(shifted, 0.03, sl2, idx2, state)
         assert torch.equal(sl, sl2) and torch.equal(idx, idx2)
+
+
+def test_chain_two_stream_variant_is_identical(ops):
+    """chain.proposal_chain(overlap=True): the two clusterings issued from two host threads on two streams give the
+    same tensors as the sequential pass."""
+    nb = scenes.make_batch(3, 40_000, config_id=6, geometry_points=40_000)
+    batch = chain.batch_to_device(nb, torch.device("cuda"))
+    a = chain.proposal_chain(ops, batch)
+    for _ in range(3):
+        b = chain.proposal_chain(ops, batch, overlap=True)
+        torch.cuda.synchronize()
+        for k in ("proposals_idx", "proposals_offset", "proposals_score_feats", "ious", "proposals_center", "proposals_size"):
+            assert torch.equal(a[k], b[k]), k
+        assert a["nActive_shift"] == b["nActive_shift"] and a["nActive_raw"] == b["nActive_raw"]
