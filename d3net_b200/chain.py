@@ -185,12 +185,14 @@ def _side_streams(dev):
     return _streams[dev]
 
 
-def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=False, overlap=False):
+def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=False, overlap=True):
     """One pass of the hot path over one collated batch (all tensors on one CUDA device).
 
     batch: locs fp32 [N,3], locs_scaled int64 [N,4], feats fp32 [N,134], pt_feats fp32 [N,16],
     semantic_preds int64 [N], pt_offsets fp32 [N,3], instance_ids int64 [N], instance_pointnum int32
-    [nInst], n_scenes.  Returns a dict of the tensors the rest of the detector consumes."""
+    [nInst], n_scenes.  Returns a dict of the tensors the rest of the detector consumes.
+    ``overlap`` (CUDA only; ignored while a timer or a trace is attached): the two independent clusterings are issued
+    from two host threads on two streams -- scheduling only, the op calls and their results are the same."""
     timer = timer or _NoTimer()
     dev = batch["locs"].device
     B = int(batch["n_scenes"])
@@ -257,7 +259,7 @@ def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=Fa
     # The two clusterings (model/pointgroup.py:296-298 and :304-306) share their inputs and nothing else.  Each needs
     # the host twice (exact output sizes); issued from two host threads on two streams, one's kernels fill the other's
     # synchronisation bubbles and launch-bound stretches.  Same calls, same results -- scheduling only.
-    if overlap and coords_.is_cuda and timer.enabled is False:
+    if overlap and coords_.is_cuda and timer.enabled is False and trace is None:
         (proposals_idx_shift, proposals_offset_shift), (proposals_idx, proposals_offset) = _run_overlapped(
             cluster_shift, cluster_raw)
     else:
