@@ -56,8 +56,9 @@ WORKLOADS = {
        "of %d scenes of %dk points) with an NCCL all-gather of the packed proposal block",
     3: "configs[3]: the same chain on %d dense %dk-point scene(s) (one room, ~7.7 mm pitch: neighbour lists at the "
        "1000 cap on shifted coordinates, one giant floor component)",
-    4: "configs[4], detector half: the reference's own PointGroup.feed (model/pointgroup.py, unmodified, stand-in "
-       "backbone) with the new ops in the loop on %d synthetic %dk-point scenes, 256 proposals per scene",
+    4: "configs[4]: D3Net speaker forward -- the reference's own PointGroup.feed + SpeakerNet (model/pointgroup.py, "
+       "model/speaker.py, model/caption_module.py unmodified; stand-in backbone / graph module) with the new ops in the loop "
+       "on %d synthetic %dk-point scenes, 256 proposals per scene",
 }
 
 
@@ -409,6 +410,37 @@ def unchanged_caller_leg(n_scenes, points, reps=2):
             "proposals_kept_per_batch": int(out["proposal_batch_mask"].sum())}
 
 
+def speaker_leg(n_scenes, points, reps=2, chunk=8):
+    """BASELINE configs[4]: the reference's detector caller + its caption module (model/speaker.py,
+    model/caption_module.py, unmodified; graph module stood in for, harness/d3net_stub.py) with the ops in the loop."""
+    from harness import d3net_stub as H
+    if not H.available():
+        return {"unavailable": "baseline/_ref not staged (harness/stage_ref.py needs /root/reference)"}
+    H._installed.clear()
+    H.install_stubs(wrapper="d3net_b200")
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cfg = H.load_cfg(max_num_proposal=256)
+    det = H.build_detector(cfg, dev)
+    spk = H.build_speaker(cfg, dev)
+    nb = scenes.make_batch(n_scenes, points, config_id=2)
+    dd = H.collate(nb, dev)
+    lang = H.speaker_inputs(nb, cfg, dev, chunk=chunk)
+    out = H.run_speaker(det, spk, dd, lang)                               # warm-up
+    ms = wall_ms(lambda: H.run_speaker(det, spk, dd, lang), reps)
+    with H.OpTimer() as ot:
+        t0 = time.perf_counter()
+        out = H.run_speaker(det, spk, dd, lang)
+        torch.cuda.synchronize()
+        total_inst = (time.perf_counter() - t0) * 1e3
+    ops_ms = sum(ot.ms.values())
+    return {"value": n_scenes / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
+            "what": "PointGroup.feed + graph stand-in + SpeakerNet forward (teacher forcing, %d descriptions per scene, 256 "
+                    "proposals per scene), reference model files unmodified over d3net_b200.pointgroup_ops; wall clock" % chunk,
+            "ops_ms": round(ops_ms, 2), "ops_share": round(ops_ms / total_inst, 3),
+            "per_op_ms": {k: round(v, 2) for k, v in sorted(ot.ms.items(), key=lambda kv: -kv[1])},
+            "captions": list(out["lang_cap"].shape), "proposals_kept_per_batch": int(out["proposal_batch_mask"].sum())}
+
+
 def reference_mixed_leg(batch, rand6, reps=1):
     """What a D3Net user runs today on this GPU: the reference's own nine CUDA kernels + its two CPU ops, compiled from
     its sources (oracle/_ref), driven through the same chain."""
@@ -754,7 +786,8 @@ def run_config4(args, rank, world, local, emit=print):
     torch.cuda.set_device(local)
     sampler = ClockSampler(local)
     sampler.start()
-    r = unchanged_caller_leg(args.scenes, args.points, reps=max(args.steps, 1))
+    det = unchanged_caller_leg(args.scenes, args.points, reps=max(args.steps, 1))
+    r = speaker_leg(args.scenes, args.points, reps=max(args.steps, 1))
     clocks = sampler.stop()
     if "unavailable" in r:
         emit(json.dumps({"metric": METRIC, "unavailable": r["unavailable"], "config": {"workload": WORKLOADS[4] % (args.scenes, args.points // 1000)}}))
@@ -765,7 +798,7 @@ def run_config4(args, rank, world, local, emit=print):
             "config": {"workload": WORKLOADS[4] % (args.scenes, args.points // 1000), "max_num_proposal": 256},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                     "note": "wall clock of the whole caller; the batch is device-resident as Lightning leaves it"},
-            "ops_share": r["ops_share"], "detail": r, "clocks": clocks, "gpu_launches": None}
+            "ops_share": r["ops_share"], "speaker_forward": r, "detector_only": det, "clocks": clocks, "gpu_launches": None}
     emit(json.dumps(line))
 
 

@@ -169,6 +169,18 @@ def ops_module():
     return _installed["ops"]
 
 
+def use_ops(ops):
+    """Point `lib.pointgroup_ops.functions.pointgroup_ops` at another provider of the operator API (the tests run the
+    caller over the CPU oracle this way) and make the model files re-import against it."""
+    sys.modules["lib.pointgroup_ops.functions.pointgroup_ops"] = ops
+    pkg = sys.modules.get("lib.pointgroup_ops.functions")
+    if pkg is not None:
+        setattr(pkg, "pointgroup_ops", ops)
+    for m in [k for k in sys.modules if k in ("model.pointgroup", "model.speaker", "model.caption_module")]:
+        del sys.modules[m]
+    _installed["ops"] = ops
+
+
 # ---- configuration -----------------------------------------------------------------------------------------------------
 class Cfg(dict):
     """Attribute access over the yaml dicts (what the reference gets from omegaconf)."""
@@ -331,3 +343,72 @@ def run_feed(model, data_dict, epoch=1, seed=1234):
 def rand6_for(seed=1234):
     torch.manual_seed(seed)
     return torch.cat([torch.rand(3), torch.rand(3)])
+
+
+# ---- the speaker (BASELINE configs[4]) -------------------------------------------------------------------------------
+# model/speaker.py's SpeakerNet = GraphModule (torch_geometric, absent here) -> TopDownSceneCaptionModule.  The caption
+# module reads three tensors only the graph module writes (`bbox_feature`, `edge_feature`, `adjacent_mat`,
+# model/graph_module.py:315-318), so the reference itself cannot run with `num_graph_steps: 0`.  The graph module is one
+# more out-of-scope network: its stand-in below is a fixed linear lift of the detector's batched proposal features to the
+# caption module's feature size, no message passing.  The caption module runs unmodified.
+SPK_FEAT = 128
+
+
+def build_speaker(cfg, device, vocab_size=3433, seed=0):
+    install_stubs(_installed.get("wrapper", "d3net_b200"))
+    SpeakerNet = importlib.import_module("model.speaker").SpeakerNet
+    words = ["sos", "eos", "unk", "pad_"] + ["w%d" % i for i in range(vocab_size - 4)]
+    vocabulary = {"word2idx": {w: i for i, w in enumerate(words)}, "idx2word": {str(i): w for i, w in enumerate(words)}}
+    rng = np.random.default_rng(seed)
+    embeddings = rng.standard_normal((vocab_size, 300)).astype(np.float32)
+    cfg.model.no_captioning = False
+    cfg.model.no_detection = False
+    torch.manual_seed(seed)
+    spk = SpeakerNet(cfg, vocabulary, embeddings).to(device).eval()
+    g = torch.Generator().manual_seed(seed)
+    spk.graph_stand_in = (torch.randn((cfg.model.m, SPK_FEAT), generator=g) / cfg.model.m ** 0.5).to(device)
+    return spk
+
+
+def speaker_inputs(np_batch, cfg, device, chunk=8, seed=0, max_instances=128, vocab_size=3433):
+    """The language / ground-truth-box keys of a captioning batch (lib/dataset/pipeline.py), synthetic."""
+    B = int(np_batch["n_scenes"])
+    rng = np.random.default_rng(seed)
+    L = cfg.data.max_spk_len + 2
+    bidx = np_batch["locs_scaled"][:, 0]
+    inst = np_batch["instance_ids"]
+    gt = np.zeros((B, max_instances, 8, 3), np.float32)
+    ref_label = np.zeros((B, chunk, max_instances), np.float32)
+    ref_corner = np.zeros((B, chunk, 8, 3), np.float32)
+    signs = np.array([[sx, sy, sz] for sx in (1, -1) for sy in (1, -1) for sz in (1, -1)], np.float32)
+    for b in range(B):
+        sel = (bidx == b) & (inst >= 0)
+        ids = np.unique(inst[sel])[:max_instances]
+        for k, i in enumerate(ids):
+            p = np_batch["locs"][sel & (inst == i)]
+            lo, hi = p.min(0), p.max(0)
+            gt[b, k] = (lo + hi) / 2 + 0.5 * (hi - lo) * signs
+        pick = rng.integers(0, max(len(ids), 1), chunk)
+        ref_label[b, np.arange(chunk), pick] = 1
+        ref_corner[b] = gt[b, pick]
+    lens = rng.integers(6, cfg.data.max_spk_len, (B, chunk))
+    ids_ = rng.integers(4, vocab_size, (B, chunk, L))
+    ids_[:, :, 0] = 0                                                   # sos
+    d = {"annotated": np.ones((B, chunk), np.int64), "lang_ids": ids_.astype(np.int64), "lang_len": lens.astype(np.int64),
+         "ref_box_label": ref_label, "ref_box_corner_label": ref_corner, "gt_bbox": gt}
+    return {k: torch.from_numpy(v).to(device) for k, v in d.items()}
+
+
+def run_speaker(det, spk, data_dict, lang, epoch=1, seed=1234):
+    """Detector feed + graph stand-in + SpeakerNet forward (teacher forcing, as the captioning training step runs it,
+    model/pipeline.py:154-157)."""
+    torch.manual_seed(seed)
+    with torch.no_grad():
+        d = det.feed(dict(data_dict), epoch)
+        d.update(lang)
+        feats = d["proposal_feats_batched"]                              # [B, P, m]
+        B, P, _ = feats.shape
+        d["bbox_feature"] = feats @ spk.graph_stand_in
+        d["edge_feature"] = feats.new_zeros((B, P, spk.cfg.model.num_locals, SPK_FEAT))
+        d["adjacent_mat"] = feats.new_zeros((B, P, P))
+        return spk(d, use_tf=True, use_rl=False, is_eval=False)

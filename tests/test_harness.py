@@ -77,15 +77,11 @@ def test_real_caller_equals_chain_on_cpu_oracle(monkeypatch):
     ops = OracleOps(use_ref=True)
     H._installed.clear()
     H.install_stubs(wrapper="d3net_b200")
-    import sys
-    monkeypatch.setitem(sys.modules, "lib.pointgroup_ops.functions.pointgroup_ops", ops)
-    monkeypatch.setitem(H._installed, "ops", ops)
-    sys.modules.pop("model.pointgroup", None)
+    H.use_ops(ops)
     try:
         cfg, model, nb, out, mine, captured, dd = _run_both(ops, torch.device("cpu"), 2, 9000)
         _compare(cfg, out, mine, captured, nb, dd)
     finally:
-        sys.modules.pop("model.pointgroup", None)
         H._installed.clear()
 
 
@@ -102,5 +98,53 @@ def test_real_caller_on_gpu(wrapper):
         cfg, model, nb, out, mine, captured, dd = _run_both(ops, torch.device("cuda"), 2, 20000)
         _compare(cfg, out, mine, captured, nb, dd)
         assert not out["proposal_scores"][1].is_cuda            # bfs_cluster got CPU tensors and answered on the CPU
+    finally:
+        H._installed.clear()
+
+
+@needs_staged
+def test_speaker_forward_on_cpu_oracle(monkeypatch):
+    """BASELINE configs[4] end to end on the CPU: the reference's detector caller AND its caption module
+    (model/speaker.py, model/caption_module.py, unmodified) over the oracle ops -- the harness wiring check."""
+    import sys
+    from oracle.ops_adapter import OracleOps
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    ops = OracleOps(use_ref=True)
+    H._installed.clear()
+    H.install_stubs(wrapper="d3net_b200")
+    H.use_ops(ops)
+    try:
+        dev = torch.device("cpu")
+        cfg = H.load_cfg(max_num_proposal=64)
+        det = H.build_detector(cfg, dev)
+        spk = H.build_speaker(cfg, dev, vocab_size=300)
+        nb = scenes.make_batch(2, 9000, config_id=5, geometry_points=9000)
+        dd = H.collate(nb, dev)
+        lang = H.speaker_inputs(nb, cfg, dev, chunk=2, vocab_size=300)
+        out = H.run_speaker(det, spk, dd, lang)
+        caps = out["lang_cap"]
+        assert caps.shape[0] == 4 and caps.shape[2] == 300 and torch.isfinite(caps).all()
+        assert out["good_bbox_masks"].shape == (4,)
+    finally:
+        H._installed.clear()
+
+
+@needs_staged
+@pytest.mark.gpu
+def test_speaker_forward_on_gpu():
+    H._installed.clear()
+    H.install_stubs(wrapper="d3net_b200")
+    try:
+        dev = torch.device("cuda")
+        cfg = H.load_cfg(max_num_proposal=256)
+        det = H.build_detector(cfg, dev)
+        spk = H.build_speaker(cfg, dev)
+        nb = scenes.make_batch(2, 20000, config_id=5, geometry_points=20000)
+        dd = H.collate(nb, dev)
+        lang = H.speaker_inputs(nb, cfg, dev, chunk=4)
+        out = H.run_speaker(det, spk, dd, lang)
+        caps = out["lang_cap"]
+        assert caps.shape[0] == 8 and caps.is_cuda and torch.isfinite(caps).all()
+        assert int(out["proposal_batch_mask"].sum()) > 10
     finally:
         H._installed.clear()
