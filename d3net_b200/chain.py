@@ -328,3 +328,68 @@ def batch_to_device(np_batch, device, pt_feat_seed=0, pin=False):
     dev = {k: v.to(device, non_blocking=pin).contiguous() for k, v in host.items()}
     dev["n_scenes"] = np_batch["n_scenes"]
     return dev
+
+
+# ---- convert_stack_to_batch (model/pointgroup.py:223-263) without the per-scene Python loop ---------------------------------
+_BOX_SIGNS = ((1, 1, 1), (1, -1, 1), (-1, -1, 1), (-1, 1, 1), (1, 1, -1), (1, -1, -1), (-1, -1, -1), (-1, 1, -1))   # lib/utils/bbox.py:67-69
+
+
+def box_corners(center, size, heading=None):
+    """get_3d_box_batch (lib/utils/bbox.py:54-74) on the device, bit for bit: half extents in fp32, corners rotated and
+    translated in fp64 (numpy's promotion), the caller rounds to fp32.  The detector only ever passes heading 0
+    (proposal_crop_bbox[:, 6] is never written, model/pointgroup.py:355-361), where the rotation is the identity."""
+    signs = torch.tensor(_BOX_SIGNS, dtype=torch.float64, device=center.device)            # [8, 3]
+    half = (size.float() / 2).double()                                                      # l/2, w/2, h/2 as fp32 values
+    c = signs[None] * half[:, None, :]                                                      # [n, 8, 3]
+    if heading is not None and bool((heading != 0).any()):
+        t = heading.double()
+        cs, sn = torch.cos(t)[:, None], torch.sin(t)[:, None]
+        x, y, z = c[..., 0], c[..., 1], c[..., 2]
+        c = torch.stack([x * cs + z * sn, y, -x * sn + z * cs], -1)                         # corners @ roty(t)^T
+    return c + center.double()[:, None, :]
+
+
+def convert_stack_to_batch(proposals_batchId, proposal_feats, proposal_crop_bbox, proposal_objectness_scores, batch_size,
+                           max_num_proposal, perms=None):
+    """The six batched tensors of PointGroup.convert_stack_to_batch with IDENTICAL values, in a handful of device ops:
+    per scene the first ``max_num_proposal`` proposals (in stack order), zero padding, then the per-scene shuffle.
+    ``perms``: int64 [batch_size, max_num_proposal]; ``None`` draws ``torch.randperm(max_num_proposal)`` once per scene
+    from the CPU generator, exactly the draws (and their order) of model/pointgroup.py:250."""
+    dev, B, P = proposal_feats.device, int(batch_size), int(max_num_proposal)
+    n = proposal_feats.size(0)
+    if perms is None:
+        perms = torch.stack([torch.randperm(P) for _ in range(B)]) if B > 0 else torch.zeros((0, P), dtype=torch.long)
+    perms = perms.to(dev)
+    out = {
+        "proposal_feats_batched": torch.zeros((B, P, proposal_feats.size(1)), dtype=proposal_feats.dtype, device=dev),
+        "proposal_bbox_batched": torch.zeros((B, P, 8, 3), dtype=proposal_feats.dtype, device=dev),
+        "proposal_center_batched": torch.zeros((B, P, 3), dtype=proposal_feats.dtype, device=dev),
+        "proposal_sem_cls_batched": torch.zeros((B, P), dtype=proposal_feats.dtype, device=dev),
+        "proposal_scores_batched": torch.zeros((B, P), dtype=proposal_feats.dtype, device=dev),
+        "proposal_batch_mask": torch.zeros((B, P), dtype=proposal_feats.dtype, device=dev),
+    }
+    if n > 0 and B > 0:
+        bid = proposals_batchId.to(dev).long()
+        order = torch.argsort(bid, stable=True)                                      # scene by scene, stack order inside
+        sb = bid[order]
+        start = torch.searchsorted(sb, torch.arange(B, device=dev))
+        slot = torch.arange(n, device=dev) - start[sb]
+        keep = (slot < P) & (sb >= 0) & (sb < B)
+        src, b, s = order[keep], sb[keep], slot[keep]
+        crop = proposal_crop_bbox
+        corners = box_corners(crop[:, :3], crop[:, 3:6], crop[:, 6]).to(proposal_feats.dtype)
+        out["proposal_feats_batched"][b, s] = proposal_feats[src]
+        out["proposal_bbox_batched"][b, s] = corners[src]
+        out["proposal_center_batched"][b, s] = crop[src, :3]
+        out["proposal_sem_cls_batched"][b, s] = crop[src, 7]
+        out["proposal_scores_batched"][b, s] = proposal_objectness_scores[src]
+        out["proposal_batch_mask"][b, s] = 1
+    rows = torch.arange(B, device=dev)[:, None]
+    return {k: v[rows, perms] for k, v in out.items()}
+
+
+def proposals_npoint(proposals_offset):
+    """model/pointgroup.py:341-344 -- a Python loop of `(proposals_idx[:, 0] == i).sum()` over every proposal, O(nProposal
+    x sumNPoint) on the CPU (0.8 s of the reference's forward at 8 x 150k points) -- is the difference of the offsets."""
+    off = proposals_offset
+    return (off[1:] - off[:-1]).float()

@@ -66,6 +66,14 @@ def _compare(cfg, out, mine, captured, nb, dd):
         assert gain == 2.0 ** round(np.log2(gain))
         assert torch.equal(out["proposal_feats"].cpu(), mine["proposals_score_feats"].cpu()[mask] * gain)
     B, P = len(out["batch_offsets"]) - 1, cfg.model.max_num_proposal
+    # convert_stack_to_batch (model/pointgroup.py:223-263) vs the loop-free helper: identical tensors, the shuffle included
+    torch.manual_seed(1234)
+    torch.rand(3), torch.rand(3)                                  # the two draws of clusters_voxelization come first (:161)
+    mine_b = chain.convert_stack_to_batch(out["proposals_batchId"], out["proposal_feats"], out["proposal_crop_bbox"],
+                                          out["proposal_objectness_scores"], B, P)
+    for k, v in mine_b.items():
+        assert torch.equal(v.cpu(), out[k].cpu()), k
+    assert torch.equal(out["proposals_npoint"].cpu(), chain.proposals_npoint(proposals_offset).cpu())
     assert tuple(out["proposal_feats_batched"].shape) == (B, P, cfg.model.m)
     assert int(out["proposal_batch_mask"].sum()) == min(int(mask.sum()), int(out["proposal_batch_mask"].numel()))
 
@@ -146,5 +154,36 @@ def test_speaker_forward_on_gpu():
         caps = out["lang_cap"]
         assert caps.shape[0] == 8 and caps.is_cuda and torch.isfinite(caps).all()
         assert int(out["proposal_batch_mask"].sum()) > 10
+    finally:
+        H._installed.clear()
+
+
+@needs_staged
+@pytest.mark.parametrize("P", [4, 64])
+def test_convert_stack_to_batch_helper_matches_the_reference_method(P):
+    """The reference's own method on random stacks (truncation at max_num_proposal, empty scenes, unsorted scene ids)."""
+    H._installed.clear()
+    H.install_stubs(wrapper="d3net_b200")
+    try:
+        cfg = H.load_cfg(max_num_proposal=P, task="test")             # "test": skips the GT assignment (needs center_label)
+        det = H.build_detector(cfg, torch.device("cpu"))
+        g = torch.Generator().manual_seed(3)
+        n, B = 90, 5
+        bid = torch.randint(0, B, (n,), generator=g)
+        bid[bid == 3] = 2                                             # scene 3 has no proposals
+        dd = {"batch_offsets": torch.arange(B + 1), "proposals_batchId": bid.int(),
+              "proposal_feats": torch.randn((n, cfg.model.m), generator=g),
+              "proposal_crop_bbox": torch.cat([torch.randn((n, 3), generator=g), torch.rand((n, 3), generator=g) * 2,
+                                               torch.zeros(n, 1), torch.randint(0, 20, (n, 1), generator=g).float(),
+                                               torch.rand((n, 1), generator=g)], 1),
+              "proposal_objectness_scores": torch.rand(n, generator=g)}
+        torch.manual_seed(77)
+        ref = det.convert_stack_to_batch(dict(dd))
+        torch.manual_seed(77)
+        mine = chain.convert_stack_to_batch(dd["proposals_batchId"], dd["proposal_feats"], dd["proposal_crop_bbox"],
+                                            dd["proposal_objectness_scores"], B, P)
+        for k, v in mine.items():
+            assert torch.equal(v, ref[k]), k
+        assert int(mine["proposal_batch_mask"].sum()) == sum(min(int((bid == b).sum()), P) for b in range(B))
     finally:
         H._installed.clear()
