@@ -448,8 +448,10 @@ def reference_mixed_leg(batch, rand6, reps=1):
     ops = RefGpuOps()
     if ops.ref is None:
         return {"unavailable": "oracle/_ref/PG_OP.so was not built"}
-    chain.proposal_chain(ops, batch, rand6)
-    ms = wall_ms(lambda: chain.proposal_chain(ops, batch, rand6), reps)
+    # one thread, one stream: the reference's bfs_cluster keeps a 4-byte-per-point array on the stack (bfs_cluster.cpp:61),
+    # more than a worker thread's stack holds at a million points
+    chain.proposal_chain(ops, batch, rand6, overlap=False)
+    ms = wall_ms(lambda: chain.proposal_chain(ops, batch, rand6, overlap=False), reps)
     return {"value": int(batch["n_scenes"]) / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
             "what": "oracle/_ref = the reference's lib/pointgroup_ops compiled unmodified for sm_100a: brute-force "
                     "ballquery_batch_p and the other eight kernels on this GPU, voxelize_idx / bfs_cluster on one CPU "
