@@ -6,8 +6,9 @@
 //   prepare
 //     1. cell key per point: (scene, floor(x/s), floor(y/s), floor(z/s)), s = 1.0001 * |r| in fp64, so
 //        every pair that can pass the predicate sits in adjacent cells;
-//     2. hash-group the keys -> dense cell ids; stable radix sort of (cell, point) -> every cell's
-//        point list in ASCENDING original index; the sorted order is also the QUERY order;
+//     2. hash-group the keys -> dense cell ids; a counting scatter puts every cell's points side by side (in no
+//        particular order inside a cell: the count kernels order the candidates themselves); that order is also the
+//        QUERY order;
 //     3. per cell: its 27 neighbour cells (hash lookups), K = size of its candidate set, and the
 //        cell's class: K <= kSmallK "sparse" (one warp), otherwise "dense" (one block);
 //   count -- one pass over the cells, each cell builds its candidate set ONCE, merged in ascending
@@ -60,13 +61,26 @@ __global__ void k_bq_keys(const float *__restrict__ xyz, const int32_t *__restri
     keys[i] = make_int4(__ldg(batch_idxs + i), cell_coord(x, inv_s), cell_coord(y, inv_s), cell_coord(z, inv_s));
 }
 
+// points side by side per cell: slot claimed from the cell's cursor; the cell's smallest / largest point index on the way
+__global__ void k_bq_scatter(const int32_t *__restrict__ cell, const int32_t *__restrict__ cstart, int32_t n,
+                             int32_t *cursor, uint32_t *__restrict__ sorted_pt, uint32_t *cmin, uint32_t *cmax) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int c = __ldg(cell + i);
+    sorted_pt[__ldg(cstart + c) + atomicAdd(cursor + c, 1)] = (uint32_t)i;
+    if (cmin[c] > (uint32_t)i) atomicMin(cmin + c, (uint32_t)i);
+    if (cmax[c] < (uint32_t)i) atomicMax(cmax + c, (uint32_t)i);
+}
+
 // one warp per cell: lane j < 27 looks up neighbour j (-1 when absent; slot 13 is the cell itself),
 // the warp sums the candidate count and files dense cells in the (unordered) dense list
 __global__ void __launch_bounds__(256) k_bq_neighbours(const int4 *__restrict__ keys, GroupTable tab,
                                                        const uint32_t *__restrict__ sorted_pt,
                                                        const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
                                                        int64_t *scalars, int32_t *__restrict__ nbr,
-                                                       int32_t *__restrict__ kc, int32_t *__restrict__ dense) {
+                                                       int32_t *__restrict__ kc, int32_t *__restrict__ dense,
+                                                       const uint32_t *__restrict__ cmin, const uint32_t *__restrict__ cmax,
+                                                       uint2 *__restrict__ crange) {
     const int64_t nc = scalars[0];
     const int lane = threadIdx.x & 31;
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -90,6 +104,16 @@ __global__ void __launch_bounds__(256) k_bq_neighbours(const int4 *__restrict__ 
         if (lane == 0) {
             kc[c] = cnt;
             if (bq_is_dense(cnt, ccnt[c])) dense[atomicAdd((unsigned long long *)&scalars[3], 1ULL)] = (int32_t)c;
+        }
+        if (bq_is_dense(cnt, ccnt[c])) {          // a dense cell: the index range of its candidates
+            uint32_t head = 0xffffffffu, tail = 0u;
+            if (id >= 0) { head = __ldg(cmin + id); tail = __ldg(cmax + id); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                head = min(head, __shfl_xor_sync(0xffffffffu, head, o));
+                tail = max(tail, __shfl_xor_sync(0xffffffffu, tail, o));
+            }
+            if (lane == 0) crange[c] = make_uint2(head, tail);
         }
     }
 }
@@ -291,10 +315,10 @@ constexpr int kTestQ = 256;                // queries of one cell handled per pa
 struct MergeSmem {
     uint32_t bm[kWinWords];          // rank bitmap over the index window [s0, s0 + kWinBits)
     const uint32_t *lptr[27];
-    int32_t llen[27], la[27], lb[27];
+    int32_t llen[27];
     int32_t wsum[kMergeThreads / 32];
-    uint32_t s0, more;
-    int32_t tw, cellslot;
+    uint32_t lo, hi;
+    int32_t cellslot;
     long long cb;
 };
 
@@ -305,8 +329,9 @@ struct MergeSmem {
 __global__ void __launch_bounds__(kMergeThreads) k_bq_merge_dense(
     const float *__restrict__ xyz, const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cstart,
     const int32_t *__restrict__ ccnt, const int32_t *__restrict__ nbr, const int32_t *__restrict__ kc,
-    const int32_t *__restrict__ cand_start, const int32_t *__restrict__ dense, int64_t *scalars,
-    uint32_t *cand_idx, float4 *__restrict__ cand_xy, float2 *__restrict__ cand_z, int32_t *__restrict__ dbase) {
+    const int32_t *__restrict__ cand_start, const int32_t *__restrict__ dense, const uint2 *__restrict__ crange,
+    int64_t *scalars, uint32_t *cand_idx, float4 *__restrict__ cand_xy, float2 *__restrict__ cand_z,
+    int32_t *__restrict__ dbase) {
     __shared__ __align__(16) MergeSmem S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nDense = scalars[3];
@@ -330,9 +355,11 @@ __global__ void __launch_bounds__(kMergeThreads) k_bq_merge_dense(
                 if (src >= 0) { len = __ldg(ccnt + src); L = sorted_pt + __ldg(cstart + src); }
                 S.lptr[lane] = L;
                 S.llen[lane] = len;
-                S.la[lane] = 0;
             }
             if (lane == 0) {                                     // where this cell's coordinates go (a multiple of 32)
+                const uint2 rg = __ldg(crange + c);
+                S.lo = rg.x;
+                S.hi = rg.y;
                 const long long cb = (long long)atomicAdd((unsigned long long *)&scalars[7], (unsigned long long)Kpad);
                 dbase[slot] = (int32_t)(uint32_t)cb;             // < 34 * 2^26 < 2^32
                 S.cb = cb;
@@ -341,39 +368,24 @@ __global__ void __launch_bounds__(kMergeThreads) k_bq_merge_dense(
         __syncthreads();
         const long long cb = S.cb;
         int rank_base = 0;                                       // candidates emitted by earlier windows
-        for (;;) {
-            // ---- next window: starts at the smallest unconsumed element of the 27 lists
-            if (warp == 0) {
-                uint32_t nxt = 0xffffffffu;
-                int a = 0, len = 0;
-                const uint32_t *L = nullptr;
-                if (lane < 27) {
-                    a = S.la[lane]; len = S.llen[lane]; L = S.lptr[lane];
-                    if (a < len) nxt = __ldg(L + a);
-                }
-                const uint32_t mn = warp_min_u32(nxt);
-                const uint32_t s0 = mn & ~31u;
-                int bnd = len;
-                if (lane < 27 && a < len && __ldg(L + len - 1) - s0 >= (uint32_t)kWinBits)
-                    bnd = a + lower_bound_u32(L + a, len - a, s0 + (uint32_t)kWinBits);
-                if (lane < 27) S.lb[lane] = bnd;
-                const unsigned more = __ballot_sync(0xffffffffu, lane < 27 && bnd < len);
-                if (lane == 0) { S.s0 = s0; S.more = more; }
-            }
+        // windows of kWinBits indices over [lo, hi] (one, unless a scene holds more than 160k points).  The lists are in
+        // no particular order: a window takes the entries that fall into it.
+        const uint32_t hi = S.hi;
+        const bool one_window = hi - (S.lo & ~31u) < (uint32_t)kWinBits;
+        for (uint32_t s0 = S.lo & ~31u;; s0 += (uint32_t)kWinBits) {
             // the bitmap is all zero here (cleared below by the threads that walked it)
-            if (rank_base == 0) {
+            if (rank_base == 0 && s0 == (S.lo & ~31u)) {
                 uint4 *z = reinterpret_cast<uint4 *>(S.bm + tid * kWordsPerThread);
 #pragma unroll
                 for (int k = 0; k < kWordsPerThread / 4; k++) z[k] = make_uint4(0u, 0u, 0u, 0u);
+                __syncthreads();
             }
-            __syncthreads();
-            const uint32_t s0 = S.s0;
             for (int j = warp; j < 27; j += kMergeThreads / 32) {
                 const uint32_t *L = S.lptr[j];
-                const int b1 = S.lb[j];
-                for (int t = S.la[j] + lane; t < b1; t += 32) {
+                const int b1 = S.llen[j];
+                for (int t = lane; t < b1; t += 32) {
                     const uint32_t v = __ldg(L + t) - s0;
-                    atomicOr(&S.bm[v >> 5], 1u << (v & 31u));
+                    if (one_window || v < (uint32_t)kWinBits) atomicOr(&S.bm[v >> 5], 1u << (v & 31u));
                 }
             }
             __syncthreads();
@@ -420,7 +432,6 @@ __global__ void __launch_bounds__(kMergeThreads) k_bq_merge_dense(
                     run[k] = make_uint4(0u, 0u, 0u, 0u);
                 }
             }
-            if (tid < 27) S.la[tid] = S.lb[tid];
             __syncthreads();                                     // the window's indices are in cand_idx (same block: visible)
             // ---- coordinates, lane-dense
             for (int e = tid; e < tw; e += kMergeThreads) {
@@ -435,8 +446,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_bq_merge_dense(
                 z_f[q] = z;
             }
             rank_base += tw;
-            if (S.more == 0u) break;                             // (read before anyone can rewrite it: the next write
-            __syncthreads();                                     //  follows this barrier)
+            if (hi - s0 < (uint32_t)kWinBits) break;             // the window held the largest index
         }
         // padding up to a multiple of 32: +inf never passes the predicate
         if (tid < Kpad - K) {
@@ -852,17 +862,16 @@ extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs,
     PG_CUDA(cudaMemsetAsync(w.scalars, 0, 8 * sizeof(int64_t), st));
     k_bq_keys<<<(unsigned)div_up(n, 256), 256, 0, st>>>(xyz, batch_idxs, n, inv_s, w.keys);
     PG_TRY(group_int4(w.keys, n, w.tab, w.pslot, w.cell, w.ccnt, w.scalars, w.scan_tmp, st));
-    int bits = 0;
-    while ((1ll << bits) < (long long)n) bits++;
-    int res = 0;
-    PG_TRY(radix_sort_pairs(reinterpret_cast<const uint32_t *>(w.cell), nullptr, w.kA, w.vA, w.kB, w.vB, n, bits,
-                            w.hist, w.scan_tmp, st, &res));
-    const uint32_t *sorted_pt = res == 0 ? w.vA : w.vB;
     PG_CUDA(cudaMemsetAsync(w.ccnt + n, 0, sizeof(int32_t), st));
     PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
+    uint32_t *sorted_pt = w.vA, *cmin = w.kA, *cmax = w.kB;
+    PG_CUDA(cudaMemsetAsync(w.kb, 0, (size_t)n * sizeof(int32_t), st));          // the cells' cursors (kb is rewritten by count)
+    PG_CUDA(cudaMemsetAsync(cmin, 0xff, (size_t)n * sizeof(uint32_t), st));
+    PG_CUDA(cudaMemsetAsync(cmax, 0, (size_t)n * sizeof(uint32_t), st));
+    k_bq_scatter<<<(unsigned)div_up(n, 256), 256, 0, st>>>(w.cell, w.cstart, n, w.kb, sorted_pt, cmin, cmax);
     const unsigned gsm = kNumSM * 8;
     { PG_KTIME("k_bq_neighbours", st);
-    k_bq_neighbours<<<kNumSM * PG_RESIDENT(k_bq_neighbours, 256, 0) * 2, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense); }
+    k_bq_neighbours<<<kNumSM * PG_RESIDENT(k_bq_neighbours, 256, 0) * 2, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense, cmin, cmax, w.crange); }
     k_bq_clear_tail<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n + 1);   // kc beyond nCells must scan as 0
     PG_TRY(scan_exclusive_i32(w.kc, w.cand_start, (int64_t)n + 1, w.scalars + 1, w.scan_tmp, st));
     k_bq_mask_sizes<<<gsm, 256, 0, st>>>(w.ccnt, w.kc, w.scalars, n + 1, w.mbase);
@@ -905,7 +914,7 @@ extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int
                                      r2, w.cand_idx, w.counts, w.kb); }
     { PG_KTIME("k_bq_merge_dense", st);
     k_bq_merge_dense<<<kNumSM * PG_RESIDENT(k_bq_merge_dense, kMergeThreads, 0), kMergeThreads, 0, st>>>(
-        xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.dense, w.scalars, w.cand_idx, w.cand_xy, w.cand_z, w.dbase); }
+        xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.dense, w.crange, w.scalars, w.cand_idx, w.cand_xy, w.cand_z, w.dbase); }
     { PG_KTIME("k_bq_test_dense", st);
     k_bq_test_dense<<<kNumSM * PG_RESIDENT(k_bq_test_dense, kTestThreads, 0), kTestThreads, 0, st>>>(
         xyz, sorted_pt, w.cstart, w.ccnt, w.kc, w.mbase, w.dense, w.dbase, w.cand_xy, w.cand_z, w.scalars, masks, mask_cap, r2,

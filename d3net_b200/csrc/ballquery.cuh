@@ -10,6 +10,7 @@ struct BqWs {
     GroupTable tab;
     int32_t *pslot, *cell, *ccnt, *cstart, *kc, *kb, *cand_start, *counts, *nbr, *mbase, *dense;
     int32_t *dbase;     // dense cells, by slot of `dense`: where the cell's candidate coordinates start in cand_xy / cand_z
+    uint2 *crange;      // dense cells: (smallest, largest) candidate index
     uint32_t *cand_idx;
     // dense cells: candidate coordinates in merged (ascending index) order, laid out in PAIRS for the packed f32x2
     // predicate and padded per cell to a multiple of 32 with +inf:  cand_xy[p] = (x0, x1, y0, y1), cand_z[p] = (z0, z1)
@@ -45,6 +46,7 @@ inline BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
     w.nbr = a.take<int32_t>(n * 27);
     w.dense = a.take<int32_t>(n);
     w.dbase = a.take<int32_t>(n);
+    w.crange = a.take<uint2>(n);
     w.kA = a.take<uint32_t>(n);
     w.vA = a.take<uint32_t>(n);
     w.kB = a.take<uint32_t>(n);
@@ -64,12 +66,8 @@ inline BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
     return w;
 }
 
-// ping-pong parity of the radix sort (prepare / count / fill must agree on where sorted_pt landed)
-inline const uint32_t *bq_sorted(const BqWs &w, int32_t n) {
-    int bits = 0;
-    while ((1ll << bits) < (long long)n) bits++;
-    const int passes = (bits + 7) / 8 < 1 ? 1 : (bits + 7) / 8;
-    return (passes & 1) ? w.vA : w.vB;
-}
+// the points grouped by cell (cell c: sorted_pt[cstart[c] .. cstart[c] + ccnt[c]), in no particular order inside a cell);
+// this is also the QUERY order.  kA / kB hold the smallest / largest point index of every cell.
+inline const uint32_t *bq_sorted(const BqWs &w, int32_t) { return w.vA; }
 
 }  // namespace pg

@@ -264,12 +264,20 @@ def test_config2_maskless_fill_matches(ops, full_batch):
     bo = chain.get_batch_offsets(bi, 8)
     shifted = (batch["locs"][obj] + batch["pt_offsets"][obj]).contiguous()
     idx, sl = ops.ballquery_batch_p(shifted, bi, bo, 0.03, 300)
+
+    def relaid(idx_, sl_):                       # every point's list, re-laid out in point order (placement is free)
+        lens = sl_[:, 1].long()
+        owner = torch.repeat_interleave(torch.arange(lens.numel(), device=idx_.device), lens)
+        pos = torch.arange(owner.numel(), device=idx_.device) - (torch.cumsum(lens, 0) - lens)[owner]
+        return idx_[sl_[:, 0].long()[owner] + pos]
+
+    want = relaid(idx, sl)
     for kw in ({"use_masks": False}, {"mask_words": 1 << 20}):                 # no buffer / a buffer that is too small
         sl2, total, state = PG_OP.ballquery_count_impl(shifted, bi, bo, 0.03, **kw)
         assert state[1] is None and total == idx.numel()
         idx2 = torch.empty(total, dtype=torch.int32, device=idx.device)
         PG_OP.ballquery_fill_impl(shifted, 0.03, sl2, idx2, state)
-        assert torch.equal(sl, sl2) and torch.equal(idx, idx2)
+        assert torch.equal(sl[:, 1], sl2[:, 1]) and torch.equal(want, relaid(idx2, sl2))
 
 
 def test_chain_two_stream_variant_is_identical(ops):

@@ -57,3 +57,12 @@ def assert_same_floats(a, b):
     na, nb = np.isnan(a), np.isnan(b)
     np.testing.assert_array_equal(na, nb)
     np.testing.assert_array_equal(a.view(np.uint32)[~na], b.view(np.uint32)[~nb])
+
+
+def relaid_on_device(idx, sl):
+    """Every point's neighbour list re-laid out in point order (torch, on the device): where a producer puts the
+    segments inside ``idx`` is its own choice (the reference places them by atomicAdd, bfs_cluster.cu:47)."""
+    lens = sl[:, 1].long()
+    owner = torch.repeat_interleave(torch.arange(lens.numel(), device=idx.device), lens)
+    pos = torch.arange(owner.numel(), device=idx.device) - (torch.cumsum(lens, 0) - lens)[owner]
+    return idx[sl[:, 0].long()[owner] + pos]
