@@ -61,6 +61,49 @@ __global__ void k_max_i32(const int32_t *__restrict__ v, const int64_t *__restri
     if ((threadIdx.x & 31) == 0 && m > 0) atomicMax((unsigned long long *)out, (unsigned long long)m);
 }
 
+constexpr int kVoxRankMax = 32;        // largest voxel (points) served by the sort-free fill: a thread per point counts
+                                       // its voxel's segment, so long segments (cluster grids: hundreds of points per voxel,
+                                       // different ones in every lane) diverge and scatter -- those keep the sort
+
+// The points of every voxel side by side (voxel v: grouped[voff[v] .. voff[v] + cnt[v]), in claim order).
+__global__ void k_vox_scatter(const int32_t *__restrict__ input_map, const int32_t *__restrict__ voff, int64_t N,
+                              int32_t *cursor, uint32_t *__restrict__ grouped) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int v = __ldg(input_map + i);
+    grouped[__ldg(voff + v) + atomicAdd(cursor + v, 1)] = (uint32_t)i;
+}
+
+// output_map rows [cnt, p0 < p1 < ..., 0-pad] (voxelize.cpp:139-149; modes 0/1/2: :121-138) without a sort: a point's
+// column is its RANK among the points of its voxel (how many of them have a smaller index), counted against the voxel's
+// segment of `grouped` -- voxels hold one or two points on a scene grid and tens to hundreds on a cluster grid, and the
+// segment is contiguous, so the count runs out of L1.  The map was zero-filled; the rank-0 (mode 2: last) point also
+// writes the voxel's row of output_coords (voxelize.cpp:39-47) and the count column.
+__global__ void __launch_bounds__(256) k_vox_rank(const int64_t *__restrict__ coords, const int32_t *__restrict__ input_map,
+                                                  const int32_t *__restrict__ cnt, const int32_t *__restrict__ voff,
+                                                  const uint32_t *__restrict__ grouped, int64_t N, int32_t W, int mode,
+                                                  int64_t *__restrict__ out_coords, int32_t *__restrict__ out_map) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const int v = __ldg(input_map + i);
+    const int n = __ldg(cnt + v);
+    const uint32_t *seg = grouped + __ldg(voff + v);
+    int rank = 0;
+    for (int t = 0; t < n; t++) rank += (__ldg(seg + t) < (uint32_t)i) ? 1 : 0;
+    int32_t *row = out_map + (int64_t)v * W;
+    const bool listed = mode == 3 || mode == 4;
+    if (listed) row[1 + rank] = (int32_t)i;
+    const bool rep = mode == 2 ? rank == n - 1 : rank == 0;           // the point whose coordinates name the voxel
+    if (rep) {
+        row[0] = listed ? n : 1;
+        if (!listed) row[1] = (int32_t)i;
+        const longlong2 *p = reinterpret_cast<const longlong2 *>(coords) + i * 2;
+        longlong2 *q = reinterpret_cast<longlong2 *>(out_coords) + (int64_t)v * 2;
+        q[0] = __ldg(p);
+        q[1] = __ldg(p + 1);
+    }
+}
+
 // flat index -> (row, column): a 32-bit division when the index fits (the 64-bit one is a ~80-instruction
 // subroutine, and these kernels do little else per element)
 __device__ __forceinline__ void row_col(int64_t t, int32_t width, int64_t &row, int &col) {
@@ -358,14 +401,26 @@ extern "C" int pg_voxelize_idx_fill(const int64_t *coords, const int32_t *input_
     PG_CHECK_ARG(coords && input_map && ws && output_coords && output_map, "null pointer");
     VoxWs w = vox_layout(ws, ws_bytes, N);
     if (!w.ok) { set_error("pg_voxelize_idx_fill: workspace too small"); return PG_EWORKSPACE; }
+    PG_TRY(scan_exclusive_i32(w.cnt, w.voff, M, nullptr, w.scan_tmp, st));
+    const int W = maxActive + 1;
+    if (maxActive <= kVoxRankMax) {
+        // no sort: points side by side per voxel, then every point finds its column by counting (see k_vox_rank)
+        int32_t *cursor = reinterpret_cast<int32_t *>(w.kA);
+        PG_CUDA(cudaMemsetAsync(cursor, 0, (size_t)M * sizeof(int32_t), st));
+        PG_CUDA(cudaMemsetAsync(output_map, 0, (size_t)M * W * sizeof(int32_t), st));           // the rows' zero padding
+        k_vox_scatter<<<(unsigned)div_up(N, 256), 256, 0, st>>>(input_map, w.voff, N, cursor, w.vA);
+        PG_KTIME("k_vox_rank", st);
+        k_vox_rank<<<(unsigned)div_up(N, 256), 256, 0, st>>>(coords, input_map, w.cnt, w.voff, w.vA, N, W, mode, output_coords, output_map);
+        PG_LAUNCH_CHECK();
+        return PG_OK;
+    }
+    // voxels with thousands of points (the counting pass is quadratic in the voxel's size): stable sort of
+    // (voxel id, point) by voxel id -- points end up ascending inside every voxel -- and a coalesced fill
     int bits = 0;
     while ((1ll << bits) < (long long)M) bits++;
     int res = 0;
-    // stable sort of (voxel id, point) by voxel id: points end up ascending inside every voxel
     PG_TRY(radix_sort_pairs(reinterpret_cast<const uint32_t *>(input_map), nullptr, w.kA, w.vA, w.kB, w.vB, N, bits, w.hist, w.scan_tmp, st, &res));
     const uint32_t *sorted = res == 0 ? w.vA : w.vB;
-    PG_TRY(scan_exclusive_i32(w.cnt, w.voff, M, nullptr, w.scan_tmp, st));
-    const int W = maxActive + 1;
     const int64_t total = (int64_t)M * W;
     const bool vec = ((uintptr_t)output_map & 15u) == 0;
     const int64_t units = vec ? (total >> 2 > (int64_t)M * 4 ? total >> 2 : (int64_t)M * 4) : total;
