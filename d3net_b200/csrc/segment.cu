@@ -277,37 +277,47 @@ __global__ void k_sec_mean_wide(const float *__restrict__ inp, const int32_t *__
 }
 
 // =================================================================================================
-// get_iou: one block per proposal builds the histogram of its points' instance labels in shared
-// memory (one pass over the proposal instead of one pass per instance, get_iou.cu:19-25), then
-// every thread finishes some instances with the reference's mixed fp32/fp64 formula (:26).
+// get_iou: the intersection counts are a sparse histogram over (proposal, instance) -- one pass over the proposals' points
+// (the reference rescans every proposal once per instance, get_iou.cu:19-25).  Work is cut by ROWS, not by proposals, so
+// the floor-sized proposal is spread over the whole grid; a warp merges equal (proposal, instance) keys before it touches
+// memory (a proposal's points mostly carry one instance).  The counts are accumulated as int32 in the output buffer
+// itself (same 4 bytes per entry) and turned into IoUs in place with the reference's mixed fp32/fp64 formula (:26).
 // =================================================================================================
-constexpr int kIouBins = 8192;
-
-__global__ void __launch_bounds__(256) k_get_iou(const int32_t *__restrict__ pidx, const int32_t *__restrict__ poff,
-                                                 const int64_t *__restrict__ labels, const int32_t *__restrict__ pointnum,
-                                                 float *__restrict__ iou, int32_t nInst, int32_t nP) {
-    __shared__ int hist[kIouBins];
-    for (int p = blockIdx.x; p < nP; p += gridDim.x) {
-        const int start = __ldg(poff + p), end = __ldg(poff + p + 1);
-        const int ptotal = end - start;
-        for (int g0 = 0; g0 < nInst; g0 += kIouBins) {
-            const int nb = min(kIouBins, nInst - g0);
-            for (int g = threadIdx.x; g < nb; g += blockDim.x) hist[g] = 0;
-            __syncthreads();
-            for (int i = start + threadIdx.x; i < end; i += blockDim.x) {
-                const int l = (int)__ldg(labels + __ldg(pidx + i)) - g0;   // (int) narrowing as in :22
-                if (l >= 0 && l < nb) atomicAdd(&hist[l], 1);
+__global__ void __launch_bounds__(256) k_iou_count(const int32_t *__restrict__ pidx, const int32_t *__restrict__ poff,
+                                                   const int64_t *__restrict__ labels, int32_t *counts, int32_t nInst,
+                                                   int32_t nP) {
+    const int S = __ldg(poff + nP);                                   // rows of proposals_idx (known on the device only)
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x + (threadIdx.x - lane); base < S; base += stride) {   // warp-uniform trips
+        const int64_t i = base + lane;
+        long long key = -1;
+        if (i < S) {
+            const int l = (int)__ldg(labels + __ldg(pidx + i));        // (int) narrowing as in :22
+            if (l >= 0 && l < nInst) {
+                int lo = 0, hi = nP;                                  // the proposal that owns row i: poff[p] <= i < poff[p + 1]
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (__ldg(poff + mid) <= (int)i) lo = mid; else hi = mid;
+                }
+                key = (long long)lo * nInst + l;
             }
-            __syncthreads();
-            for (int g = threadIdx.x; g < nb; g += blockDim.x) {
-                const int inter = hist[g];
-                const int itotal = __ldg(pointnum + g0 + g);
-                const double den = (double)(float)(ptotal + itotal - inter) + 1e-5;
-                iou[(int64_t)p * nInst + g0 + g] = (float)((double)(float)inter / den);
-            }
-            __syncthreads();
         }
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key >= 0 && (peers & lanemask_lt()) == 0) atomicAdd(counts + key, __popc(peers));
     }
+}
+
+__global__ void __launch_bounds__(256) k_iou_final(const int32_t *__restrict__ poff, const int32_t *__restrict__ pointnum,
+                                                   float *iou, int32_t nInst, int64_t total) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int p = (int)(t / nInst), g = (int)(t - (int64_t)p * nInst);
+    const int inter = reinterpret_cast<const int32_t *>(iou)[t];
+    const int ptotal = __ldg(poff + p + 1) - __ldg(poff + p);
+    const int itotal = __ldg(pointnum + g);
+    const double den = (double)(float)(ptotal + itotal - inter) + 1e-5;
+    iou[t] = (float)((double)(float)inter / den);
 }
 
 }  // namespace pg
@@ -376,9 +386,14 @@ extern "C" int pg_get_iou(const int32_t *proposals_idx, const int32_t *proposals
     PG_CHECK_ARG(nInstance >= 0 && nProposal >= 0, "negative size");
     if ((int64_t)nInstance * nProposal == 0) return PG_OK;
     PG_CHECK_ARG(proposals_offset && instance_pointnum && proposals_iou, "null pointer");
-    const unsigned grid = (unsigned)(nProposal < kNumSM * 16 ? nProposal : kNumSM * 16);
-    k_get_iou<<<grid, 256, 0, (cudaStream_t)stream>>>(proposals_idx, proposals_offset, instance_labels,
-                                                      instance_pointnum, proposals_iou, nInstance, nProposal);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t total = (int64_t)nInstance * nProposal;
+    PG_CHECK_ARG(proposals_idx && instance_labels, "null pointer");
+    PG_CUDA(cudaMemsetAsync(proposals_iou, 0, (size_t)total * sizeof(float), st));
+    { PG_KTIME("k_iou_count", st);
+    k_iou_count<<<kNumSM * 8, 256, 0, st>>>(proposals_idx, proposals_offset, instance_labels,
+                                           reinterpret_cast<int32_t *>(proposals_iou), nInstance, nProposal); }
+    k_iou_final<<<(unsigned)div_up(total, 256), 256, 0, st>>>(proposals_offset, instance_pointnum, proposals_iou, nInstance, total);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }
