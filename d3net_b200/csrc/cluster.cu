@@ -561,7 +561,10 @@ __global__ void k_cl_pending(const int2 *__restrict__ pend, unsigned long long n
 // instead of twice.  More than kPendBlockMax parked edges: raise scalars[10]; the host reruns the two-sync path.
 constexpr unsigned long long kPendBlockMax = 4096;
 
-__global__ void __launch_bounds__(1024) k_cl_pending_block(const int2 *__restrict__ pend, unsigned long long pend_cap,
+// FIND: the forest has not been flattened since the sweep (trusted path): the ends' roots come from uf_find (no unions
+// run any more, so concurrent path halving only shortens paths) and are written back into the parked pair.
+template <bool FIND>
+__global__ void __launch_bounds__(1024) k_cl_pending_block(int2 *pend, unsigned long long pend_cap, uint2 *pl,
                                                            const int32_t *__restrict__ root, int32_t *lab,
                                                            unsigned long long *scalars) {
     const unsigned long long n_pend = scalars[2];
@@ -571,13 +574,25 @@ __global__ void __launch_bounds__(1024) k_cl_pending_block(const int2 *__restric
         return;
     }
     __shared__ int s_changed;
+    if (FIND) {
+        for (unsigned long long t = threadIdx.x; t < n_pend; t += blockDim.x) {
+            const int2 e = pend[t];
+            pend[t] = make_int2(uf_find(pl, e.x), uf_find(pl, e.y));
+        }
+        __syncthreads();
+    }
     for (int it = 0; it < (1 << 24); it++) {
         if (threadIdx.x == 0) s_changed = 0;
         __syncthreads();
         bool changed = false;
         for (unsigned long long t = threadIdx.x; t < n_pend; t += blockDim.x) {
             const int2 e = pend[t];
-            if (root[e.x] != root[e.y]) changed |= propagate_edge(root, lab, e.x, e.y);
+            if (FIND) {                                  // the pair holds roots: lab[rb] <- min(., resolve(ra))
+                if (e.x != e.y) {
+                    const int mine = lab_resolve(lab, e.x);
+                    changed |= mine < lab_resolve(lab, e.y) && atomicMin(&lab[e.y], mine) > mine;
+                }
+            } else if (root[e.x] != root[e.y]) changed |= propagate_edge(root, lab, e.x, e.y);
         }
         if (changed) s_changed = 1;
         __syncthreads();
@@ -624,13 +639,17 @@ __global__ void k_cl_reset(int32_t *__restrict__ root, int32_t *__restrict__ lab
 
 // final label per point, sizes per label (warp-aggregated: a floor-sized component would otherwise
 // serialise tens of thousands of atomics on one counter)
-__global__ void k_cl_label(const int32_t *__restrict__ root, int32_t *lab, int32_t N, int32_t *__restrict__ size,
+template <bool FIND>
+__global__ void k_cl_label(uint2 *pl, int32_t *root, int32_t *lab, int32_t N, int32_t *__restrict__ size,
                            uint32_t *__restrict__ key0) {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = v < N;
     int l = -1;
     if (on) {
-        l = lab_resolve(lab, root[v]);
+        int r;
+        if (FIND) { r = uf_find(pl, v); root[v] = r; }           // the flatten pass folded in (trusted path)
+        else r = root[v];
+        l = lab_resolve(lab, r);
         key0[v] = (uint32_t)l;
     }
     const unsigned peers = __match_any_sync(0xffffffffu, l);
@@ -765,14 +784,15 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
         if (trusted) { if (wide) PG_VERIFY(32, true); else PG_VERIFY(8, true); }
         else { if (wide) PG_VERIFY(32, false); else PG_VERIFY(8, false); } }
 #undef PG_VERIFY
-        k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
+        // trusted lists: the last flatten is folded into the label pass (the parked edges resolve their own roots)
+        if (!trusted) k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
         PG_LAUNCH_CHECK();
     }
     // Trusted lists need no verdict from the sweep (no checksum, no range flags): the parked one-way edges are
     // settled on the device and the host reads everything back once, together with the sizes.
     const bool fast = trusted && !use_generic;
     if (fast) {
-        k_cl_pending_block<<<1, 1024, 0, st>>>(w.pend, (unsigned long long)w.pend_cap, w.root, w.lab, w.scalars);
+        k_cl_pending_block<true><<<1, 1024, 0, st>>>(w.pend, (unsigned long long)w.pend_cap, w.pl, w.root, w.lab, w.scalars);
     } else {
         PG_CUDA(cudaMemcpyAsync(h, w.scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
@@ -815,9 +835,11 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
     };
     // final labels, sizes, kept clusters; everything the host needs comes back in one copy
     unsigned long long all[12];
+    bool find_in_label = fast;
     auto finish = [&]() -> int {
         { PG_KTIME("k_cl_label", st);
-        k_cl_label<<<nb, 256, 0, st>>>(w.root, w.lab, N, w.size, w.key0); }
+        if (find_in_label) k_cl_label<true><<<nb, 256, 0, st>>>(w.pl, w.root, w.lab, N, w.size, w.key0);
+        else k_cl_label<false><<<nb, 256, 0, st>>>(w.pl, w.root, w.lab, N, w.size, w.key0); }
         k_cl_keep<<<nb, 256, 0, st>>>(w.key0, w.size, N, threshold, w.cid);
         PG_CUDA(cudaMemsetAsync(w.cid + N, 0, sizeof(int32_t), st));
         PG_TRY(scan_exclusive_i32(w.cid, w.cid, (int64_t)N + 1, (int64_t *)(w.scalars + 4), w.scan_tmp, st));
@@ -838,6 +860,8 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
         g_cl_dbg[4] = (grid && all[8]) ? (long long)all[8] : (long long)N;
         if (all[10] != 0) {
             // more parked edges than one block settles quickly: the host-driven rounds after all, then the labels again
+            // (root[] is complete: the label pass above wrote it)
+            find_in_label = false;
             PG_TRY(settle_host(all[2]));
             PG_CUDA(cudaMemsetAsync(w.size, 0, ((size_t)N + 1) * sizeof(int32_t), st));
             PG_CUDA(cudaMemsetAsync(w.scalars + 4, 0, 2 * sizeof(unsigned long long), st));
