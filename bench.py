@@ -500,13 +500,13 @@ def run_b200(args, rank, world, local, emit=print):
     HOST_KEYS = ("locs", "locs_scaled_f", "feats131", "instance_ids32", "instance_pointnum", "batch_offsets")
     h2d_bytes = n_sub * sum(host[k].numel() * host[k].element_size() for k in HOST_KEYS)
 
-    def one_chain(b, timer=None, fused_glue=False, overlap=True):
-        out = chain.proposal_chain(ops, b, rand6, timer, fused_glue=fused_glue, overlap=overlap)
+    def one_chain(b, timer=None, fused_glue=False, overlap=True, fused_cluster=False):
+        out = chain.proposal_chain(ops, b, rand6, timer, fused_glue=fused_glue, overlap=overlap, fused_cluster=fused_cluster)
         packed = pgdist.pack_proposals(out, b, args.max_proposals)
         return out, packed
 
-    def step_device(timer=None, fused_glue=False, overlap=True):
-        outs = [one_chain(b, timer, fused_glue, overlap) for _, _, b in subs]
+    def step_device(timer=None, fused_glue=False, overlap=True, fused_cluster=False):
+        outs = [one_chain(b, timer, fused_glue, overlap, fused_cluster) for _, _, b in subs]
         packed = outs[0][1] if n_sub == 1 else torch.cat([p for _, p in outs], 0)
         gathered = pgdist.all_gather_proposals(packed)
         return outs[0][0], gathered
@@ -625,6 +625,14 @@ def run_b200(args, rank, world, local, emit=print):
         for _ in range(2):
             step_device(fused_glue=True)
         ms_fused = timed(lambda: step_device(fused_glue=True), args.steps)
+    ms_fc = ms_all = None
+    if extras or world > 1 or args.overlap_variant:
+        for _ in range(3):
+            step_device(fused_cluster=True)
+        ms_fc = timed(lambda: step_device(fused_cluster=True), args.steps)
+        for _ in range(2):
+            step_device(fused_cluster=True, fused_glue=True)
+        ms_all = timed(lambda: step_device(fused_cluster=True, fused_glue=True), args.steps)
     ms_overlap = None
     if extras or world > 1 or args.overlap_variant:
         for _ in range(3):
@@ -763,6 +771,13 @@ def run_b200(args, rank, world, local, emit=print):
                                   "ms_per_step": ms_fused / args.steps,
                                   "what": "same chain with the caller-side clusters_voxelization glue (model/pointgroup.py:125-167) "
                                           "done by pointgroup_ops.cluster_voxel_coords; bit-identical outputs"}
+        if ms_fc is not None:
+            line["fused_cluster"] = {"value": scenes_per_step * args.steps / (ms_fc / 1e3), "unit": UNIT, "ms_per_step": ms_fc / args.steps,
+                                     "what": "same chain with each ballquery_batch_p + bfs_cluster pair (model/pointgroup.py:296-297, "
+                                             ":304-305) as one op, pointgroup_ops.ballquery_bfs_cluster: neighbour lists are only "
+                                             "decoded where the clustering sweep reads them; identical clusters"}
+            line["fused_cluster_and_glue"] = {"value": scenes_per_step * args.steps / (ms_all / 1e3), "unit": UNIT,
+                                              "ms_per_step": ms_all / args.steps, "what": "both caller edits together"}
         if ms_overlap is not None:
             line["single_stream"] = {"value": scenes_per_step * args.steps / (ms_overlap / 1e3), "unit": UNIT,
                                      "ms_per_step": ms_overlap / args.steps,

@@ -175,6 +175,43 @@ def bfs_cluster_impl(semantic_label, ball_query_idxs, start_len, threshold, gene
     return cluster_idxs, cluster_offsets, bool(sizes[2])
 
 
+def ballquery_bfs_cluster_impl(xyz, batch_idxs, batch_offsets, radius, semantic_label, threshold):
+    """Fused ballquery_batch_p + bfs_cluster for callers that need the clusters, not the lists (model/pointgroup.py:296-297
+    passes idx straight on and never looks at it again): the neighbour lists stay in the form the count phase leaves them
+    in (hit masks + merged candidates per cell) and only the lists the clustering sweep actually reads are decoded.
+    Returns (cluster_idxs, cluster_offsets, nActive); same clusters as the two ops called one after the other."""
+    _need(semantic_label, "semantic_label", torch.int32)
+    start_len, total, state = ballquery_count_impl(xyz, batch_idxs, batch_offsets, radius)
+    ws_bq, masks = state
+    n = xyz.size(0)
+    dev = xyz.device
+    lazy_ok = masks is not None and n > 0 and total >= 12 * n        # long lists only (the sweep's cell pass needs them)
+    with torch.cuda.device(dev):
+        L = _L()
+        if lazy_ok:
+            nws = L.pg_bfs_cluster_workspace_bytes(n) + 8 * min(total // 8, 64 << 20)
+            ws = _ws(nws, dev)
+            idx = torch.empty(total, dtype=torch.int32, device=dev)      # only the swept lists get written
+            sizes = (ctypes.c_int32 * 3)()
+            need = ctypes.c_int(0)
+            check(L.pg_bfs_cluster_count_lazy(_p(semantic_label), _p(start_len), n, total, int(threshold), _p(ws), nws,
+                                              _p(ws_bq), ws_bq.numel(), _p(masks), _p(idx), sizes, ctypes.byref(need),
+                                              _stream()), "ballquery_bfs_cluster(count)")
+            if not need.value:
+                nC, S = int(sizes[0]), int(sizes[1])
+                cluster_idxs = torch.empty((S, 2), dtype=torch.int32, device=dev)
+                cluster_offsets = torch.empty(nC + 1, dtype=torch.int32, device=dev)
+                check(L.pg_bfs_cluster_fill(n, nC, S, _p(ws), nws, _p(cluster_idxs), _p(cluster_offsets), _stream()),
+                      "ballquery_bfs_cluster(fill)")
+                return cluster_idxs, cluster_offsets, total
+        else:
+            idx = torch.empty(total, dtype=torch.int32, device=dev)
+    # short lists, no mask buffer, or a parking-lot overflow: materialise everything, cluster as usual
+    ballquery_fill_impl(xyz, radius, start_len, idx, state)
+    ci, co, _ = bfs_cluster_impl(semantic_label, idx, start_len, threshold, trusted=True, grid_ws=ws_bq)
+    return ci, co, total
+
+
 def bfs_cluster_debug():
     """Diagnostics of this thread's last bfs_cluster count phase: [checksum != 0, bad lists, parked one-way
     edges, propagation sweeps, neighbour lists the edge sweep read]."""

@@ -18,7 +18,7 @@ INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC_FLAGS = ["-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
 
-ABI_VERSION = 2        # must equal pg_abi_version() of the loaded library (bumped with every signature change)
+ABI_VERSION = 3        # must equal pg_abi_version() of the loaded library (bumped with every signature change)
 
 _lib = None
 
@@ -87,6 +87,7 @@ SIGNATURES = {
     "pg_bfs_cluster_workspace_bytes": (_sz, [_i64]),
     "pg_bfs_cluster_count": (_int, [_vp, _vp, _vp, _i32, _i64, _i32, _int, _vp, _sz, _vp, _vp]),
     "pg_bfs_cluster_count_grid": (_int, [_vp, _vp, _vp, _i32, _i64, _i32, _vp, _sz, _vp, _sz, _vp, _vp]),
+    "pg_bfs_cluster_count_lazy": (_int, [_vp, _vp, _i32, _i64, _i32, _vp, _sz, _vp, _sz, _vp, _vp, _vp, _vp, _vp]),
     "pg_bfs_cluster_debug": (None, [_vp]),
     "pg_bfs_cluster_fill": (_int, [_i32, _i32, _i32, _vp, _sz, _vp, _vp, _vp]),
     "pg_roipool_workspace_bytes": (_sz, [_i32, _i32]),

@@ -185,12 +185,14 @@ def _side_streams(dev):
     return _streams[dev]
 
 
-def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=False, overlap=True):
+def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=False, overlap=True, fused_cluster=False):
     """One pass of the hot path over one collated batch (all tensors on one CUDA device).
 
     batch: locs fp32 [N,3], locs_scaled int64 [N,4], feats fp32 [N,134], pt_feats fp32 [N,16],
     semantic_preds int64 [N], pt_offsets fp32 [N,3], instance_ids int64 [N], instance_pointnum int32
     [nInst], n_scenes.  Returns a dict of the tensors the rest of the detector consumes.
+    ``fused_cluster``: each ballquery_batch_p + bfs_cluster pair as ONE op (pointgroup_ops.ballquery_bfs_cluster: the
+    neighbour lists are never materialised where the clustering does not read them) -- a caller edit, like ``fused_glue``.
     ``overlap`` (CUDA only; ignored while a timer or a trace is attached): the two independent clusterings are issued
     from two host threads on two streams -- scheduling only, the op calls and their results are the same."""
     timer = timer or _NoTimer()
@@ -226,7 +228,20 @@ def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=Fa
 
     shifted = (coords_ + pt_offsets_).contiguous()
 
+    fused = fused_cluster and trace is None and getattr(ops, "ballquery_bfs_cluster", None) is not None
+
+    def cluster_fused(pts, mean_active, key):
+        t = timer.start("ballquery_bfs_cluster(%s)" % key)
+        pidx, poff, n_active = ops.ballquery_bfs_cluster(pts, batch_idxs_, batch_offsets_, scenes.CLUSTER_RADIUS, mean_active,
+                                                         sem_, scenes.CLUSTER_NPOINT_THRE)
+        timer.stop(t)
+        out["nActive_" + key] = n_active
+        pidx[:, 1] = object_idxs[pidx[:, 1].long()].int()
+        return pidx, poff
+
     def cluster_shift():
+        if fused:
+            return cluster_fused(shifted, scenes.CLUSTER_SHIFT_MEANACTIVE, "shift")
         t = timer.start("ballquery(shift)")
         idx_shift, start_len_shift = ops.ballquery_batch_p(shifted, batch_idxs_, batch_offsets_, scenes.CLUSTER_RADIUS,
                                                            scenes.CLUSTER_SHIFT_MEANACTIVE)
@@ -242,6 +257,8 @@ def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=Fa
         return pidx, poff
 
     def cluster_raw():
+        if fused:
+            return cluster_fused(coords_, scenes.CLUSTER_MEANACTIVE, "raw")
         t = timer.start("ballquery(raw)")
         idx, start_len = ops.ballquery_batch_p(coords_, batch_idxs_, batch_offsets_, scenes.CLUSTER_RADIUS,
                                                scenes.CLUSTER_MEANACTIVE)

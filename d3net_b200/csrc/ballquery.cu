@@ -654,9 +654,14 @@ __global__ void __launch_bounds__(kTestThreads, 8) k_bq_test_dense(
 
 // start_len rows from the per-query counts and their exclusive scan (both in query order)
 __global__ void k_bq_start_len(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ counts,
-                               const int32_t *__restrict__ starts, int32_t n, int2 *__restrict__ start_len) {
+                               const int32_t *__restrict__ starts, int32_t n, int2 *__restrict__ start_len,
+                               int32_t *__restrict__ qpos) {
     int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < n) start_len[sorted_pt[q]] = make_int2(starts[q], counts[q]);
+    if (q < n) {
+        const uint32_t k = sorted_pt[q];
+        start_len[k] = make_int2(starts[q], counts[q]);
+        qpos[k] = q;
+    }
 }
 
 // ---- fill -------------------------------------------------------------------------------------------
@@ -838,6 +843,96 @@ __global__ void __launch_bounds__(256, 5) k_bq_fill_mask(const uint32_t *__restr
     }
 }
 
+// ---- lazy lists (see ballquery.cuh) ---------------------------------------------------------------------------------
+// n-th (1-based) set bit of m
+__device__ __forceinline__ int nth_set_bit(unsigned m, int nth) {
+    for (int i = 1; i < nth; i++) m &= m - 1u;
+    return __ffs((int)m) - 1;
+}
+
+// a thread per query (consecutive queries of a cell read consecutive mask words: coalesced)
+__global__ void __launch_bounds__(256) k_bq_list_samples(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cell,
+                                                        const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
+                                                        const int32_t *__restrict__ cand_start, const int32_t *__restrict__ kb,
+                                                        const uint32_t *__restrict__ cand_idx, const int32_t *__restrict__ mbase,
+                                                        const uint32_t *__restrict__ masks, const int32_t *__restrict__ counts,
+                                                        int32_t n, int4 *__restrict__ samples) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint32_t k = __ldg(sorted_pt + q);
+    const int len = __ldg(counts + q);
+    int e0 = (int)k, e1 = (int)k, em = (int)k, el = (int)k;          // an empty list samples the point itself (a self edge)
+    if (len > 0) {
+        const int c = __ldg(cell + k);
+        const int nq = __ldg(ccnt + c);
+        const int nb = (__ldg(kb + c) + 31) >> 5;
+        const uint32_t *mrow = masks + __ldg(mbase + c) + (q - __ldg(cstart + c));
+        const uint32_t *cp = cand_idx + __ldg(cand_start + c);
+        int seen = 0, p0 = -1, p1 = -1, pm = -1, pl = -1;
+        for (int b = 0; b < nb; b++) {
+            unsigned m = __ldg(mrow + (int64_t)b * nq);
+            if (m == 0u) continue;
+            const int pc = __popc(m);
+            if (seen + pc >= len) {                                  // the list ends inside this word (later bits: hits beyond the cap)
+                const int at = nth_set_bit(m, len - seen);
+                pl = (b << 5) + at;
+                m &= (at == 31) ? 0xffffffffu : ((2u << at) - 1u);
+            }
+            if (p0 < 0) {
+                p0 = (b << 5) + __ffs((int)m) - 1;
+                const unsigned r = m & (m - 1u);
+                if (r) p1 = (b << 5) + __ffs((int)r) - 1;
+            } else if (p1 < 0) p1 = (b << 5) + __ffs((int)m) - 1;
+            if (pm < 0 && seen + pc >= (len + 1) / 2) pm = (b << 5) + nth_set_bit(m, max(1, min(pc, (len + 1) / 2 - seen)));
+            seen += pc;
+            if (pl >= 0) break;
+        }
+        e0 = (int)__ldg(cp + p0);
+        e1 = p1 >= 0 ? (int)__ldg(cp + p1) : e0;
+        em = pm >= 0 ? (int)__ldg(cp + pm) : e0;
+        el = pl >= 0 ? (int)__ldg(cp + pl) : e0;
+    }
+    samples[k] = make_int4(e0, e1, em, el);
+}
+
+// a warp per listed point
+__global__ void __launch_bounds__(256, 5) k_bq_fill_lists(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ cell,
+                                                       const int32_t *__restrict__ cstart, const int32_t *__restrict__ ccnt,
+                                                       const int32_t *__restrict__ cand_start, const int32_t *__restrict__ kb,
+                                                       const uint32_t *__restrict__ cand_idx, const int32_t *__restrict__ mbase,
+                                                       const uint32_t *__restrict__ masks, const int2 *__restrict__ start_len,
+                                                       const int32_t *__restrict__ qpos, const uint32_t *__restrict__ worklist,
+                                                       const unsigned long long *__restrict__ count, int32_t *__restrict__ idx) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = lanemask_lt();
+    const long long nl = (long long)*count;
+    const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < nl; e += nWarps) {
+        const uint32_t i = __ldg(worklist + e);
+        if (__ldg(&start_len[i].y) == 0) continue;
+        bq_fill_run(__ldg(qpos + i), 1, __ldg(cell + i), sorted_pt, cstart, ccnt, cand_start, kb, cand_idx, mbase, masks, start_len,
+                    idx, lane, lt);
+    }
+}
+
+int bq_list_samples(const BqWs &w, const uint32_t *masks, int32_t n, int4 *samples, cudaStream_t st) {
+    PG_KTIME("k_bq_list_samples", st);
+    k_bq_list_samples<<<(unsigned)div_up(n, 256), 256, 0, st>>>(bq_sorted(w, n), w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx,
+                                                               w.mbase, masks, w.counts, n, samples);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
+int bq_fill_lists(const BqWs &w, const uint32_t *masks, const int2 *start_len, const uint32_t *worklist,
+                  const unsigned long long *count, int32_t n, int32_t *idx, cudaStream_t st) {
+    PG_KTIME("k_bq_fill_lists", st);
+    k_bq_fill_lists<<<kNumSM * PG_RESIDENT(k_bq_fill_lists, 256, 0) * 4, 256, 0, st>>>(bq_sorted(w, n), w.cell, w.cstart, w.ccnt, w.cand_start,
+                                                                                   w.kb, w.cand_idx, w.mbase, masks, start_len, w.qpos,
+                                                                                   worklist, count, idx);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
 }  // namespace pg
 
 using namespace pg;
@@ -921,7 +1016,7 @@ extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int
         w.counts, w.kb); }
     // starts (reuse pslot) in query order, then the interleaved (start, len) rows per point
     PG_TRY(scan_exclusive_i32(w.counts, w.pslot, n, w.scalars + 2, w.scan_tmp, st));
-    k_bq_start_len<<<(unsigned)div_up(n, 256), 256, 0, st>>>(sorted_pt, w.counts, w.pslot, n, (int2 *)start_len);
+    k_bq_start_len<<<(unsigned)div_up(n, 256), 256, 0, st>>>(sorted_pt, w.counts, w.pslot, n, (int2 *)start_len, w.qpos);
     PG_LAUNCH_CHECK();
     int64_t back[5] = {0, 0, 0, 0, 0};               // scalars [2] total neighbours ... [6] mask words
     PG_CUDA(cudaMemcpyAsync(back, w.scalars + 2, sizeof(back), cudaMemcpyDeviceToHost, st));

@@ -11,6 +11,7 @@ struct BqWs {
     int32_t *pslot, *cell, *ccnt, *cstart, *kc, *kb, *cand_start, *counts, *nbr, *mbase, *dense;
     int32_t *dbase;     // dense cells, by slot of `dense`: where the cell's candidate coordinates start in cand_xy / cand_z
     uint2 *crange;      // dense cells: (smallest, largest) candidate index
+    int32_t *qpos;      // point -> its position in the query order (inverse of sorted_pt)
     uint32_t *cand_idx;
     // dense cells: candidate coordinates in merged (ascending index) order, laid out in PAIRS for the packed f32x2
     // predicate and padded per cell to a multiple of 32 with +inf:  cand_xy[p] = (x0, x1, y0, y1), cand_z[p] = (z0, z1)
@@ -47,6 +48,7 @@ inline BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
     w.dense = a.take<int32_t>(n);
     w.dbase = a.take<int32_t>(n);
     w.crange = a.take<uint2>(n);
+    w.qpos = a.take<int32_t>(n);
     w.kA = a.take<uint32_t>(n);
     w.vA = a.take<uint32_t>(n);
     w.kB = a.take<uint32_t>(n);
@@ -69,5 +71,16 @@ inline BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
 // the points grouped by cell (cell c: sorted_pt[cstart[c] .. cstart[c] + ccnt[c]), in no particular order inside a cell);
 // this is also the QUERY order.  kA / kB hold the smallest / largest point index of every cell.
 inline const uint32_t *bq_sorted(const BqWs &w, int32_t) { return w.vA; }
+
+// Lazy lists (cluster.cu's fused path): the neighbour lists stay in the form the count phase left them in -- one bit per
+// (query, candidate) plus every cell's merged candidate indices -- and are only turned into index lists where the
+// clustering sweep reads them.
+//   bq_list_samples  per point (first, second, a middle, last) entry of its list, straight from the masks; `last` is the
+//                    1000th hit when the list is full.  What k_cl_prep / k_cl_sample need instead of idx.
+//   bq_fill_lists    the lists of the points in `worklist[0 .. *count)` (device count), written at their start_len
+//                    positions of idx; everything else in idx stays untouched.
+int bq_list_samples(const BqWs &w, const uint32_t *masks, int32_t n, int4 *samples, cudaStream_t st);
+int bq_fill_lists(const BqWs &w, const uint32_t *masks, const int2 *start_len, const uint32_t *worklist,
+                  const unsigned long long *count, int32_t n, int32_t *idx, cudaStream_t st);
 
 }  // namespace pg

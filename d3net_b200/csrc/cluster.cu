@@ -41,6 +41,7 @@ struct ClWs {
     int32_t *cid;        // cluster id per kept label (exclusive scan of keep flags)
     int32_t *csize;      // sizes in cluster order -> offsets
     int2 *pend;          // parked one-way edges (i -> j)
+    int4 *samples;       // lazy lists: (first, second, middle, last) entry of every point's list
     uint2 *cellsum;      // grid-assisted mode, per ball-query cell: (main label, snapshot root)
     int32_t *cstate;     //   skip threshold L per cell
     int32_t *cthr;       //   three minima of last(j) over the cell's full points (T1, T2, T3)
@@ -71,6 +72,7 @@ static ClWs cl_layout(void *ws, size_t ws_bytes, int64_t N_) {
     w.cellsum = a.take<uint2>(n);
     w.cstate = a.take<int32_t>(n);
     w.cthr = a.take<int32_t>(3 * n);
+    w.samples = a.take<int4>(n);
     w.key0 = a.take<uint32_t>(n);
     w.kA = a.take<uint32_t>(n);
     w.vA = a.take<uint32_t>(n);
@@ -103,11 +105,13 @@ __device__ __forceinline__ unsigned long long mix64(unsigned a, unsigned b) {
 // hangs itself under the first entry of its list (the smallest index in its ball) when that is a
 // smaller, equal-label point that lists it back -- parents only ever point to smaller indices, so the
 // result is a forest, and in a ball-query graph every ball-sized neighbourhood is already one tree.
+// `samples` (lazy lists): the entries this kernel would read from idx -- first, second and last of every list -- come from
+// there instead; idx is not touched.
 __global__ void k_cl_prep(const int32_t *__restrict__ label, const int32_t *__restrict__ idx,
                           const int2 *__restrict__ start_len, int32_t N, int64_t nActive, int hook,
                           uint2 *__restrict__ pl, uint32_t *__restrict__ trunc, int32_t *__restrict__ last,
                           int32_t *__restrict__ root, int32_t *__restrict__ lab, uint32_t *__restrict__ skey, int shift,
-                          unsigned long long *scalars) {
+                          unsigned long long *scalars, const int4 *__restrict__ samples) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     bool full = false;
     if (v < N) {
@@ -118,15 +122,18 @@ __global__ void k_cl_prep(const int32_t *__restrict__ label, const int32_t *__re
         const int lv = __ldg(label + v);
         if (sl.y < 0 || sl.x < 0 || (int64_t)sl.x + sl.y > nActive) scalars[1] = 2;   // malformed row
         else {
-            if (sl.y >= kCapC) { lst = __ldg(idx + sl.x + sl.y - 1); full = true; }
+            int4 sm = make_int4(v, v, v, v);
+            if (samples) sm = __ldg(samples + v);
+            if (sl.y >= kCapC) { lst = samples ? sm.w : __ldg(idx + sl.x + sl.y - 1); full = true; }
             if (hook && sl.y > 0) {
-                int j = __ldg(idx + sl.x);
-                if (j == v && sl.y > 1) j = __ldg(idx + sl.x + 1);
+                int j = samples ? sm.x : __ldg(idx + sl.x);
+                if (j == v && sl.y > 1) j = samples ? sm.y : __ldg(idx + sl.x + 1);
                 if (j >= 0 && j < v && __ldg(label + j) == lv) {
                     const int2 sj = __ldg(start_len + j);
                     bool back = true;                              // does j list v?  (only a full list may not)
                     if (sj.y >= kCapC)
-                        back = sj.x >= 0 && (int64_t)sj.x + sj.y <= nActive && v <= __ldg(idx + sj.x + sj.y - 1);
+                        back = sj.x >= 0 && (int64_t)sj.x + sj.y <= nActive &&
+                               v <= (samples ? __ldg(&samples[j].w) : __ldg(idx + sj.x + sj.y - 1));
                     if (back) parent = j;
                 }
             }
@@ -187,7 +194,7 @@ constexpr int kSampleRounds = 1;
 template <int P>
 __global__ void k_cl_sample(const int32_t *__restrict__ idx, const int2 *__restrict__ start_len, uint2 *pl,
                             const int32_t *__restrict__ last, const uint32_t *__restrict__ snap, int32_t N, int64_t nActive,
-                            int round) {
+                            int round, const int4 *__restrict__ samples) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int2 sl = start_len[i];
@@ -202,8 +209,14 @@ __global__ void k_cl_sample(const int32_t *__restrict__ idx, const int2 *__restr
     pos[2] = sl.y >> 2;
     pos[3] = (int)(((long long)sl.y * 3) >> 2);
     int jj[P];
+    if (samples) {                                  // lazy lists: the last and a middle entry were sampled from the hit masks
+        const int4 sm = __ldg(samples + i);
 #pragma unroll
-    for (int u = 0; u < P; u++) jj[u] = __ldg(idx + sl.x + pos[u]);
+        for (int u = 0; u < P; u++) jj[u] = (u & 1) ? sm.z : sm.w;
+    } else {
+#pragma unroll
+        for (int u = 0; u < P; u++) jj[u] = __ldg(idx + sl.x + pos[u]);
+    }
     const unsigned si = __ldg(snap + i);
     unsigned sj[P];
 #pragma unroll
@@ -709,9 +722,14 @@ extern "C" size_t pg_bfs_cluster_workspace_bytes(int64_t N) {
 
 // `bq_ws` (optional, trusted mode only): the workspace of the pg_ballquery_* calls that produced the lists,
 // untouched since -- its grid lets whole cells skip the edge sweep (k_cl_cells)
+// `lazy_masks` (with bq_ws, trusted): the lists exist only as the ball query's hit masks; `ball_query_idxs` is then a
+// scratch buffer of nActive ints into which the lists the sweep reads are decoded (the others are never materialised).
+// *need_lists is raised (and nothing else returned) when the parked one-way edges overflow their lot and the fall-back
+// needs every list: the caller materialises them and calls the ordinary entry point.
 static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_query_idxs, const int32_t *start_len, int32_t N,
                           int64_t nActive, int32_t threshold, int mode, void *ws, size_t ws_bytes, void *bq_ws,
-                          size_t bq_ws_bytes, int32_t *host_sizes, void *stream) {
+                          size_t bq_ws_bytes, int32_t *host_sizes, void *stream, const uint32_t *lazy_masks = nullptr,
+                          int *need_lists = nullptr) {
     cudaStream_t st = (cudaStream_t)stream;
     PG_CHECK_ARG(host_sizes, "null host_sizes");
     host_sizes[0] = host_sizes[1] = host_sizes[2] = 0;
@@ -733,9 +751,6 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
     int abits = 0;
     while ((1ll << abits) <= nActive) abits++;
     const int shift = abits > 16 ? abits - 16 : 0;
-    k_cl_prep<<<(unsigned)div_up((int64_t)N + 32, 256), 256, 0, st>>>(semantic_label, ball_query_idxs, sl, N, nActive,
-                                                                     generic ? 0 : 1, w.pl, w.trunc, w.last, w.root, w.lab,
-                                                                     w.key0, shift, w.scalars);
     unsigned long long h[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     bool use_generic = generic != 0;
     const bool trusted = mode == PG_BFS_TRUSTED;
@@ -745,6 +760,16 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
         g = bq_layout(bq_ws, bq_ws_bytes, N);
         if (!g.ok) { set_error("pg_bfs_cluster_count_grid: ball-query workspace too small for N = %d", N); return PG_EWORKSPACE; }
     }
+    const bool lazy = lazy_masks != nullptr;
+    const int4 *samples = nullptr;
+    if (lazy) {
+        PG_CHECK_ARG(grid && wide, "lazy lists need the producing ball query's workspace and long lists");
+        PG_TRY(bq_list_samples(g, lazy_masks, N, w.samples, st));
+        samples = w.samples;
+    }
+    k_cl_prep<<<(unsigned)div_up((int64_t)N + 32, 256), 256, 0, st>>>(semantic_label, ball_query_idxs, sl, N, nActive,
+                                                                     generic ? 0 : 1, w.pl, w.trunc, w.last, w.root, w.lab,
+                                                                     w.key0, shift, w.scalars, samples);
     if (!use_generic) {
         // the cell pass pays off on long lists only: it reads ~27 cells' worth of candidates per cell, which on
         // short lists (raw coordinates, ~5 neighbours per point) is more than the edges themselves
@@ -763,7 +788,7 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
         k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
         for (int round = 0; round < kSampleRounds; round++) {
             { PG_KTIME("k_cl_sample", st);
-            k_cl_sample<2><<<nb, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.last, w.snap, N, nActive, round); }
+            k_cl_sample<2><<<nb, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.last, w.snap, N, nActive, round, samples); }
             PG_KTIME("k_cl_flatten", st);
             k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
         }
@@ -776,6 +801,8 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
             k_cl_cell_settle<<<cg, 256, 0, st>>>(g.nbr, g.scalars, w.cellsum, w.cthr, w.cstate);
             k_cl_cell_worklist<<<nb, 256, 0, st>>>(sp, g.cell, w.pl, w.snap, w.cellsum, w.cstate, N, w.vA, w.scalars);
         }
+        // lazy lists: only now, and only for the lists the sweep is about to read, do indices get written
+        if (lazy) PG_TRY(bq_fill_lists(g, lazy_masks, sl, w.vA, w.scalars + 8, N, const_cast<int32_t *>(ball_query_idxs), st));
         const unsigned vg = kNumSM * 3;
 #define PG_VERIFY(G, T)                                                                                              \
     k_cl_verify<G, T><<<vg, kVerThreads, 0, st>>>(ball_query_idxs, sl, order, w.pl, w.last, w.snap, N, nActive, w.pend, \
@@ -810,9 +837,11 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
     g_cl_dbg[4] = (grid && h[8]) ? (long long)h[8] : (long long)N;
     // min-label propagation to a fixed point, one launch + one readback per round (the parked edges, or -- on the
     // generic path / when the parking lot overflowed -- every edge)
+    bool lists_needed = false;
     auto settle_host = [&](unsigned long long n_parked) -> int {
         const bool sweep = use_generic || n_parked > w.pend_cap;
         if (!sweep && n_parked == 0) return PG_OK;
+        if (sweep && lazy) { lists_needed = true; return PG_OK; }     // every list would be read: not with lazy lists
         for (int it = 0; it < 1000000; it++) {
             PG_CUDA(cudaMemsetAsync(w.scalars + 3, 0, sizeof(unsigned long long), st));
             if (!sweep) {
@@ -863,6 +892,7 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
             // (root[] is complete: the label pass above wrote it)
             find_in_label = false;
             PG_TRY(settle_host(all[2]));
+            if (lists_needed) { *need_lists = 1; return PG_OK; }
             PG_CUDA(cudaMemsetAsync(w.size, 0, ((size_t)N + 1) * sizeof(int32_t), st));
             PG_CUDA(cudaMemsetAsync(w.scalars + 4, 0, 2 * sizeof(unsigned long long), st));
             PG_TRY(finish());
@@ -888,6 +918,17 @@ extern "C" int pg_bfs_cluster_count_grid(const int32_t *semantic_label, const in
     PG_CHECK_ARG(ballquery_ws != nullptr, "null ballquery_ws");
     return bfs_count_impl(semantic_label, ball_query_idxs, start_len, N, nActive, threshold, PG_BFS_TRUSTED, ws, ws_bytes,
                           ballquery_ws, ballquery_ws_bytes, host_sizes, stream);
+}
+
+extern "C" int pg_bfs_cluster_count_lazy(const int32_t *semantic_label, const int32_t *start_len, int32_t N, int64_t nActive,
+                                         int32_t threshold, void *ws, size_t ws_bytes, void *ballquery_ws,
+                                         size_t ballquery_ws_bytes, const uint32_t *masks, int32_t *idx_scratch,
+                                         int32_t *host_sizes, int *host_need_lists, void *stream) {
+    PG_CHECK_ARG(ballquery_ws != nullptr && masks != nullptr && host_need_lists != nullptr, "null pointer");
+    PG_CHECK_ARG(idx_scratch != nullptr || nActive == 0, "null idx_scratch");
+    *host_need_lists = 0;
+    return bfs_count_impl(semantic_label, idx_scratch, start_len, N, nActive, threshold, PG_BFS_TRUSTED, ws, ws_bytes,
+                          ballquery_ws, ballquery_ws_bytes, host_sizes, stream, masks, host_need_lists);
 }
 
 extern "C" int pg_bfs_cluster_fill(int32_t N, int32_t nCluster, int32_t sumNPoint, void *ws, size_t ws_bytes,

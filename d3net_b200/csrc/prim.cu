@@ -407,4 +407,4 @@ extern "C" size_t pg_kernel_timing_report(char *buf, size_t cap) {
 }
 
 extern "C" const char *pg_last_error(void) { return pg::last_error(); }
-extern "C" int pg_abi_version(void) { return 2; }
+extern "C" int pg_abi_version(void) { return 3; }

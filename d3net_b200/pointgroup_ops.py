@@ -243,6 +243,22 @@ class BFSCluster(Function):
 bfs_cluster = BFSCluster.apply
 
 
+def ballquery_bfs_cluster(coords, batch_idxs, batch_offsets, radius, meanActive, semantic_label, threshold):
+    """Not part of the reference's operator API: ``bfs_cluster(semantic_label, *ballquery_batch_p(coords, ...), threshold)``
+    as ONE op for callers that hand the neighbour lists straight on (model/pointgroup.py:296-297 and :304-305).  The
+    lists are clustered from the ball query's hit masks; only the ones the sweep has to read are ever decoded.  Returns
+    (cluster_idxs, cluster_offsets, nActive) -- the same clusters, bit for bit."""
+    assert coords.is_contiguous() and coords.is_cuda
+    assert batch_idxs.is_contiguous() and batch_idxs.is_cuda
+    assert batch_offsets.is_contiguous() and batch_offsets.is_cuda
+    dev = coords.device
+    ci, co, total = PG_OP.ballquery_bfs_cluster_impl(coords, batch_idxs, batch_offsets, radius,
+                                                     semantic_label.to(dev).contiguous(), threshold)
+    if not semantic_label.is_cuda:
+        ci, co = ci.cpu(), co.cpu()
+    return ci, co, total
+
+
 class RoiPool(Function):
     @staticmethod
     def forward(ctx, feats, proposals_offset):

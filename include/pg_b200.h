@@ -138,6 +138,16 @@ int pg_bfs_cluster_count_grid(const int32_t *semantic_label, const int32_t *ball
                               const int32_t *start_len, int32_t N, int64_t nActive, int32_t threshold, void *ws,
                               size_t ws_bytes, void *ballquery_ws, size_t ballquery_ws_bytes, int32_t *host_sizes,
                               void *stream);
+/* Lazy lists -- the fused form of ballquery_batch_p + bfs_cluster for callers that need the clusters but not the lists
+ * (model/pointgroup.py:296-297 hands idx to bfs_cluster and never looks at it again): after pg_ballquery_prepare/count
+ * WITH hit masks, the lists are clustered straight from (masks, merged candidates); only the lists the edge sweep has
+ * to read are decoded, into idx_scratch (device, nActive ints, otherwise untouched).  Same clusters as
+ * pg_bfs_cluster_count on the materialised lists.  *host_need_lists = 1 (sizes not valid): so many one-way edges were
+ * parked that the fall-back needs every list -- call pg_ballquery_fill and pg_bfs_cluster_count_grid instead. */
+int pg_bfs_cluster_count_lazy(const int32_t *semantic_label, const int32_t *start_len, int32_t N, int64_t nActive,
+                              int32_t threshold, void *ws, size_t ws_bytes, void *ballquery_ws, size_t ballquery_ws_bytes,
+                              const uint32_t *masks, int32_t *idx_scratch, int32_t *host_sizes, int *host_need_lists,
+                              void *stream);
 /* Diagnostics of this thread's last count phase (no reference counterpart): out[5] = {list checksum failed,
  * malformed lists, parked one-way edges, propagation sweeps, neighbour lists the edge sweep read}. */
 void pg_bfs_cluster_debug(long long *out);

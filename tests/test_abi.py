@@ -25,7 +25,7 @@ def lib():
 def test_every_declared_symbol_is_exported_and_bound(lib):
     from d3net_b200 import _native
     names = _declared()
-    assert len(names) == 37
+    assert len(names) == 38
     for n in names:
         assert hasattr(lib, n), "libpg_b200.so does not export " + n
         assert n in _native.SIGNATURES, "no ctypes signature for " + n

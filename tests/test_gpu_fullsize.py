@@ -250,6 +250,10 @@ def test_config4_one_million_point_scene_oracle_replay(ops):
             assert int((sl[:, 1] == 1000).sum()) > 100_000                     # the cap really is exercised
         trace = {"ballquery(%s)" % tag: (pts, bi, bo, idx, sl), "bfs_cluster(%s)" % tag: (sem, idx, sl, ci, co)}
         replay.check_trace(trace, ref=ref, big=True)
+        # the fused op (lists decoded only where the sweep reads them; here most lists are full): same clusters
+        fi, fo, total = ops.ballquery_bfs_cluster(pts, bi, bo, 0.03, 300, sem, 50)
+        assert total == idx.numel() and torch.equal(fo, co) and torch.equal(fi, ci)
+        del fi, fo
         del idx, sl, trace
         torch.cuda.empty_cache()
 
@@ -278,6 +282,18 @@ def test_config2_maskless_fill_matches(ops, full_batch):
         idx2 = torch.empty(total, dtype=torch.int32, device=idx.device)
         PG_OP.ballquery_fill_impl(shifted, 0.03, sl2, idx2, state)
         assert torch.equal(sl[:, 1], sl2[:, 1]) and torch.equal(want, relaid(idx2, sl2))
+
+
+def test_config2_fused_cluster_chain_is_identical(ops, full_batch):
+    """chain.proposal_chain(fused_cluster=True) on the full 8 x 150k batch: every output tensor equals the plain chain's."""
+    nb, batch = full_batch
+    a = chain.proposal_chain(ops, batch, overlap=False)
+    b = chain.proposal_chain(ops, batch, fused_cluster=True, fused_glue=True)
+    torch.cuda.synchronize()
+    for k in ("proposals_idx", "proposals_offset", "proposals_score_feats", "ious", "proposals_center", "proposals_size",
+              "proposals_voxel_feats", "proposals_voxel_coords"):
+        assert torch.equal(a[k], b[k]), k
+    assert a["nActive_shift"] == b["nActive_shift"] and a["nActive_raw"] == b["nActive_raw"]
 
 
 def test_chain_two_stream_variant_is_identical(ops):

@@ -643,3 +643,41 @@ def test_fused_cluster_glue_equals_torch_sequence(ops):
             assert torch.equal(a[k].view(torch.int32), b[k].view(torch.int32)), k
         else:
             assert torch.equal(a[k], b[k]), k
+
+
+# ------------------------------------------------------------------------------------------------
+# fused ballquery_batch_p + bfs_cluster (lazy neighbour lists)
+# ------------------------------------------------------------------------------------------------
+def _fused_vs_separate(ops, oracle, xyz, bi, bo, sem, r, thr):
+    x, b, o, s_ = cu(xyz), cu(bi), cu(bo), cu(sem)
+    idx, sl = ops.ballquery_batch_p(x, b, o, r, 300)
+    ci, co = ops.bfs_cluster(s_, idx, sl, thr)
+    fi, fo, total = ops.ballquery_bfs_cluster(x, b, o, r, 300, s_, thr)
+    assert total == idx.numel()
+    assert torch.equal(co, fo) and torch.equal(ci, fi)
+    oidx, osl = oracle.ballquery_batch_p(xyz, bi, bo, r)
+    rci, rco = oracle.bfs_cluster(sem, oidx, osl, thr)
+    np.testing.assert_array_equal(npy(fo), rco)
+    for a, c in zip(oracle.canonical_clusters(npy(fi), npy(fo)), oracle.canonical_clusters(rci, rco)):
+        np.testing.assert_array_equal(a, c)
+    return int(osl[:, 1].max())
+
+
+def test_fused_cluster_scene(ops, oracle):
+    s = object_subset(small_batch(3, 20000))
+    for key in ("shifted", "coords"):                      # long lists (lazy path) and short ones (falls back to the two ops)
+        _fused_vs_separate(ops, oracle, s[key], s["batch_idxs"], s["batch_offsets"], s["sem"], 0.03, 50)
+
+
+def test_fused_cluster_truncated_lists(ops, oracle):
+    """Blobs whose lists hit the 1000 cap (one-way edges, exact `last` entries from the masks) plus a bridge."""
+    rng = np.random.default_rng(12)
+    blobs = [rng.normal(c, 0.006, (1800, 3)) for c in ([0, 0, 0], [0.05, 0, 0], [0.3, 0.3, 0])]
+    bridge = np.linspace([0, 0, 0], [0.3, 0.3, 0], 40)
+    xyz = np.concatenate(blobs + [bridge, rng.uniform(-1, 1, (2000, 3))]).astype(np.float32)
+    xyz = xyz[rng.permutation(len(xyz))]
+    bi = np.zeros(len(xyz), np.int32)
+    bo = np.array([0, len(xyz)], np.int32)
+    for labels in (np.ones(len(xyz), np.int32), rng.integers(1, 3, len(xyz)).astype(np.int32)):
+        mx = _fused_vs_separate(ops, oracle, xyz, bi, bo, labels, 0.03, 5)
+        assert mx == 1000

@@ -8,7 +8,7 @@ timeout 300 python bench.py --steps 10 --warmup 3 --no-extras --overlap-variant 
 python - <<PY
 import json
 d=json.load(open('gpurun_out/${TAG}_bench.json'))
-print('single_stream', d.get('single_stream',{}).get('ms_per_step')); print('value',round(d['value'],1),'ms',round(d['ms_per_step'],3),'e2e',round(d['e2e']['value'],1),'launches',d['gpu_launches_per_step'],d['all_kernel_launches_per_step'])
+print('single_stream', d.get('single_stream',{}).get('ms_per_step'), 'fused_cluster', d.get('fused_cluster',{}).get('ms_per_step'), 'fused_all', d.get('fused_cluster_and_glue',{}).get('ms_per_step')); print('value',round(d['value'],1),'ms',round(d['ms_per_step'],3),'e2e',round(d['e2e']['value'],1),'launches',d['gpu_launches_per_step'],d['all_kernel_launches_per_step'])
 for k,v in d['per_op'].items(): print('  %-32s %s'%(k,v['ms']))
 for k,v in list(d['per_kernel'].items())[:16]: print('  %-28s %s'%(k,v['ms_per_step']))
 PY
