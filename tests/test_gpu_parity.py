@@ -681,3 +681,24 @@ def test_fused_cluster_truncated_lists(ops, oracle):
     for labels in (np.ones(len(xyz), np.int32), rng.integers(1, 3, len(xyz)).astype(np.int32)):
         mx = _fused_vs_separate(ops, oracle, xyz, bi, bo, labels, 0.03, 5)
         assert mx == 1000
+
+
+def test_fused_cluster_edge_cases(ops, oracle):
+    """Empty input, radius 0 (nobody has a neighbour but itself), one tight blob (every list full), NaN coordinates."""
+    z3 = torch.zeros((0, 3), device="cuda")
+    zi = torch.zeros(0, dtype=torch.int32, device="cuda")
+    ci, co, total = ops.ballquery_bfs_cluster(z3, zi, torch.tensor([0, 0], dtype=torch.int32, device="cuda"), 0.03, 50, zi, 50)
+    assert total == 0 and tuple(ci.shape) == (0, 2) and co.tolist() == [0]
+    rng = np.random.default_rng(8)
+    xyz = rng.uniform(0, 1, (3000, 3)).astype(np.float32)
+    bi = np.zeros(3000, np.int32)
+    bo = np.array([0, 3000], np.int32)
+    sem = np.ones(3000, np.int32)
+    _fused_vs_separate(ops, oracle, xyz, bi, bo, sem, 0.0, 1)                     # r = 0: 3000 singletons... none (strict <)
+    blob = rng.normal(0, 0.003, (2500, 3)).astype(np.float32)                     # every list holds the first 1000 points
+    mx = _fused_vs_separate(ops, oracle, blob, np.zeros(2500, np.int32), np.array([0, 2500], np.int32), np.ones(2500, np.int32), 0.03, 10)
+    assert mx == 1000
+    bad = blob.copy()
+    bad[::7] = np.nan
+    bad[3::11, 1] = np.inf
+    _fused_vs_separate(ops, oracle, bad, np.zeros(2500, np.int32), np.array([0, 2500], np.int32), np.ones(2500, np.int32), 0.03, 10)

@@ -20,3 +20,4 @@ for f in ("bench", "bench_c3", "bench_c4"):
         print("  speaker", {k: d["speaker_forward"].get(k) for k in ("value", "ms_per_step", "ops_share", "ops_ms", "captions")})
         print("  detector", {k: d["detector_only"].get(k) for k in ("value", "ms_per_step", "ops_share", "ops_ms")})
 PY
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
