@@ -36,6 +36,7 @@ inline BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
     w.keys = a.take<int4>(n);
     w.tab.slot_rep = a.take<int32_t>(w.tab.cap);
     w.tab.slot_gid = a.take<int32_t>(w.tab.cap);
+    w.tab.slot_key = a.take<int4>(w.tab.cap);
     w.pslot = a.take<int32_t>(n);
     w.cell = a.take<int32_t>(n);
     w.ccnt = a.take<int32_t>(n + 1);

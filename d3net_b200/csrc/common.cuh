@@ -137,8 +137,9 @@ int radix_sort_pairs(const uint32_t *keys_src, const uint32_t *vals_src, uint32_
 // slot's key (-1 empty), slot_gid[s] = its group id.
 struct GroupTable {
     int32_t *slot_rep;  // [cap]
-    int32_t *slot_gid;  // [cap]  (min point index while building, group id afterwards)
+    int32_t *slot_gid;  // [cap]  (min point index while building, group id afterwards; 0x7fffffff = empty slot)
     uint32_t cap;
+    int4 *slot_key;     // [cap] or null: the slot's key itself, for lookups that should not chase slot_rep -> keys[]
 };
 uint32_t group_table_cap(int64_t n);
 int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot /*[n] scratch*/,
@@ -147,6 +148,15 @@ int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot /*[n]
 
 __device__ __forceinline__ int group_lookup(const int4 *keys, const GroupTable &tab, int4 k) {
     unsigned h = hash4(k.x, k.y, k.z, k.w) & (tab.cap - 1);
+    if (tab.slot_key) {                 // key and id of a slot are two independent loads: one memory round trip per probe
+        for (;;) {
+            const int gid = __ldg(tab.slot_gid + h);
+            const int4 o = __ldg(tab.slot_key + h);
+            if (gid == 0x7fffffff) return -1;
+            if (o.x == k.x && o.y == k.y && o.z == k.z && o.w == k.w) return gid;
+            h = (h + 1) & (tab.cap - 1);
+        }
+    }
     for (;;) {
         int rep = tab.slot_rep[h];
         if (rep < 0) return -1;

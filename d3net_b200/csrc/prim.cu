@@ -309,12 +309,16 @@ __global__ void k_group_flag(const int32_t *__restrict__ pslot, const int32_t *_
 // first points publish their rank (= group id) into the slot; needs the pre-scan flags, which after
 // the in-place scan are recovered as rank[i+1] - rank[i] (or total - rank[n-1])
 __global__ void k_group_publish(const int32_t *__restrict__ pslot, int32_t *slot_min, const int32_t *__restrict__ rank,
-                                const int64_t *__restrict__ total, int64_t n) {
+                                const int64_t *__restrict__ total, int64_t n, const int4 *__restrict__ keys,
+                                int4 *__restrict__ slot_key) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     int r = rank[i];
     int next = (i + 1 < n) ? rank[i + 1] : (int)*total;
-    if (next != r) slot_min[pslot[i]] = r;
+    if (next != r) {
+        slot_min[pslot[i]] = r;
+        if (slot_key) slot_key[pslot[i]] = keys[i];
+    }
 }
 
 __global__ void k_group_assign(const int32_t *__restrict__ pslot, const int32_t *__restrict__ slot_gid, int64_t n,
@@ -339,7 +343,7 @@ int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot, int3
     k_group_insert<<<nb, T, 0, st>>>(keys, n, tab.slot_rep, tab.slot_gid, tab.cap, pslot);
     k_group_flag<<<nb, T, 0, st>>>(pslot, tab.slot_gid, n, gid);
     PG_TRY(scan_exclusive_i32(gid, gid, n, nGroups, scan_tmp, st));
-    k_group_publish<<<nb, T, 0, st>>>(pslot, tab.slot_gid, gid, nGroups, n);
+    k_group_publish<<<nb, T, 0, st>>>(pslot, tab.slot_gid, gid, nGroups, n, keys, tab.slot_key);
     k_group_assign<<<nb, T, 0, st>>>(pslot, tab.slot_gid, n, gid, cnt);
     PG_LAUNCH_CHECK();
     return PG_OK;

@@ -27,6 +27,7 @@ static VoxWs vox_layout(void *ws, size_t ws_bytes, int64_t N) {
     w.keys = a.take<int4>(n);
     w.tab.slot_rep = a.take<int32_t>(w.tab.cap);
     w.tab.slot_gid = a.take<int32_t>(w.tab.cap);
+    w.tab.slot_key = nullptr;                     // nobody looks voxels up by key afterwards
     w.pslot = a.take<int32_t>(n);
     w.cnt = a.take<int32_t>(n + 1);
     w.voff = a.take<int32_t>(n + 1);
