@@ -145,44 +145,54 @@ def clusters_voxelization(ops, clusters_idx, clusters_offset, feats, coords, ful
 
 
 _pool = None
-
-
-def _run_overlapped(fa, fb):
-    """fa() on a side stream in a worker thread, fb() on another side stream in this thread; both start after the
-    current stream's pending work and the current stream continues after both."""
-    global _pool
-    if _pool is None:
-        from concurrent.futures import ThreadPoolExecutor
-        _pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pg-chain")
-    dev = torch.cuda.current_device()
-    main = torch.cuda.current_stream()
-    sa, sb = _side_streams(dev)
-    sa.wait_stream(main)
-    sb.wait_stream(main)
-
-    def in_stream(fn, st):
-        torch.cuda.set_device(dev)
-        with torch.cuda.stream(st):
-            r = fn()
-        return r
-
-    fut = _pool.submit(in_stream, fa, sa)
-    rb = in_stream(fb, sb)
-    ra = fut.result()
-    main.wait_stream(sa)
-    main.wait_stream(sb)
-    for t in ra + rb:
-        t.record_stream(main)
-    return ra, rb
-
-
 _streams = {}
 
 
-def _side_streams(dev):
-    if dev not in _streams:
-        _streams[dev] = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
-    return _streams[dev]
+class _Fork:
+    """Independent parts of one step on side streams: ``spawn(fn)`` runs fn in a worker thread on a side stream of its own,
+    ``here(fn)`` in this thread on another; both start after the work the current stream holds at that moment, and
+    ``join()`` makes the current stream wait for all of them.  Each fn returns a tuple of tensors."""
+
+    def __init__(self, dev):
+        global _pool
+        if _pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+            _pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="pg-chain")
+        if dev not in _streams:
+            _streams[dev] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
+        self.dev, self.main, self.side, self.used, self.jobs = dev, torch.cuda.current_stream(), _streams[dev], 0, []
+
+    def _in_stream(self, fn, st):
+        torch.cuda.set_device(self.dev)
+        with torch.cuda.stream(st):
+            return fn()
+
+    def _next(self):
+        st = self.side[self.used]
+        self.used += 1
+        st.wait_stream(self.main)
+        return st
+
+    def spawn(self, fn):
+        st = self._next()
+        self.jobs.append((st, _pool.submit(self._in_stream, fn, st)))
+        return len(self.jobs) - 1
+
+    def here(self, fn):
+        st = self._next()
+        self.jobs.append((st, self._in_stream(fn, st)))
+        return len(self.jobs) - 1
+
+    def join(self):
+        res = []
+        for st, r in self.jobs:
+            r = r if isinstance(r, tuple) else r.result()
+            self.main.wait_stream(st)
+            for t in r:
+                if torch.is_tensor(t):
+                    t.record_stream(self.main)
+            res.append(r)
+        return res
 
 
 def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=False, overlap=True, fused_cluster=False):
@@ -193,8 +203,9 @@ def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=Fa
     [nInst], n_scenes.  Returns a dict of the tensors the rest of the detector consumes.
     ``fused_cluster``: each ballquery_batch_p + bfs_cluster pair as ONE op (pointgroup_ops.ballquery_bfs_cluster: the
     neighbour lists are never materialised where the clustering does not read them) -- a caller edit, like ``fused_glue``.
-    ``overlap`` (CUDA only; ignored while a timer or a trace is attached): the two independent clusterings are issued
-    from two host threads on two streams -- scheduling only, the op calls and their results are the same."""
+    ``overlap`` (CUDA only; ignored while a timer or a trace is attached): the input cloud's voxelisation and the two
+    clusterings, which share inputs and nothing else, are issued from three host threads on three streams -- scheduling
+    only, the op calls and their results are the same."""
     timer = timer or _NoTimer()
     dev = batch["locs"].device
     B = int(batch["n_scenes"])
@@ -202,19 +213,34 @@ def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=Fa
         rand6 = torch.full((6,), 0.5, device=dev)
     out = {}
 
+    # The three independent parts of the step -- the input cloud's voxelisation and the two clusterings -- share their
+    # inputs and nothing else, and each needs the host for its exact output sizes.  Issued from three host threads on three
+    # streams, one's kernels fill the others' synchronisation bubbles and launch-bound stretches.  Same calls, same
+    # results -- scheduling only (bench.py reports the one-stream schedule beside it).
+    fork = _Fork(dev) if (overlap and dev.type == "cuda" and timer.enabled is False and trace is None) else None
+
     # ---- collate-side voxelisation of the input cloud (pipeline.py:992, pointgroup.py:472)
-    t = timer.start("voxelization_idx(scene)")
-    voxel_locs, p2v_map, v2p_map = ops.voxelization_idx(batch["locs_scaled"], B, scenes.SCORE_MODE)
-    timer.stop(t)
-    if trace is not None:
-        trace["voxelization_idx(scene)"] = (batch["locs_scaled"], B, voxel_locs, p2v_map, v2p_map)
-    t = timer.start("voxelization(scene)")
-    voxel_feats = ops.voxelization(batch["feats"], v2p_map, scenes.SCORE_MODE)
-    timer.stop(t)
-    if trace is not None:
-        trace["voxelization(scene)"] = (batch["feats"], v2p_map, voxel_feats)
-    out["voxel_locs"], out["voxel_feats"], out["p2v_map"] = voxel_locs, voxel_feats, p2v_map
-    out["v2p_map_numel"] = v2p_map.numel()
+    def voxelize_scene():
+        t = timer.start("voxelization_idx(scene)")
+        voxel_locs, p2v_map, v2p_map = ops.voxelization_idx(batch["locs_scaled"], B, scenes.SCORE_MODE)
+        timer.stop(t)
+        if trace is not None:
+            trace["voxelization_idx(scene)"] = (batch["locs_scaled"], B, voxel_locs, p2v_map, v2p_map)
+        t = timer.start("voxelization(scene)")
+        voxel_feats = ops.voxelization(batch["feats"], v2p_map, scenes.SCORE_MODE)
+        timer.stop(t)
+        if trace is not None:
+            trace["voxelization(scene)"] = (batch["feats"], v2p_map, voxel_feats)
+        return voxel_locs, voxel_feats, p2v_map, v2p_map
+
+    def keep_scene(r):
+        out["voxel_locs"], out["voxel_feats"], out["p2v_map"] = r[0], r[1], r[2]
+        out["v2p_map_numel"] = r[3].numel()
+
+    if fork is not None:
+        fork.spawn(voxelize_scene)
+    else:
+        keep_scene(voxelize_scene())
 
     # ---- clustering on the predicted-object points (pointgroup.py:284-316)
     semantic_preds = batch["semantic_preds"]
@@ -273,12 +299,11 @@ def proposal_chain(ops, batch, rand6=None, timer=None, trace=None, fused_glue=Fa
         pidx[:, 1] = object_idxs[pidx[:, 1].long()].int()
         return pidx, poff
 
-    # The two clusterings (model/pointgroup.py:296-298 and :304-306) share their inputs and nothing else.  Each needs
-    # the host twice (exact output sizes); issued from two host threads on two streams, one's kernels fill the other's
-    # synchronisation bubbles and launch-bound stretches.  Same calls, same results -- scheduling only.
-    if overlap and coords_.is_cuda and timer.enabled is False and trace is None:
-        (proposals_idx_shift, proposals_offset_shift), (proposals_idx, proposals_offset) = _run_overlapped(
-            cluster_shift, cluster_raw)
+    if fork is not None:                  # model/pointgroup.py:296-298 and :304-306
+        fork.spawn(cluster_raw)
+        fork.here(cluster_shift)
+        scene_r, (proposals_idx, proposals_offset), (proposals_idx_shift, proposals_offset_shift) = fork.join()
+        keep_scene(scene_r)
     else:
         proposals_idx_shift, proposals_offset_shift = cluster_shift()
         proposals_idx, proposals_offset = cluster_raw()

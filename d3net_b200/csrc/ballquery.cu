@@ -27,6 +27,7 @@
 
 #include "common.cuh"
 #include "ballquery.cuh"
+#include "scan.cuh"
 
 namespace pg {
 
@@ -68,7 +69,8 @@ __global__ void k_bq_scatter(const int32_t *__restrict__ cell, const int32_t *__
     if (i >= n) return;
     const int c = __ldg(cell + i);
     sorted_pt[__ldg(cstart + c) + atomicAdd(cursor + c, 1)] = (uint32_t)i;
-    if (cmin[c] > (uint32_t)i) atomicMin(cmin + c, (uint32_t)i);
+    // the smallest index is kept as the largest complement, so that all three arrays start from zero (one memset)
+    if (cmin[c] < ~(uint32_t)i) atomicMax(cmin + c, ~(uint32_t)i);
     if (cmax[c] < (uint32_t)i) atomicMax(cmax + c, (uint32_t)i);
 }
 
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(256) k_bq_neighbours(const int4 *__restrict__ 
         }
         if (bq_is_dense(cnt, ccnt[c])) {          // a dense cell: the index range of its candidates
             uint32_t head = 0xffffffffu, tail = 0u;
-            if (id >= 0) { head = __ldg(cmin + id); tail = __ldg(cmax + id); }
+            if (id >= 0) { head = ~__ldg(cmin + id); tail = __ldg(cmax + id); }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 head = min(head, __shfl_xor_sync(0xffffffffu, head, o));
@@ -135,21 +137,50 @@ __device__ __forceinline__ bool bq_hit(float ox, float oy, float oz, float4 c, f
     return d2 < r2;
 }
 
-__global__ void k_bq_clear_tail(int32_t *kc, const int64_t *__restrict__ nCells, int32_t n1) {
-    const int64_t nc = *nCells;
-    for (int64_t c = nc + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n1; c += (int64_t)gridDim.x * blockDim.x) kc[c] = 0;
-}
-
+// ---- scans with their producers / consumers fused in (scan.cuh) -----------------------------------------------------
+// candidate-list starts: the scan runs over n + 1 entries, kc beyond nCells counts (and is left) as 0
+struct CandLoad {
+    const int32_t *kc;
+    const int64_t *nCells;
+    __device__ int operator()(int64_t c) const { return c < *nCells ? kc[c] : 0; }
+};
+struct CandStore {
+    int32_t *kc, *cand_start;
+    const int64_t *nCells;
+    __device__ void operator()(int64_t c, int start, int) const {
+        cand_start[c] = start;
+        if (c >= *nCells) kc[c] = 0;
+    }
+};
 // Hit masks: one bit per (query, candidate) pair, 32 candidates per word, laid out per cell as
 // [block of 32 candidates][query of the cell].
-__global__ void k_bq_mask_sizes(const int32_t *__restrict__ ccnt, const int32_t *__restrict__ kc,
-                                const int64_t *__restrict__ nCells, int32_t n1, int32_t *__restrict__ words) {
-    const int64_t nc = *nCells;
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < n1; c += (int64_t)gridDim.x * blockDim.x) {
-        long long w = c < nc ? (long long)ccnt[c] * ((kc[c] + 31) >> 5) : 0;
-        words[c] = w > 0x7fffffffLL ? 0x7fffffff : (int32_t)w;     // saturates: the int64 total then exceeds the cap
+struct MaskLoad {
+    const int32_t *ccnt, *kc;
+    const int64_t *nCells;
+    __device__ int operator()(int64_t c) const {
+        const long long w = c < *nCells ? (long long)ccnt[c] * ((kc[c] + 31) >> 5) : 0;
+        return w > 0x7fffffffLL ? 0x7fffffff : (int32_t)w;       // saturates: the int64 total then exceeds the cap
     }
-}
+};
+struct MaskStore {
+    int32_t *mbase;
+    __device__ void operator()(int64_t c, int start, int) const { mbase[c] = start; }
+};
+// start_len rows from the per-query counts (query order) and their exclusive scan
+struct CountLoad {
+    const int32_t *counts;
+    __device__ int operator()(int64_t q) const { return counts[q]; }
+};
+struct StartLenStore {
+    const uint32_t *sorted_pt;
+    int2 *start_len;
+    int32_t *qpos;
+    __device__ void operator()(int64_t q, int start, int len) const {
+        const uint32_t k = sorted_pt[q];
+        start_len[k] = make_int2(start, len);
+        qpos[k] = (int32_t)q;
+    }
+};
 
 // ---- sparse cells: one warp per cell, candidates sorted in registers ------------------------------
 // Striped layout: register r of lane l holds position r * 32 + l, so after the sort register r IS
@@ -652,18 +683,6 @@ __global__ void __launch_bounds__(kTestThreads, 8) k_bq_test_dense(
     }
 }
 
-// start_len rows from the per-query counts and their exclusive scan (both in query order)
-__global__ void k_bq_start_len(const uint32_t *__restrict__ sorted_pt, const int32_t *__restrict__ counts,
-                               const int32_t *__restrict__ starts, int32_t n, int2 *__restrict__ start_len,
-                               int32_t *__restrict__ qpos) {
-    int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q < n) {
-        const uint32_t k = sorted_pt[q];
-        start_len[k] = make_int2(starts[q], counts[q]);
-        qpos[k] = q;
-    }
-}
-
 // ---- fill -------------------------------------------------------------------------------------------
 constexpr int kFillQ = 4;
 constexpr int kFillShortK = kSmallK;     // the cells of the warp-per-cell count kernels: at most eight mask words per query
@@ -956,21 +975,18 @@ extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs,
     const double inv_s = (s > 0.0 && isfinite(s)) ? 1.0 / s : 0.0;   // r = 0 / inf / NaN: one cell per scene
     PG_CUDA(cudaMemsetAsync(w.scalars, 0, 8 * sizeof(int64_t), st));
     k_bq_keys<<<(unsigned)div_up(n, 256), 256, 0, st>>>(xyz, batch_idxs, n, inv_s, w.keys);
-    PG_TRY(group_int4(w.keys, n, w.tab, w.pslot, w.cell, w.ccnt, w.scalars, w.scan_tmp, st));
-    PG_CUDA(cudaMemsetAsync(w.ccnt + n, 0, sizeof(int32_t), st));
+    PG_TRY(group_int4(w.keys, n, w.tab, w.pslot, w.cell, w.ccnt, w.scalars, w.scan_tmp, st, nullptr, (int64_t)n + 1));
     PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
-    uint32_t *sorted_pt = w.vA, *cmin = w.kA, *cmax = w.kB;
-    PG_CUDA(cudaMemsetAsync(w.kb, 0, (size_t)n * sizeof(int32_t), st));          // the cells' cursors (kb is rewritten by count)
-    PG_CUDA(cudaMemsetAsync(cmin, 0xff, (size_t)n * sizeof(uint32_t), st));
-    PG_CUDA(cudaMemsetAsync(cmax, 0, (size_t)n * sizeof(uint32_t), st));
-    k_bq_scatter<<<(unsigned)div_up(n, 256), 256, 0, st>>>(w.cell, w.cstart, n, w.kb, sorted_pt, cmin, cmax);
-    const unsigned gsm = kNumSM * 8;
+    // scratch of the scatter, adjacent in the workspace: the cells' cursors, the complement of their smallest and their
+    // largest point index
+    uint32_t *sorted_pt = w.kA, *cmin = w.kB, *cmax = w.vB;
+    int32_t *cursor = reinterpret_cast<int32_t *>(w.vA);
+    PG_TRY(fill_u32(cursor, 0u, ((size_t)((char *)w.vB - (char *)w.vA) + align_up((size_t)n * 4)) / 4, st));   // to the padded end of vB
+    k_bq_scatter<<<(unsigned)div_up(n, 256), 256, 0, st>>>(w.cell, w.cstart, n, cursor, sorted_pt, cmin, cmax);
     { PG_KTIME("k_bq_neighbours", st);
     k_bq_neighbours<<<kNumSM * PG_RESIDENT(k_bq_neighbours, 256, 0) * 2, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense, cmin, cmax, w.crange); }
-    k_bq_clear_tail<<<gsm, 256, 0, st>>>(w.kc, w.scalars, n + 1);   // kc beyond nCells must scan as 0
-    PG_TRY(scan_exclusive_i32(w.kc, w.cand_start, (int64_t)n + 1, w.scalars + 1, w.scan_tmp, st));
-    k_bq_mask_sizes<<<gsm, 256, 0, st>>>(w.ccnt, w.kc, w.scalars, n + 1, w.mbase);
-    PG_TRY(scan_exclusive_i32(w.mbase, w.mbase, (int64_t)n + 1, w.scalars + 6, w.scan_tmp, st));
+    PG_TRY(scan_fused(CandLoad{w.kc, w.scalars}, CandStore{w.kc, w.cand_start, w.scalars}, (int64_t)n + 1, w.scalars + 1, w.scan_tmp, st));
+    PG_TRY(scan_fused(MaskLoad{w.ccnt, w.kc, w.scalars}, MaskStore{w.mbase}, (int64_t)n + 1, w.scalars + 6, w.scan_tmp, st));
     PG_LAUNCH_CHECK();
     return PG_OK;
 }
@@ -1014,9 +1030,8 @@ extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int
     k_bq_test_dense<<<kNumSM * PG_RESIDENT(k_bq_test_dense, kTestThreads, 0), kTestThreads, 0, st>>>(
         xyz, sorted_pt, w.cstart, w.ccnt, w.kc, w.mbase, w.dense, w.dbase, w.cand_xy, w.cand_z, w.scalars, masks, mask_cap, r2,
         w.counts, w.kb); }
-    // starts (reuse pslot) in query order, then the interleaved (start, len) rows per point
-    PG_TRY(scan_exclusive_i32(w.counts, w.pslot, n, w.scalars + 2, w.scan_tmp, st));
-    k_bq_start_len<<<(unsigned)div_up(n, 256), 256, 0, st>>>(sorted_pt, w.counts, w.pslot, n, (int2 *)start_len, w.qpos);
+    // starts in query order, written straight into the interleaved (start, len) rows per point
+    PG_TRY(scan_fused(CountLoad{w.counts}, StartLenStore{sorted_pt, (int2 *)start_len, w.qpos}, n, w.scalars + 2, w.scan_tmp, st));
     PG_LAUNCH_CHECK();
     int64_t back[5] = {0, 0, 0, 0, 0};               // scalars [2] total neighbours ... [6] mask words
     PG_CUDA(cudaMemcpyAsync(back, w.scalars + 2, sizeof(back), cudaMemcpyDeviceToHost, st));

@@ -70,8 +70,8 @@ inline BqWs bq_layout(void *ws, size_t ws_bytes, int64_t n_) {
 }
 
 // the points grouped by cell (cell c: sorted_pt[cstart[c] .. cstart[c] + ccnt[c]), in no particular order inside a cell);
-// this is also the QUERY order.  kA / kB hold the smallest / largest point index of every cell.
-inline const uint32_t *bq_sorted(const BqWs &w, int32_t) { return w.vA; }
+// this is also the QUERY order.
+inline const uint32_t *bq_sorted(const BqWs &w, int32_t) { return w.kA; }
 
 // Lazy lists (cluster.cu's fused path): the neighbour lists stay in the form the count phase left them in -- one bit per
 // (query, candidate) plus every cell's merged candidate indices -- and are only turned into index lists where the

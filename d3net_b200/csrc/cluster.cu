@@ -25,6 +25,7 @@
 // Both checks ride along in the verify sweep and need no extra memory traffic.
 #include "common.cuh"
 #include "ballquery.cuh"
+#include "scan.cuh"
 
 namespace pg {
 
@@ -669,26 +670,31 @@ __global__ void k_cl_label(uint2 *pl, int32_t *root, int32_t *lab, int32_t N, in
     if (on && (peers & lanemask_lt()) == 0) atomicAdd(&size[l], __popc(peers));
 }
 
-// keep[l] = 1 when l is a label with >= threshold points (written into cid for the scan)
-__global__ void k_cl_keep(const uint32_t *__restrict__ key0, const int32_t *__restrict__ size, int32_t N, int32_t threshold,
-                          int32_t *__restrict__ cid) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N) return;
-    const int n = size[v];
-    cid[v] = (key0[v] == (uint32_t)v && n > 0 && n >= threshold) ? 1 : 0;
-}
-
-// cluster sizes in cluster order + totals
-__global__ void k_cl_sizes(const int32_t *__restrict__ size, const int32_t *__restrict__ cid, int32_t N,
-                           int32_t *__restrict__ csize, unsigned long long *scalars) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N) return;
-    const int c = cid[v], next = cid[v + 1];   // cid has N+1 entries after the scan (last = total)
-    if (next != c) {
-        csize[c] = size[v];
-        atomicAdd(&scalars[5], (unsigned long long)size[v]);
+// keep -> scan -> sizes as one pass (scan.cuh): a label l with >= threshold points is a cluster; its exclusive prefix is
+// the cluster's number; cid[0..N] keeps the prefixes (cid[N] = nCluster) for k_cl_keys, the kept labels write their size
+// into csize in cluster order and add it to the member total.
+struct KeepLoad {
+    const uint32_t *key0;
+    const int32_t *size;
+    int32_t N, threshold;
+    __device__ int operator()(int64_t v) const {
+        if (v >= N) return 0;
+        const int n = size[v];
+        return (key0[v] == (uint32_t)v && n > 0 && n >= threshold) ? 1 : 0;
     }
-}
+};
+struct SizesStore {
+    const int32_t *size;
+    int32_t *cid, *csize;
+    unsigned long long *scalars;
+    __device__ void operator()(int64_t v, int c, int keep) const {
+        cid[v] = c;
+        if (keep) {
+            csize[c] = size[v];
+            atomicAdd(&scalars[5], (unsigned long long)size[v]);
+        }
+    }
+};
 
 // sort key per point: cluster id, or nCluster for points of dropped components (they sort last)
 __global__ void k_cl_keys(const uint32_t *__restrict__ key0, const int32_t *__restrict__ cid, int32_t N, int32_t nCluster,
@@ -746,7 +752,7 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
     const bool wide = nActive / N >= 12;          // lanes per neighbour list: 32 for long lists, 8 for short
     const unsigned eg = kNumSM * 8;
     PG_CUDA(cudaMemsetAsync(w.scalars, 0, 12 * sizeof(unsigned long long), st));
-    PG_CUDA(cudaMemsetAsync(w.size, 0, ((size_t)N + 1) * sizeof(int32_t), st));
+    PG_TRY(fill_u32(w.size, 0u, (size_t)N + 1, st));
     // sweep order = ascending segment start, on the top 16 bits of the position (two radix passes)
     int abits = 0;
     while ((1ll << abits) <= nActive) abits++;
@@ -869,10 +875,8 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
         { PG_KTIME("k_cl_label", st);
         if (find_in_label) k_cl_label<true><<<nb, 256, 0, st>>>(w.pl, w.root, w.lab, N, w.size, w.key0);
         else k_cl_label<false><<<nb, 256, 0, st>>>(w.pl, w.root, w.lab, N, w.size, w.key0); }
-        k_cl_keep<<<nb, 256, 0, st>>>(w.key0, w.size, N, threshold, w.cid);
-        PG_CUDA(cudaMemsetAsync(w.cid + N, 0, sizeof(int32_t), st));
-        PG_TRY(scan_exclusive_i32(w.cid, w.cid, (int64_t)N + 1, (int64_t *)(w.scalars + 4), w.scan_tmp, st));
-        k_cl_sizes<<<nb, 256, 0, st>>>(w.size, w.cid, N, w.csize, w.scalars);
+        PG_TRY(scan_fused(KeepLoad{w.key0, w.size, N, threshold}, SizesStore{w.size, w.cid, w.csize, (unsigned long long *)w.scalars},
+                          (int64_t)N + 1, (int64_t *)(w.scalars + 4), w.scan_tmp, st));
         PG_LAUNCH_CHECK();
         PG_CUDA(cudaMemcpyAsync(all, w.scalars, sizeof(all), cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
@@ -893,7 +897,7 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
             find_in_label = false;
             PG_TRY(settle_host(all[2]));
             if (lists_needed) { *need_lists = 1; return PG_OK; }
-            PG_CUDA(cudaMemsetAsync(w.size, 0, ((size_t)N + 1) * sizeof(int32_t), st));
+            PG_TRY(fill_u32(w.size, 0u, (size_t)N + 1, st));
             PG_CUDA(cudaMemsetAsync(w.scalars + 4, 0, 2 * sizeof(unsigned long long), st));
             PG_TRY(finish());
         }

@@ -122,6 +122,9 @@ size_t scan_tmp_count(int64_t n);
 int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, int64_t *total, int64_t *tmp,
                        cudaStream_t st);
 
+// count 32-bit words of `value` at ptr: a kernel above 1 MB (see prim.cu), cudaMemsetAsync below
+int fill_u32(void *ptr, uint32_t value, size_t count, cudaStream_t st);
+
 // Stable LSD radix sort of (key, value) pairs on the low `bits` bits of the key (8-bit digits).
 // Pass 0 reads (keys_src, vals_src) -- vals_src == nullptr means "values are 0..n-1" -- and the
 // passes ping-pong between the A and B buffers, so the source arrays are never written.
@@ -137,14 +140,16 @@ int radix_sort_pairs(const uint32_t *keys_src, const uint32_t *vals_src, uint32_
 // slot's key (-1 empty), slot_gid[s] = its group id.
 struct GroupTable {
     int32_t *slot_rep;  // [cap]
-    int32_t *slot_gid;  // [cap]  (min point index while building, group id afterwards; 0x7fffffff = empty slot)
+    int32_t *slot_gid;  // [cap]  (min point index while building, group id afterwards; -1 = empty slot)
     uint32_t cap;
     int4 *slot_key;     // [cap] or null: the slot's key itself, for lookups that should not chase slot_rep -> keys[]
 };
 uint32_t group_table_cap(int64_t n);
+// cnt_max (optional, device, zeroed by the caller): the largest group size.  cnt_len: how many entries of cnt to zero
+// (>= n; callers that scan cnt over n + 1 entries pass n + 1).
 int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot /*[n] scratch*/,
                int32_t *gid /*[n]*/, int32_t *cnt /*[n]*/, int64_t *nGroups, int64_t *scan_tmp,
-               cudaStream_t st);
+               cudaStream_t st, int64_t *cnt_max = nullptr, int64_t cnt_len = 0);
 
 __device__ __forceinline__ int group_lookup(const int4 *keys, const GroupTable &tab, int4 k) {
     unsigned h = hash4(k.x, k.y, k.z, k.w) & (tab.cap - 1);
@@ -152,7 +157,7 @@ __device__ __forceinline__ int group_lookup(const int4 *keys, const GroupTable &
         for (;;) {
             const int gid = __ldg(tab.slot_gid + h);
             const int4 o = __ldg(tab.slot_key + h);
-            if (gid == 0x7fffffff) return -1;
+            if (gid < 0) return -1;
             if (o.x == k.x && o.y == k.y && o.z == k.z && o.w == k.w) return gid;
             h = (h + 1) & (tab.cap - 1);
         }

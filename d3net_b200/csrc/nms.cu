@@ -217,7 +217,7 @@ extern "C" int pg_pick_masks(const int32_t *proposals_idx, const int32_t *propos
     PG_CHECK_ARG(proposals_idx && proposals_offset && pick && out && ws, "null pointer");
     unsigned long long *d_bad = (unsigned long long *)ws;          // 8 bytes: out-of-range flag
     PG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), st));
-    PG_CUDA(cudaMemsetAsync(out, 0, (size_t)nPick * (size_t)N * sizeof(int32_t), st));
+    PG_TRY(fill_u32(out, 0u, (size_t)nPick * (size_t)N, st));
     k_pick_masks<<<(unsigned)(nPick < kNumSM * 8 ? nPick : kNumSM * 8), 256, 0, st>>>((const int2 *)proposals_idx, proposals_offset, pick,
                                                                                    nPick, nProposal, N, out, d_bad);
     PG_LAUNCH_CHECK();

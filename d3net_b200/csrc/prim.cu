@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "scan.cuh"
 
 namespace pg {
 
@@ -25,40 +26,8 @@ void set_error(const char *fmt, ...) {
 const char *last_error() { return g_err; }
 
 // ---------------------------------------------------------------------------------------------
-// exclusive scan (single pass, decoupled look-back)
+// exclusive scan of a plain array (single pass, decoupled look-back: scan.cuh), 16 items per thread through int4 loads
 // ---------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 256;
-constexpr int kScanRounds = 16;
-constexpr int kScanTile = kScanThreads * kScanRounds;
-
-// inclusive block scan of one int per thread; returns inclusive value, *block_total = sum over block
-__device__ __forceinline__ int block_scan_incl(int v, int *warp_tot /*[32] smem*/, int *block_total) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int t = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += t;
-    }
-    if (lane == 31) warp_tot[w] = v;
-    __syncthreads();
-    int before = 0, all = 0;
-    for (int i = 0; i < nw; i++) {
-        int t = warp_tot[i];
-        if (i < w) before += t;
-        all += t;
-    }
-    __syncthreads();
-    *block_total = all;
-    return v + before;
-}
-
-// Single pass with decoupled look-back: a block takes the next tile (ticket from an atomic counter, so
-// every earlier tile is already running or done), scans it, publishes its aggregate, and warp 0 walks
-// back over the predecessors' published words -- 32 at a time -- until it meets an inclusive prefix.
-// One 64-bit word per tile: [63:62] 0 = nothing yet, 1 = aggregate, 2 = inclusive prefix; [61:0] value.
-// tmp[0] is the ticket counter, tmp[1 + t] tile t's word; the launcher zeroes them.
-constexpr unsigned long long kSpValueMask = (1ULL << 62) - 1;
-
 __global__ void __launch_bounds__(kScanThreads) k_scan_onepass(const int32_t *__restrict__ in, int32_t *__restrict__ out,
                                                                int64_t n, unsigned long long *tmp, int64_t *__restrict__ total,
                                                                int aligned) {
@@ -66,9 +35,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_onepass(const int32_t *__
     __shared__ long long s_tile, s_prefix;
     if (threadIdx.x == 0) s_tile = (long long)atomicAdd(tmp, 1ULL);
     __syncthreads();
-    const int64_t t = s_tile;
-    volatile unsigned long long *state = tmp + 1;
-    const int64_t base = t * kScanTile + (int64_t)threadIdx.x * kScanRounds;
+    const int64_t base = (int64_t)s_tile * kScanTile + (int64_t)threadIdx.x * kScanRounds;
     int v[kScanRounds];
     const bool full = aligned && base + kScanRounds <= n;
     if (full) {
@@ -87,40 +54,10 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_onepass(const int32_t *__
     for (int k = 0; k < kScanRounds; k++) { const int q = v[k]; v[k] = tsum; tsum += q; }
     int tot;
     const int incl = block_scan_incl(tsum, warp_tot, &tot);
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        long long prefix = 0;
-        if (t == 0) {
-            if (lane == 0) state[0] = (2ULL << 62) | (unsigned long long)(long long)tot;
-        } else {
-            if (lane == 0) state[t] = (1ULL << 62) | ((unsigned long long)(long long)tot & kSpValueMask);
-            int64_t hi = t - 1;                       // the newest predecessor not yet added
-            for (;;) {
-                const int64_t k = hi - lane;
-                unsigned long long w = (2ULL << 62);  // below tile 0: an inclusive prefix of 0
-                if (k >= 0) w = state[k];
-                const unsigned flag = (unsigned)(w >> 62);
-                const unsigned empty = __ballot_sync(0xffffffffu, flag == 0u);
-                const unsigned incl_m = __ballot_sync(0xffffffffu, flag == 2u);
-                // usable lanes: from lane 0 up to the first inclusive word, all of them published
-                const int stop = incl_m ? __ffs((int)incl_m) - 1 : 31;
-                if (empty & ((stop == 31 ? 0xffffffffu : ((2u << stop) - 1u)))) continue;   // somebody in range is not there yet
-                long long val = (lane <= stop) ? (long long)(w & kSpValueMask) : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
-                prefix += val;
-                if (incl_m) break;
-                hi -= 32;
-            }
-            if (lane == 0) state[t] = (2ULL << 62) | ((unsigned long long)(prefix + tot) & kSpValueMask);
-        }
-        if (lane == 0) {
-            s_prefix = prefix;
-            if (total && (t + 1) * (int64_t)kScanTile >= n) *total = prefix + tot;
-        }
-    }
-    __syncthreads();
-    const int off = (int)s_prefix + incl - tsum;
+    int64_t t;
+    const long long prefix = scan_tile_prefix(tmp, tot, &t, &s_tile, &s_prefix);
+    if (total && threadIdx.x == 0 && (t + 1) * (int64_t)kScanTile >= n) *total = prefix + tot;
+    const int off = (int)prefix + incl - tsum;
     if (full) {
         int4 *q = reinterpret_cast<int4 *>(out + base);
 #pragma unroll
@@ -151,45 +88,59 @@ int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, int64_t *tota
 }
 
 // ---------------------------------------------------------------------------------------------
-// stable LSD radix sort, 8-bit digits: histogram -> scan -> ranked scatter per pass
+// stable LSD radix sort, 8-bit digits, one kernel per pass ("onesweep"): the digit histograms of ALL passes are taken in
+// one sweep over the keys up front; a pass then ranks its tile, publishes the tile's 256 digit counts, and finds its
+// global offsets by decoupled look-back over the earlier tiles' published counts (chained scan, one thread per digit)
+// instead of a histogram kernel + a device-wide scan per pass.
 // ---------------------------------------------------------------------------------------------
 constexpr int kRadixThreads = 256;
 constexpr int kRadixRounds = 8;
 constexpr int kRadixTile = kRadixThreads * kRadixRounds;
+constexpr int kRadixMaxPasses = 4;
+// scratch layout (int32 words): [0, 4*256) global digit counts per pass; [4*256, 4*256 + 16) tile tickets per pass;
+// then per pass nb * 256 look-back words: [31:30] 0 = nothing yet, 1 = the tile's count, 2 = inclusive prefix; [29:0] value
+constexpr int kRadixHead = kRadixMaxPasses * 256 + 16;
 
-__global__ void __launch_bounds__(kRadixThreads) k_radix_hist(const uint32_t *__restrict__ keys, int64_t n,
-                                                              int shift, int32_t *__restrict__ hist, int nb) {
-    __shared__ int h[256];
-    h[threadIdx.x] = 0;
+__global__ void __launch_bounds__(kRadixThreads) k_radix_hist_all(const uint32_t *__restrict__ keys, int64_t n, int passes,
+                                                                  int32_t *__restrict__ scratch, int64_t state_words) {
+    __shared__ int h[kRadixMaxPasses][256];
+    for (int p = 0; p < passes; p++) h[p][threadIdx.x] = 0;
     __syncthreads();
-    const int64_t base = (int64_t)blockIdx.x * kRadixTile;
-#pragma unroll
-    for (int r = 0; r < kRadixRounds; r++) {
-        int64_t i = base + r * kRadixThreads + threadIdx.x;
-        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t k = keys[i];
+        for (int p = 0; p < passes; p++) atomicAdd(&h[p][(k >> (8 * p)) & 255u], 1);
     }
     __syncthreads();
-    hist[(int64_t)threadIdx.x * nb + blockIdx.x] = h[threadIdx.x];
+    for (int p = 0; p < passes; p++)
+        if (h[p][threadIdx.x]) atomicAdd(&scratch[p * 256 + threadIdx.x], h[p][threadIdx.x]);
+    // the passes' look-back words start from zero
+    int32_t *state = scratch + kRadixHead;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < state_words; i += (int64_t)gridDim.x * blockDim.x) state[i] = 0;
 }
 
 // Each warp owns a contiguous 256-element slice of the tile (8 rounds of 32 consecutive elements), so the stable
 // order inside the tile is (warp, round, lane): a warp ranks its own slice with nothing but warp-level
 // primitives -- `__match_any_sync` groups equal digits, a per-warp counter row in shared memory carries the
-// running count from round to round -- and the block meets only twice per tile: once to turn the eight counter
-// rows into per-warp bases, once before the rows are reused.  Keys, values and ranks stay in registers.
+// running count from round to round.  Keys, values and ranks stay in registers.
 __global__ void __launch_bounds__(kRadixThreads)
-k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
-                uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
-                const int32_t *__restrict__ hist, int nb) {
+k_radix_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
+                 uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
+                 const int32_t *__restrict__ ghist, unsigned *ticket, unsigned *state) {
     constexpr int kWarps = kRadixThreads / 32;
-    __shared__ int wcnt[kWarps][256];                 // per-warp digit counts, then exclusive bases across warps
+    __shared__ int wcnt[kWarps][256];                 // per-warp digit counts, then global bases per warp
+    __shared__ int s_scan[32];
+    __shared__ unsigned s_tile;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
-    const int gbase = hist[(int64_t)threadIdx.x * nb + blockIdx.x];   // global base of this tile's run of digit tid
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
 #pragma unroll
     for (int k = 0; k < kWarps; k++) wcnt[k][threadIdx.x] = 0;
-    __syncthreads();
-    const int64_t slice = (int64_t)blockIdx.x * kRadixTile + (int64_t)w * (kRadixRounds * 32);
+    // exclusive scan of the pass's global digit counts: where digit `tid`'s run starts in the output
+    const int gcount = ghist[threadIdx.x];
+    int unused;
+    const int gincl = block_scan_incl(gcount, s_scan, &unused);          // (two block barriers: s_tile is visible after them)
+    const unsigned tile = s_tile;
+    const int64_t slice = (int64_t)tile * kRadixTile + (int64_t)w * (kRadixRounds * 32);
     uint32_t key[kRadixRounds], val[kRadixRounds];
     int rank[kRadixRounds];                           // position inside the warp's slice among equal digits
     unsigned dig[kRadixRounds];
@@ -215,13 +166,29 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
         rank[r] = run + before;
     }
     __syncthreads();
-    {   // digit `tid`: exclusive prefix of the eight warp counts, shifted by the tile's global base
-        int acc = gbase;
+    {   // digit `tid`: the tile's count goes out, the earlier tiles' counts come in, the eight warp counts become bases
+        int c = 0;
+#pragma unroll
+        for (int k = 0; k < kWarps; k++) c += wcnt[k][threadIdx.x];
+        volatile unsigned *st = state + threadIdx.x;
+        int before = 0;
+        if (tile == 0) st[0] = (2u << 30) | (unsigned)c;
+        else {
+            st[(size_t)tile * 256] = (1u << 30) | (unsigned)c;
+            for (int64_t t = (int64_t)tile - 1;; t--) {
+                unsigned wv;
+                do { wv = st[(size_t)t * 256]; } while ((wv >> 30) == 0u);
+                before += (int)(wv & 0x3fffffffu);
+                if ((wv >> 30) == 2u) break;
+            }
+            st[(size_t)tile * 256] = (2u << 30) | (unsigned)(before + c);
+        }
+        int acc = gincl - gcount + before;
 #pragma unroll
         for (int k = 0; k < kWarps; k++) {
-            const int c = wcnt[k][threadIdx.x];
+            const int cw = wcnt[k][threadIdx.x];
             wcnt[k][threadIdx.x] = acc;
-            acc += c;
+            acc += cw;
         }
     }
     __syncthreads();
@@ -235,24 +202,29 @@ k_radix_scatter(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict
     }
 }
 
-size_t radix_tmp_count(int64_t n) { return (size_t)256 * (size_t)div_up(n > 0 ? n : 1, kRadixTile) + 16; }
+size_t radix_tmp_count(int64_t n) { return (size_t)kRadixHead + (size_t)kRadixMaxPasses * 256 * (size_t)div_up(n > 0 ? n : 1, kRadixTile); }
 
 int radix_sort_pairs(const uint32_t *keys_src, const uint32_t *vals_src, uint32_t *keysA, uint32_t *valsA,
                      uint32_t *keysB, uint32_t *valsB, int64_t n, int bits, int32_t *hist, int64_t *scan_tmp,
                      cudaStream_t st, int *result_buf) {
+    (void)scan_tmp;
     *result_buf = 0;
     if (n <= 0) return PG_OK;
     int passes = (bits + 7) / 8;
     if (passes < 1) passes = 1;
+    if (passes > kRadixMaxPasses) passes = kRadixMaxPasses;
     const int nb = (int)div_up(n, kRadixTile);
     uint32_t *k[2] = {keysA, keysB}, *v[2] = {valsA, valsB};
     const uint32_t *kin = keys_src, *vin = vals_src;
+    PG_CUDA(cudaMemsetAsync(hist, 0, (size_t)kRadixHead * sizeof(int32_t), st));
+    const int64_t state_words = (int64_t)passes * 256 * nb;
+    const int hgrid = nb < kNumSM * 8 ? nb : kNumSM * 8;
+    k_radix_hist_all<<<hgrid, kRadixThreads, 0, st>>>(keys_src, n, passes, hist, state_words);
     int dst = 0;
     for (int p = 0; p < passes; p++) {
-        const int shift = 8 * p;
-        k_radix_hist<<<nb, kRadixThreads, 0, st>>>(kin, n, shift, hist, nb);
-        PG_TRY(scan_exclusive_i32(hist, hist, (int64_t)256 * nb, nullptr, scan_tmp, st));
-        k_radix_scatter<<<nb, kRadixThreads, 0, st>>>(kin, vin, k[dst], v[dst], n, shift, hist, nb);
+        k_radix_onesweep<<<nb, kRadixThreads, 0, st>>>(kin, vin, k[dst], v[dst], n, 8 * p, hist + p * 256,
+                                                       reinterpret_cast<unsigned *>(hist) + kRadixMaxPasses * 256 + p,
+                                                       reinterpret_cast<unsigned *>(hist) + kRadixHead + (size_t)p * 256 * nb);
         kin = k[dst];
         vin = v[dst];
         *result_buf = dst;
@@ -271,13 +243,32 @@ uint32_t group_table_cap(int64_t n) {
     return (uint32_t)c;
 }
 
-__global__ void k_group_init(int32_t *__restrict__ slot_rep, int32_t *__restrict__ slot_min, uint32_t cap) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += gridDim.x * blockDim.x) {
-        slot_rep[i] = -1;
-        slot_min[i] = 0x7fffffff;
-    }
+// Large fills run as a kernel: the driver may hand a big cudaMemsetAsync to a copy engine, where it queues behind an
+// upload in flight on another stream (measured: the end-to-end loop lost its copy / compute overlap, 12.6 -> 15.3 ms).
+__global__ void k_fill_u32(uint32_t *__restrict__ p, uint32_t v, size_t count) {
+    const size_t n16 = count / 4;
+    const uint4 q = make_uint4(v, v, v, v);
+    uint4 *p16 = reinterpret_cast<uint4 *>(p);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p16[i] = q;
+    if (blockIdx.x == 0 && threadIdx.x < (count & 3)) p[n16 * 4 + threadIdx.x] = v;
 }
 
+int fill_u32(void *ptr, uint32_t value, size_t count, cudaStream_t st) {
+    if (count == 0) return PG_OK;
+    const bool bytewise = ((value & 0xff) * 0x01010101u) == value;
+    if (bytewise && (count * 4 <= (1u << 20) || ((uintptr_t)ptr & 15u))) {
+        PG_CUDA(cudaMemsetAsync(ptr, (int)(value & 0xff), count * 4, st));
+        return PG_OK;
+    }
+    if ((uintptr_t)ptr & 15u) { set_error("fill_u32: unaligned fill of a non-byte pattern"); return PG_EINVAL; }
+    const size_t want = (count / 4 + 255) / 256 + 1;
+    k_fill_u32<<<(unsigned)(want < (size_t)kNumSM * 16 ? want : (size_t)kNumSM * 16), 256, 0, st>>>((uint32_t *)ptr, value, count);
+    PG_LAUNCH_CHECK();
+    return PG_OK;
+}
+
+// Empty slots: slot_rep = -1, slot_gid = 0xffffffff -- one byte pattern, so one fill initialises the table.  While the
+// table is built slot_gid holds the smallest point index of the slot's group (unsigned atomicMin), afterwards its group id.
 __global__ void k_group_insert(const int4 *__restrict__ keys, int64_t n, int32_t *slot_rep, int32_t *slot_min,
                                uint32_t cap, int32_t *__restrict__ pslot) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -295,56 +286,73 @@ __global__ void k_group_insert(const int4 *__restrict__ keys, int64_t n, int32_t
         if (o.x == k.x && o.y == k.y && o.z == k.z && o.w == k.w) break;
         h = (h + 1) & (cap - 1);
     }
-    atomicMin(&slot_min[h], (int)i);
+    atomicMin(reinterpret_cast<unsigned *>(&slot_min[h]), (unsigned)i);
     pslot[i] = (int)h;
 }
 
-// flag[i] = 1 when i is the first (lowest-index) point of its group
-__global__ void k_group_flag(const int32_t *__restrict__ pslot, const int32_t *__restrict__ slot_min, int64_t n,
-                             int32_t *__restrict__ flag) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flag[i] = (slot_min[pslot[i]] == (int)i) ? 1 : 0;
-}
+// flag -> scan -> publish as ONE pass (scan.cuh): element i's value is "i is the first (lowest-index) point of its
+// group", its exclusive prefix is then the group's id, which the first point writes into the slot.  Reading the flag and
+// overwriting the slot's minimum with the id in the same pass is safe: only point i compares the slot with i, and it
+// does so before it publishes; every other point j > i of the group sees either i or the id r <= i, never j.
+struct GroupFlagLoad {
+    const int32_t *pslot, *slot_min;
+    __device__ int operator()(int64_t i) const { return slot_min[pslot[i]] == (int)i ? 1 : 0; }
+};
+struct GroupPublishStore {
+    const int32_t *pslot;
+    int32_t *slot_min;
+    const int4 *keys;
+    int4 *slot_key;
+    __device__ void operator()(int64_t i, int rank, int flag) const {
+        if (flag) {
+            const int s = pslot[i];
+            slot_min[s] = rank;
+            if (slot_key) slot_key[s] = keys[i];
+        }
+    }
+};
 
-// first points publish their rank (= group id) into the slot; needs the pre-scan flags, which after
-// the in-place scan are recovered as rank[i+1] - rank[i] (or total - rank[n-1])
-__global__ void k_group_publish(const int32_t *__restrict__ pslot, int32_t *slot_min, const int32_t *__restrict__ rank,
-                                const int64_t *__restrict__ total, int64_t n, const int4 *__restrict__ keys,
-                                int4 *__restrict__ slot_key) {
+// every point takes its group's id and counts itself; *cnt_max (optional) receives the largest group size: the
+// increment that completes the fullest group returns its final size, so the maximum over all increments is it
+__global__ void __launch_bounds__(256) k_group_assign(const int32_t *__restrict__ pslot, const int32_t *__restrict__ slot_gid,
+                                                      int64_t n, int32_t *__restrict__ gid, int32_t *__restrict__ cnt,
+                                                      int64_t *cnt_max) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int r = rank[i];
-    int next = (i + 1 < n) ? rank[i + 1] : (int)*total;
-    if (next != r) {
-        slot_min[pslot[i]] = r;
-        if (slot_key) slot_key[pslot[i]] = keys[i];
+    int mine = 0;
+    if (i < n) {
+        int g = slot_gid[pslot[i]];
+        gid[i] = g;
+        mine = atomicAdd(&cnt[g], 1) + 1;
+    }
+    if (cnt_max) {
+        __shared__ int s_max;
+        if (threadIdx.x == 0) s_max = 0;
+        __syncthreads();
+        mine = __reduce_max_sync(0xffffffffu, mine);
+        if ((threadIdx.x & 31) == 0 && mine > s_max) atomicMax(&s_max, mine);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_max > 0) atomicMax(reinterpret_cast<long long *>(cnt_max), (long long)s_max);
     }
 }
 
-__global__ void k_group_assign(const int32_t *__restrict__ pslot, const int32_t *__restrict__ slot_gid, int64_t n,
-                               int32_t *__restrict__ gid, int32_t *__restrict__ cnt) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int g = slot_gid[pslot[i]];
-    gid[i] = g;
-    atomicAdd(&cnt[g], 1);
-}
-
 int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot, int32_t *gid, int32_t *cnt,
-               int64_t *nGroups, int64_t *scan_tmp, cudaStream_t st) {
+               int64_t *nGroups, int64_t *scan_tmp, cudaStream_t st, int64_t *cnt_max, int64_t cnt_len) {
     if (n <= 0) {
         PG_CUDA(cudaMemsetAsync(nGroups, 0, sizeof(int64_t), st));
         return PG_OK;
     }
     const int T = 256;
     const unsigned nb = (unsigned)div_up(n, T);
-    k_group_init<<<kNumSM * 8, T, 0, st>>>(tab.slot_rep, tab.slot_gid, tab.cap);
-    PG_CUDA(cudaMemsetAsync(cnt, 0, (size_t)n * sizeof(int32_t), st));
+    if (tab.slot_gid == tab.slot_rep + tab.cap) PG_TRY(fill_u32(tab.slot_rep, 0xffffffffu, (size_t)tab.cap * 2, st));
+    else {
+        PG_TRY(fill_u32(tab.slot_rep, 0xffffffffu, tab.cap, st));
+        PG_TRY(fill_u32(tab.slot_gid, 0xffffffffu, tab.cap, st));
+    }
+    PG_TRY(fill_u32(cnt, 0u, (size_t)(cnt_len > n ? cnt_len : n), st));
     k_group_insert<<<nb, T, 0, st>>>(keys, n, tab.slot_rep, tab.slot_gid, tab.cap, pslot);
-    k_group_flag<<<nb, T, 0, st>>>(pslot, tab.slot_gid, n, gid);
-    PG_TRY(scan_exclusive_i32(gid, gid, n, nGroups, scan_tmp, st));
-    k_group_publish<<<nb, T, 0, st>>>(pslot, tab.slot_gid, gid, nGroups, n, keys, tab.slot_key);
-    k_group_assign<<<nb, T, 0, st>>>(pslot, tab.slot_gid, n, gid, cnt);
+    PG_TRY(scan_fused(GroupFlagLoad{pslot, tab.slot_gid}, GroupPublishStore{pslot, tab.slot_gid, keys, tab.slot_key}, n, nGroups,
+                      scan_tmp, st));
+    k_group_assign<<<nb, T, 0, st>>>(pslot, tab.slot_gid, n, gid, cnt, cnt_max);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

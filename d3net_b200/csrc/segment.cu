@@ -389,7 +389,7 @@ extern "C" int pg_get_iou(const int32_t *proposals_idx, const int32_t *proposals
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t total = (int64_t)nInstance * nProposal;
     PG_CHECK_ARG(proposals_idx && instance_labels, "null pointer");
-    PG_CUDA(cudaMemsetAsync(proposals_iou, 0, (size_t)total * sizeof(float), st));
+    PG_TRY(fill_u32(proposals_iou, 0u, (size_t)total, st));
     { PG_KTIME("k_iou_count", st);
     k_iou_count<<<kNumSM * 8, 256, 0, st>>>(proposals_idx, proposals_offset, instance_labels,
                                            reinterpret_cast<int32_t *>(proposals_iou), nInstance, nProposal); }

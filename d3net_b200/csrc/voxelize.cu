@@ -52,16 +52,6 @@ __global__ void k_vox_keys(const int64_t *__restrict__ coords, int64_t N, int4 *
     keys[i] = make_int4((int)a.x, (int)a.y, (int)b.x, (int)b.y);
 }
 
-__global__ void k_max_i32(const int32_t *__restrict__ v, const int64_t *__restrict__ n_dev, int64_t *out) {
-    const int64_t n = *n_dev;
-    int m = 0;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        m = max(m, v[i]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax((unsigned long long *)out, (unsigned long long)m);
-}
-
 constexpr int kVoxRankMax = 32;        // largest voxel (points) served by the sort-free fill: a thread per point counts
                                        // its voxel's segment, so long segments (cluster grids: hundreds of points per voxel,
                                        // different ones in every lane) diverge and scatter -- those keep the sort
@@ -381,8 +371,7 @@ extern "C" int pg_voxelize_idx_map(const int64_t *coords, int64_t N, int mode, i
     if (!w.ok) { set_error("pg_voxelize_idx_map: workspace too small (%zu < %zu)", ws_bytes, w.used); return PG_EWORKSPACE; }
     PG_CUDA(cudaMemsetAsync(w.scalars, 0, 4 * sizeof(int64_t), st));
     k_vox_keys<<<(unsigned)div_up(N, 256), 256, 0, st>>>(coords, N, w.keys);
-    PG_TRY(group_int4(w.keys, N, w.tab, w.pslot, input_map, w.cnt, w.scalars, w.scan_tmp, st));
-    k_max_i32<<<kNumSM * 4, 256, 0, st>>>(w.cnt, w.scalars, w.scalars + 1);
+    PG_TRY(group_int4(w.keys, N, w.tab, w.pslot, input_map, w.cnt, w.scalars, w.scan_tmp, st, w.scalars + 1));   // + the largest voxel
     PG_LAUNCH_CHECK();
     int64_t h[2];
     PG_CUDA(cudaMemcpyAsync(h, w.scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -407,8 +396,8 @@ extern "C" int pg_voxelize_idx_fill(const int64_t *coords, const int32_t *input_
     if (maxActive <= kVoxRankMax) {
         // no sort: points side by side per voxel, then every point finds its column by counting (see k_vox_rank)
         int32_t *cursor = reinterpret_cast<int32_t *>(w.kA);
-        PG_CUDA(cudaMemsetAsync(cursor, 0, (size_t)M * sizeof(int32_t), st));
-        PG_CUDA(cudaMemsetAsync(output_map, 0, (size_t)M * W * sizeof(int32_t), st));           // the rows' zero padding
+        PG_TRY(fill_u32(cursor, 0u, (size_t)M, st));
+        PG_TRY(fill_u32(output_map, 0u, (size_t)M * W, st));           // the rows' zero padding
         k_vox_scatter<<<(unsigned)div_up(N, 256), 256, 0, st>>>(input_map, w.voff, N, cursor, w.vA);
         PG_KTIME("k_vox_rank", st);
         k_vox_rank<<<(unsigned)div_up(N, 256), 256, 0, st>>>(coords, input_map, w.cnt, w.voff, w.vA, N, W, mode, output_coords, output_map);

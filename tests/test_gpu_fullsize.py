@@ -297,14 +297,16 @@ def test_config2_fused_cluster_chain_is_identical(ops, full_batch):
 
 
 def test_chain_two_stream_variant_is_identical(ops):
-    """chain.proposal_chain(overlap=True): the two clusterings issued from two host threads on two streams give the
-    same tensors as the sequential pass."""
+    """chain.proposal_chain(overlap=True): the scene voxelisation and the two clusterings issued from three host threads
+    on three streams give the same tensors as the sequential pass."""
     nb = scenes.make_batch(3, 40_000, config_id=6, geometry_points=40_000)
     batch = chain.batch_to_device(nb, torch.device("cuda"))
     a = chain.proposal_chain(ops, batch, overlap=False)
     for _ in range(3):
         b = chain.proposal_chain(ops, batch, overlap=True)
         torch.cuda.synchronize()
-        for k in ("proposals_idx", "proposals_offset", "proposals_score_feats", "ious", "proposals_center", "proposals_size"):
+        for k in ("proposals_idx", "proposals_offset", "proposals_score_feats", "ious", "proposals_center", "proposals_size",
+                  "voxel_locs", "voxel_feats", "p2v_map"):
             assert torch.equal(a[k], b[k]), k
         assert a["nActive_shift"] == b["nActive_shift"] and a["nActive_raw"] == b["nActive_raw"]
+        assert a["v2p_map_numel"] == b["v2p_map_numel"]
