@@ -56,6 +56,7 @@ __device__ __forceinline__ int cell_coord(float x, double inv_s) {
 
 __global__ void k_bq_keys(const float *__restrict__ xyz, const int32_t *__restrict__ batch_idxs, int32_t n,
                           double inv_s, int4 *__restrict__ keys) {
+    pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float x = __ldg(xyz + 3 * (int64_t)i), y = __ldg(xyz + 3 * (int64_t)i + 1), z = __ldg(xyz + 3 * (int64_t)i + 2);
@@ -65,6 +66,7 @@ __global__ void k_bq_keys(const float *__restrict__ xyz, const int32_t *__restri
 // points side by side per cell: slot claimed from the cell's cursor; the cell's smallest / largest point index on the way
 __global__ void k_bq_scatter(const int32_t *__restrict__ cell, const int32_t *__restrict__ cstart, int32_t n,
                              int32_t *cursor, uint32_t *__restrict__ sorted_pt, uint32_t *cmin, uint32_t *cmax) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int c = __ldg(cell + i);
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256) k_bq_neighbours(const int4 *__restrict__ 
                                                        int32_t *__restrict__ kc, int32_t *__restrict__ dense,
                                                        const uint32_t *__restrict__ cmin, const uint32_t *__restrict__ cmax,
                                                        uint2 *__restrict__ crange) {
+    pdl_enter();
     const int64_t nc = scalars[0];
     const int lane = threadIdx.x & 31;
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -265,6 +268,7 @@ __global__ void __launch_bounds__(256) k_bq_cells_small(const float *__restrict_
                                                         uint32_t *__restrict__ masks, int64_t mask_capacity, float r2,
                                                         uint32_t *__restrict__ cand_idx, int32_t *__restrict__ counts,
                                                         int32_t *__restrict__ kb) {
+    pdl_enter();
     __shared__ uint32_t scratch_all[8][HI];
     uint32_t *scratch = scratch_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -363,6 +367,7 @@ __global__ void __launch_bounds__(kMergeThreads) k_bq_merge_dense(
     const int32_t *__restrict__ cand_start, const int32_t *__restrict__ dense, const uint2 *__restrict__ crange,
     int64_t *scalars, uint32_t *cand_idx, float4 *__restrict__ cand_xy, float2 *__restrict__ cand_z,
     int32_t *__restrict__ dbase) {
+    pdl_enter();
     __shared__ __align__(16) MergeSmem S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nDense = scalars[3];
@@ -586,6 +591,7 @@ __global__ void __launch_bounds__(kTestThreads, 8) k_bq_test_dense(
     const int32_t *__restrict__ dense, const int32_t *__restrict__ dbase, const float4 *__restrict__ cand_xy,
     const float2 *__restrict__ cand_z, int64_t *scalars, uint32_t *__restrict__ masks, int64_t mask_capacity, float r2,
     int32_t *__restrict__ counts, int32_t *__restrict__ kb) {
+    pdl_enter();
     __shared__ __align__(128) TestSmem S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t nDense = scalars[3];
@@ -693,6 +699,7 @@ __global__ void __launch_bounds__(256) k_bq_fill(const float *__restrict__ xyz, 
                                                  const int32_t *__restrict__ kb, const uint32_t *__restrict__ cand_idx,
                                                  const int2 *__restrict__ start_len, float r2, int32_t n,
                                                  int32_t *__restrict__ idx) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -804,6 +811,7 @@ __global__ void __launch_bounds__(256) k_bq_fill_short(const uint32_t *__restric
                                                        const uint32_t *__restrict__ cand_idx, const int32_t *__restrict__ mbase,
                                                        const uint32_t *__restrict__ masks, const int2 *__restrict__ start_len,
                                                        int32_t n, int32_t *__restrict__ idx) {
+    pdl_enter();
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const uint32_t k = __ldg(sorted_pt + q);
@@ -838,6 +846,7 @@ __global__ void __launch_bounds__(256, 5) k_bq_fill_mask(const uint32_t *__restr
                                                       const uint32_t *__restrict__ cand_idx, const int32_t *__restrict__ mbase,
                                                       const uint32_t *__restrict__ masks, const int2 *__restrict__ start_len,
                                                       int32_t n, int32_t *__restrict__ idx) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -876,6 +885,7 @@ __global__ void __launch_bounds__(256) k_bq_list_samples(const uint32_t *__restr
                                                         const uint32_t *__restrict__ cand_idx, const int32_t *__restrict__ mbase,
                                                         const uint32_t *__restrict__ masks, const int32_t *__restrict__ counts,
                                                         int32_t n, int4 *__restrict__ samples) {
+    pdl_enter();
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
     const uint32_t k = __ldg(sorted_pt + q);
@@ -922,6 +932,7 @@ __global__ void __launch_bounds__(256, 5) k_bq_fill_lists(const uint32_t *__rest
                                                        const uint32_t *__restrict__ masks, const int2 *__restrict__ start_len,
                                                        const int32_t *__restrict__ qpos, const uint32_t *__restrict__ worklist,
                                                        const unsigned long long *__restrict__ count, int32_t *__restrict__ idx) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const unsigned lt = lanemask_lt();
     const long long nl = (long long)*count;
@@ -936,7 +947,7 @@ __global__ void __launch_bounds__(256, 5) k_bq_fill_lists(const uint32_t *__rest
 
 int bq_list_samples(const BqWs &w, const uint32_t *masks, int32_t n, int4 *samples, cudaStream_t st) {
     PG_KTIME("k_bq_list_samples", st);
-    k_bq_list_samples<<<(unsigned)div_up(n, 256), 256, 0, st>>>(bq_sorted(w, n), w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx,
+    launch(k_bq_list_samples, (unsigned)div_up(n, 256), 256, 0, st, bq_sorted(w, n), w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx,
                                                                w.mbase, masks, w.counts, n, samples);
     PG_LAUNCH_CHECK();
     return PG_OK;
@@ -945,7 +956,7 @@ int bq_list_samples(const BqWs &w, const uint32_t *masks, int32_t n, int4 *sampl
 int bq_fill_lists(const BqWs &w, const uint32_t *masks, const int2 *start_len, const uint32_t *worklist,
                   const unsigned long long *count, int32_t n, int32_t *idx, cudaStream_t st) {
     PG_KTIME("k_bq_fill_lists", st);
-    k_bq_fill_lists<<<kNumSM * PG_RESIDENT(k_bq_fill_lists, 256, 0) * 4, 256, 0, st>>>(bq_sorted(w, n), w.cell, w.cstart, w.ccnt, w.cand_start,
+    launch(k_bq_fill_lists, kNumSM * PG_RESIDENT(k_bq_fill_lists, 256, 0) * 4, 256, 0, st, bq_sorted(w, n), w.cell, w.cstart, w.ccnt, w.cand_start,
                                                                                    w.kb, w.cand_idx, w.mbase, masks, start_len, w.qpos,
                                                                                    worklist, count, idx);
     PG_LAUNCH_CHECK();
@@ -974,7 +985,7 @@ extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs,
     const double s = fabs((double)radius) * 1.0001;
     const double inv_s = (s > 0.0 && isfinite(s)) ? 1.0 / s : 0.0;   // r = 0 / inf / NaN: one cell per scene
     PG_CUDA(cudaMemsetAsync(w.scalars, 0, 8 * sizeof(int64_t), st));
-    k_bq_keys<<<(unsigned)div_up(n, 256), 256, 0, st>>>(xyz, batch_idxs, n, inv_s, w.keys);
+    launch(k_bq_keys, (unsigned)div_up(n, 256), 256, 0, st, xyz, batch_idxs, n, inv_s, w.keys);
     PG_TRY(group_int4(w.keys, n, w.tab, w.pslot, w.cell, w.ccnt, w.scalars, w.scan_tmp, st, nullptr, (int64_t)n + 1));
     PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
     // scratch of the scatter, adjacent in the workspace: the cells' cursors, the complement of their smallest and their
@@ -982,9 +993,9 @@ extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs,
     uint32_t *sorted_pt = w.kA, *cmin = w.kB, *cmax = w.vB;
     int32_t *cursor = reinterpret_cast<int32_t *>(w.vA);
     PG_TRY(fill_u32(cursor, 0u, ((size_t)((char *)w.vB - (char *)w.vA) + align_up((size_t)n * 4)) / 4, st));   // to the padded end of vB
-    k_bq_scatter<<<(unsigned)div_up(n, 256), 256, 0, st>>>(w.cell, w.cstart, n, cursor, sorted_pt, cmin, cmax);
+    launch(k_bq_scatter, (unsigned)div_up(n, 256), 256, 0, st, w.cell, w.cstart, n, cursor, sorted_pt, cmin, cmax);
     { PG_KTIME("k_bq_neighbours", st);
-    k_bq_neighbours<<<kNumSM * PG_RESIDENT(k_bq_neighbours, 256, 0) * 2, 256, 0, st>>>(w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense, cmin, cmax, w.crange); }
+    launch(k_bq_neighbours, kNumSM * PG_RESIDENT(k_bq_neighbours, 256, 0) * 2, 256, 0, st, w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense, cmin, cmax, w.crange); }
     PG_TRY(scan_fused(CandLoad{w.kc, w.scalars}, CandStore{w.kc, w.cand_start, w.scalars}, (int64_t)n + 1, w.scalars + 1, w.scan_tmp, st));
     PG_TRY(scan_fused(MaskLoad{w.ccnt, w.kc, w.scalars}, MaskStore{w.mbase}, (int64_t)n + 1, w.scalars + 6, w.scan_tmp, st));
     PG_LAUNCH_CHECK();
@@ -1018,17 +1029,15 @@ extern "C" int pg_ballquery_count(const float *xyz, int32_t n, float radius, int
     const unsigned gsmall = (unsigned)(gsmall_want < gsmall_max ? gsmall_want : gsmall_max);
     const unsigned gmedium = (unsigned)(gsmall_want < gmedium_max ? gsmall_want : gmedium_max);
     { PG_KTIME("k_bq_cells_small", st);
-    ksmall<<<gsmall, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars, masks, mask_cap,
+    launch(ksmall, gsmall, 256, 0, st, xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars, masks, mask_cap,
                                    r2, w.cand_idx, w.counts, w.kb); }
     { PG_KTIME("k_bq_cells_medium", st);
-    kmedium<<<gmedium, 256, 0, st>>>(xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars, masks, mask_cap,
+    launch(kmedium, gmedium, 256, 0, st, xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.mbase, w.scalars, masks, mask_cap,
                                      r2, w.cand_idx, w.counts, w.kb); }
     { PG_KTIME("k_bq_merge_dense", st);
-    k_bq_merge_dense<<<kNumSM * PG_RESIDENT(k_bq_merge_dense, kMergeThreads, 0), kMergeThreads, 0, st>>>(
-        xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.dense, w.crange, w.scalars, w.cand_idx, w.cand_xy, w.cand_z, w.dbase); }
+    launch(k_bq_merge_dense, kNumSM * PG_RESIDENT(k_bq_merge_dense, kMergeThreads, 0), kMergeThreads, 0, st, xyz, sorted_pt, w.cstart, w.ccnt, w.nbr, w.kc, w.cand_start, w.dense, w.crange, w.scalars, w.cand_idx, w.cand_xy, w.cand_z, w.dbase); }
     { PG_KTIME("k_bq_test_dense", st);
-    k_bq_test_dense<<<kNumSM * PG_RESIDENT(k_bq_test_dense, kTestThreads, 0), kTestThreads, 0, st>>>(
-        xyz, sorted_pt, w.cstart, w.ccnt, w.kc, w.mbase, w.dense, w.dbase, w.cand_xy, w.cand_z, w.scalars, masks, mask_cap, r2,
+    launch(k_bq_test_dense, kNumSM * PG_RESIDENT(k_bq_test_dense, kTestThreads, 0), kTestThreads, 0, st, xyz, sorted_pt, w.cstart, w.ccnt, w.kc, w.mbase, w.dense, w.dbase, w.cand_xy, w.cand_z, w.scalars, masks, mask_cap, r2,
         w.counts, w.kb); }
     // starts in query order, written straight into the interleaved (start, len) rows per point
     PG_TRY(scan_fused(CountLoad{w.counts}, StartLenStore{sorted_pt, (int2 *)start_len, w.qpos}, n, w.scalars + 2, w.scan_tmp, st));
@@ -1059,15 +1068,15 @@ extern "C" int pg_ballquery_fill(const float *xyz, int32_t n, float radius, cons
     const float r2 = radius * radius;
     if (masks) {
         PG_KTIME("k_bq_fill_short", st);
-        k_bq_fill_short<<<(unsigned)div_up(n, 256), 256, 0, st>>>(sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx,
+        launch(k_bq_fill_short, (unsigned)div_up(n, 256), 256, 0, st, sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx,
                                                                   w.mbase, masks, (const int2 *)start_len, n, idx);
     }
     PG_KTIME(masks ? "k_bq_fill_mask" : "k_bq_fill", st);
     if (masks)
-        k_bq_fill_mask<<<kNumSM * PG_RESIDENT(k_bq_fill_mask, 256, 0) * 4, 256, 0, st>>>(sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx, w.mbase,
+        launch(k_bq_fill_mask, kNumSM * PG_RESIDENT(k_bq_fill_mask, 256, 0) * 4, 256, 0, st, sorted_pt, w.cell, w.cstart, w.ccnt, w.cand_start, w.kb, w.cand_idx, w.mbase,
                                                    masks, (const int2 *)start_len, n, idx);
     else
-        k_bq_fill<<<kNumSM * PG_RESIDENT(k_bq_fill, 256, 0) * 4, 256, 0, st>>>(xyz, sorted_pt, w.cell, w.cand_start, w.kb, w.cand_idx, (const int2 *)start_len,
+        launch(k_bq_fill, kNumSM * PG_RESIDENT(k_bq_fill, 256, 0) * 4, 256, 0, st, xyz, sorted_pt, w.cell, w.cand_start, w.kb, w.cand_idx, (const int2 *)start_len,
                                               r2, n, idx);
     PG_LAUNCH_CHECK();
     return PG_OK;

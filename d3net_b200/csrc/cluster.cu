@@ -47,10 +47,11 @@ struct ClWs {
     int32_t *cstate;     //   skip threshold L per cell
     int32_t *cthr;       //   three minima of last(j) over the cell's full points (T1, T2, T3)
     uint32_t *key0, *kA, *vA, *kB, *vB;
+    int32_t *pubA, *pubB;  // a tree's new root, published by the tree's old root for its other points (find_via_old_root)
     int32_t *hist;
     int64_t *scan_tmp;
     // [0] checksum [1] bad [2] pending count [3] changed [4] nCluster [5] sumNPoint [6] verify work counter
-    // [7] some list is full [8] lists left to the sweep (grid-assisted mode)
+    // [7] some list is full [8] lists left to the sweep (grid-assisted mode) [9] [11] block tickets of the ordered passes
     unsigned long long *scalars;
     size_t pend_cap;
     bool ok;
@@ -79,6 +80,8 @@ static ClWs cl_layout(void *ws, size_t ws_bytes, int64_t N_) {
     w.vA = a.take<uint32_t>(n);
     w.kB = a.take<uint32_t>(n);
     w.vB = a.take<uint32_t>(n);
+    w.pubA = a.take<int32_t>(n);
+    w.pubB = a.take<int32_t>(n);
     w.hist = a.take<int32_t>(radix_tmp_count(N_));
     w.scan_tmp = a.take<int64_t>(scan_tmp_count((int64_t)(n + radix_tmp_count(N_))));
     w.scalars = a.take<unsigned long long>(12);
@@ -113,6 +116,7 @@ __global__ void k_cl_prep(const int32_t *__restrict__ label, const int32_t *__re
                           uint2 *__restrict__ pl, uint32_t *__restrict__ trunc, int32_t *__restrict__ last,
                           int32_t *__restrict__ root, int32_t *__restrict__ lab, uint32_t *__restrict__ skey, int shift,
                           unsigned long long *scalars, const int4 *__restrict__ samples) {
+    pdl_enter();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     bool full = false;
     if (v < N) {
@@ -178,6 +182,36 @@ __device__ __forceinline__ int uf_union_roots(uint2 *pl, int a, int b) {
     }
 }
 
+// Between two flattens only ROOTS get new parents (k_cl_sample and the sweep hang a root under another root), so every
+// point of a tree reaches the forest through its old root A = root[v] <= v, and all of them would walk the same chain of
+// hooked roots from there -- thousands of threads in the same few lines.  Instead A's own thread walks the chain once and
+// publishes the result in pub[A] (-1 before); the tree's other points wait for it.  Safe because the blocks of these passes
+// take their index range from a ticket counter: A <= v sits in the same or an earlier ticket, whose block is running or
+// done; inside a warp the roots go first (__syncwarp).  Every lane of the warp must call this (v >= N: pass v = -1).
+// (After the SWEEP the chains of hooked roots are long and everybody's path halving helps: the label pass keeps the
+// plain find -- see k_cl_label.)
+__device__ __forceinline__ int find_via_old_root(uint2 *pl, const int32_t *root_old, volatile int32_t *pub, int v) {
+    const int A = v >= 0 ? root_old[v] : -1;
+    int r = -1;
+    if (v >= 0 && A == v) {
+        r = uf_find(pl, v);
+        pub[v] = r;
+    }
+    __syncwarp();
+    if (v >= 0 && A != v) {
+        while ((r = pub[A]) < 0) {}
+    }
+    return r;
+}
+
+// the block's index range from a ticket (see find_via_old_root)
+__device__ __forceinline__ int ticket_block(unsigned long long *ticket) {
+    __shared__ int s_b;
+    if (threadIdx.x == 0) s_b = (int)atomicAdd(ticket, 1ULL);
+    __syncthreads();
+    return s_b;
+}
+
 // Snapshot word per point, written by k_cl_flatten and read (through the read-only L1 path) once per edge
 // by the sweep:  [31] the point's list is full   [30:26] low 5 bits of its label   [25:0] its root.
 // Equal roots = already connected.  Different label bits = never connected.  Only a pair that differs in
@@ -196,6 +230,7 @@ template <int P>
 __global__ void k_cl_sample(const int32_t *__restrict__ idx, const int2 *__restrict__ start_len, uint2 *pl,
                             const int32_t *__restrict__ last, const uint32_t *__restrict__ snap, int32_t N, int64_t nActive,
                             int round, const int4 *__restrict__ samples) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int2 sl = start_len[i];
@@ -255,6 +290,7 @@ __global__ void __launch_bounds__(kVerThreads, 3) k_cl_verify(const int32_t *__r
                                                               const uint32_t *__restrict__ snap, int32_t N, int64_t nActive,
                                                               int2 *__restrict__ pend, unsigned long long pend_cap,
                                                               unsigned long long *scalars, int use_list_count) {
+    pdl_enter();
     constexpr int kGroups = kVerThreads / G;
     // lists to sweep: all N of them in `order`, or the scalars[8] the cell pass left over (grid-assisted mode)
     const long long NL = use_list_count ? (long long)scalars[8] : (long long)N;
@@ -435,6 +471,7 @@ __global__ void k_cl_cell_main(const uint32_t *__restrict__ sorted_pt, const int
                                const int32_t *__restrict__ ccnt, const int64_t *__restrict__ bq_scalars,
                                const uint2 *__restrict__ pl, const uint32_t *__restrict__ snap, uint2 *__restrict__ cellsum,
                                int32_t *__restrict__ cthr) {
+    pdl_enter();
     const int64_t nCells = bq_scalars[0];
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += (int64_t)gridDim.x * blockDim.x) {
         const int nq = __ldg(ccnt + c), qs = __ldg(cstart + c);
@@ -454,6 +491,7 @@ __global__ void k_cl_cell_main(const uint32_t *__restrict__ sorted_pt, const int
 __global__ void k_cl_cell_thresholds(const int32_t *__restrict__ cell, const uint2 *__restrict__ pl,
                                      const uint32_t *__restrict__ snap, const int32_t *__restrict__ last, int32_t N,
                                      const uint2 *__restrict__ cellsum, int32_t *cthr) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const unsigned sv = __ldg(snap + i);
@@ -473,6 +511,7 @@ __global__ void k_cl_cell_thresholds(const int32_t *__restrict__ cell, const uin
 __global__ void k_cl_cell_settle(const int32_t *__restrict__ nbr, const int64_t *__restrict__ bq_scalars,
                                  const uint2 *__restrict__ cellsum, const int32_t *__restrict__ cthr,
                                  int32_t *__restrict__ cstate) {
+    pdl_enter();
     const int64_t nCells = bq_scalars[0];
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += (int64_t)gridDim.x * blockDim.x) {
         const uint2 me = cellsum[c];
@@ -497,6 +536,7 @@ __global__ void k_cl_cell_worklist(const uint32_t *__restrict__ sorted_pt, const
                                    const uint2 *__restrict__ pl, const uint32_t *__restrict__ snap,
                                    const uint2 *__restrict__ cellsum, const int32_t *__restrict__ cstate, int32_t N,
                                    uint32_t *__restrict__ worklist, unsigned long long *scalars) {
+    pdl_enter();
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     bool keep = false;
     uint32_t i = 0;
@@ -525,13 +565,27 @@ __global__ void k_cl_cell_worklist(const uint32_t *__restrict__ sorted_pt, const
 
 // Roots go to their own array: writing them back into the forest would race with the path-halving
 // stores of other threads' finds, which may re-install an intermediate ancestor after the root.
-__global__ void k_cl_flatten(uint2 *pl, const uint32_t *__restrict__ trunc, int32_t *__restrict__ root,
-                             uint32_t *__restrict__ snap, int32_t N) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N) return;
-    const int r = uf_find(pl, v);
+// VIA: root[] holds the previous flatten's roots -- the find goes through them (find_via_old_root, pub_use); either way
+// pub_reset is set to -1 for the next ordered pass.
+template <bool VIA>
+__global__ void __launch_bounds__(256) k_cl_flatten(uint2 *pl, const uint32_t *__restrict__ trunc, int32_t *root,
+                                                    uint32_t *__restrict__ snap, int32_t N, int32_t *pub_use,
+                                                    int32_t *__restrict__ pub_reset, unsigned long long *ticket) {
+    pdl_enter();
+    int v;
+    int r;
+    if (VIA) {
+        v = ticket_block(ticket) * blockDim.x + threadIdx.x;
+        r = find_via_old_root(pl, root, pub_use, v < N ? v : -1);
+        if (v >= N) return;
+    } else {
+        v = blockIdx.x * blockDim.x + threadIdx.x;
+        if (v >= N) return;
+        r = uf_find(pl, v);
+    }
     root[v] = r;
     pl[v].x = (unsigned)r;        // a hint only (another thread's halving store may replace it with another ancestor)
+    if (pub_reset) pub_reset[v] = -1;
     const unsigned full = (trunc[v >> 5] >> (v & 31)) & 1u;
     snap[v] = (unsigned)r | ((pl[v].y & 31u) << 26) | (full << 31);
 }
@@ -561,6 +615,7 @@ __device__ __forceinline__ bool propagate_edge(const int32_t *__restrict__ root,
 
 __global__ void k_cl_pending(const int2 *__restrict__ pend, unsigned long long n_pend, const int32_t *__restrict__ root,
                              int32_t *lab, unsigned long long *scalars) {
+    pdl_enter();
     bool changed = false;
     for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_pend;
          t += (unsigned long long)gridDim.x * blockDim.x) {
@@ -581,6 +636,7 @@ template <bool FIND>
 __global__ void __launch_bounds__(1024) k_cl_pending_block(int2 *pend, unsigned long long pend_cap, uint2 *pl,
                                                            const int32_t *__restrict__ root, int32_t *lab,
                                                            unsigned long long *scalars) {
+    pdl_enter();
     const unsigned long long n_pend = scalars[2];
     if (n_pend == 0) return;
     if (n_pend > pend_cap || n_pend > kPendBlockMax) {
@@ -624,6 +680,7 @@ __global__ void __launch_bounds__(256) k_cl_propagate(const int32_t *__restrict_
                                                       const int32_t *__restrict__ last, int32_t N,
                                                       const int32_t *__restrict__ root, int32_t *lab,
                                                       unsigned long long *scalars) {
+    pdl_enter();
     const int sub = threadIdx.x % G;
     const int64_t groups = (int64_t)gridDim.x * (blockDim.x / G);
     bool changed = false;
@@ -647,6 +704,7 @@ __global__ void __launch_bounds__(256) k_cl_propagate(const int32_t *__restrict_
 }
 
 __global__ void k_cl_reset(int32_t *__restrict__ root, int32_t *__restrict__ lab, int32_t N) {
+    pdl_enter();
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v < N) { root[v] = v; lab[v] = v; }
 }
@@ -654,14 +712,18 @@ __global__ void k_cl_reset(int32_t *__restrict__ root, int32_t *__restrict__ lab
 // final label per point, sizes per label (warp-aggregated: a floor-sized component would otherwise
 // serialise tens of thousands of atomics on one counter)
 template <bool FIND>
-__global__ void k_cl_label(uint2 *pl, int32_t *root, int32_t *lab, int32_t N, int32_t *__restrict__ size,
-                           uint32_t *__restrict__ key0) {
+__global__ void __launch_bounds__(256) k_cl_label(uint2 *pl, int32_t *root, int32_t *lab, int32_t N, int32_t *__restrict__ size,
+                                                  uint32_t *__restrict__ key0) {
+    pdl_enter();
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     const bool on = v < N;
     int l = -1;
     if (on) {
         int r;
-        if (FIND) { r = uf_find(pl, v); root[v] = r; }           // the flatten pass folded in (trusted path)
+        // the flatten pass folded in (trusted path).  Every thread walks: after the sweep the chains of hooked roots are
+        // long and the walkers' path halving helps each other (through the old roots, find_via_old_root: 0.093 -> 0.134 ms
+        // waiting, 0.114 ms with a walk where the root has not published yet)
+        if (FIND) { r = uf_find(pl, v); root[v] = r; }
         else r = root[v];
         l = lab_resolve(lab, r);
         key0[v] = (uint32_t)l;
@@ -699,6 +761,7 @@ struct SizesStore {
 // sort key per point: cluster id, or nCluster for points of dropped components (they sort last)
 __global__ void k_cl_keys(const uint32_t *__restrict__ key0, const int32_t *__restrict__ cid, int32_t N, int32_t nCluster,
                           uint32_t *__restrict__ keys) {
+    pdl_enter();
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= N) return;
     const uint32_t l = key0[v];
@@ -708,6 +771,7 @@ __global__ void k_cl_keys(const uint32_t *__restrict__ key0, const int32_t *__re
 
 __global__ void k_cl_emit(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int32_t S,
                           int2 *__restrict__ cluster_idxs) {
+    pdl_enter();
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < S) cluster_idxs[k] = make_int2((int)keys[k], (int)vals[k]);
 }
@@ -773,7 +837,7 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
         PG_TRY(bq_list_samples(g, lazy_masks, N, w.samples, st));
         samples = w.samples;
     }
-    k_cl_prep<<<(unsigned)div_up((int64_t)N + 32, 256), 256, 0, st>>>(semantic_label, ball_query_idxs, sl, N, nActive,
+    launch(k_cl_prep, (unsigned)div_up((int64_t)N + 32, 256), 256, 0, st, semantic_label, ball_query_idxs, sl, N, nActive,
                                                                      generic ? 0 : 1, w.pl, w.trunc, w.last, w.root, w.lab,
                                                                      w.key0, shift, w.scalars, samples);
     if (!use_generic) {
@@ -791,41 +855,42 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
                                     w.scan_tmp, st, &res));
             order = res == 0 ? w.vA : w.vB;
         }
-        k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
+        launch(k_cl_flatten<false>, nb, 256, 0, st, w.pl, w.trunc, w.root, w.snap, N, nullptr, w.pubA, nullptr);
+        static_assert(kSampleRounds == 1, "one ordered flatten per ticket / publish array");
         for (int round = 0; round < kSampleRounds; round++) {
             { PG_KTIME("k_cl_sample", st);
-            k_cl_sample<2><<<nb, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.last, w.snap, N, nActive, round, samples); }
+            launch(k_cl_sample<2>, nb, 256, 0, st, ball_query_idxs, sl, w.pl, w.last, w.snap, N, nActive, round, samples); }
             PG_KTIME("k_cl_flatten", st);
-            k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
+            launch(k_cl_flatten<true>, nb, 256, 0, st, w.pl, w.trunc, w.root, w.snap, N, w.pubA, w.pubB, w.scalars + 9);
         }
         if (use_cells) {
             PG_KTIME("k_cl_cells", st);      // the four passes of the cell pre-pass, timed as one
             const uint32_t *sp = bq_sorted(g, N);
             const unsigned cg = kNumSM * 8;
-            k_cl_cell_main<<<cg, 256, 0, st>>>(sp, g.cstart, g.ccnt, g.scalars, w.pl, w.snap, w.cellsum, w.cthr);
-            k_cl_cell_thresholds<<<nb, 256, 0, st>>>(g.cell, w.pl, w.snap, w.last, N, w.cellsum, w.cthr);
-            k_cl_cell_settle<<<cg, 256, 0, st>>>(g.nbr, g.scalars, w.cellsum, w.cthr, w.cstate);
-            k_cl_cell_worklist<<<nb, 256, 0, st>>>(sp, g.cell, w.pl, w.snap, w.cellsum, w.cstate, N, w.vA, w.scalars);
+            launch(k_cl_cell_main, cg, 256, 0, st, sp, g.cstart, g.ccnt, g.scalars, w.pl, w.snap, w.cellsum, w.cthr);
+            launch(k_cl_cell_thresholds, nb, 256, 0, st, g.cell, w.pl, w.snap, w.last, N, w.cellsum, w.cthr);
+            launch(k_cl_cell_settle, cg, 256, 0, st, g.nbr, g.scalars, w.cellsum, w.cthr, w.cstate);
+            launch(k_cl_cell_worklist, nb, 256, 0, st, sp, g.cell, w.pl, w.snap, w.cellsum, w.cstate, N, w.vA, w.scalars);
         }
         // lazy lists: only now, and only for the lists the sweep is about to read, do indices get written
         if (lazy) PG_TRY(bq_fill_lists(g, lazy_masks, sl, w.vA, w.scalars + 8, N, const_cast<int32_t *>(ball_query_idxs), st));
         const unsigned vg = kNumSM * 3;
 #define PG_VERIFY(G, T)                                                                                              \
-    k_cl_verify<G, T><<<vg, kVerThreads, 0, st>>>(ball_query_idxs, sl, order, w.pl, w.last, w.snap, N, nActive, w.pend, \
+    launch(k_cl_verify<G, T>, vg, kVerThreads, 0, st, ball_query_idxs, sl, order, w.pl, w.last, w.snap, N, nActive, w.pend, \
                                                   (unsigned long long)w.pend_cap, w.scalars, use_cells ? 1 : 0)
         { PG_KTIME(trusted ? "k_cl_verify<trusted>" : "k_cl_verify<validating>", st);
         if (trusted) { if (wide) PG_VERIFY(32, true); else PG_VERIFY(8, true); }
         else { if (wide) PG_VERIFY(32, false); else PG_VERIFY(8, false); } }
 #undef PG_VERIFY
         // trusted lists: the last flatten is folded into the label pass (the parked edges resolve their own roots)
-        if (!trusted) k_cl_flatten<<<nb, 256, 0, st>>>(w.pl, w.trunc, w.root, w.snap, N);
+        if (!trusted) launch(k_cl_flatten<true>, nb, 256, 0, st, w.pl, w.trunc, w.root, w.snap, N, w.pubB, nullptr, w.scalars + 11);
         PG_LAUNCH_CHECK();
     }
     // Trusted lists need no verdict from the sweep (no checksum, no range flags): the parked one-way edges are
     // settled on the device and the host reads everything back once, together with the sizes.
     const bool fast = trusted && !use_generic;
     if (fast) {
-        k_cl_pending_block<true><<<1, 1024, 0, st>>>(w.pend, (unsigned long long)w.pend_cap, w.pl, w.root, w.lab, w.scalars);
+        launch(k_cl_pending_block<true>, 1, 1024, 0, st, w.pend, (unsigned long long)w.pend_cap, w.pl, w.root, w.lab, w.scalars);
     } else {
         PG_CUDA(cudaMemcpyAsync(h, w.scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
         PG_CUDA(cudaStreamSynchronize(st));
@@ -836,7 +901,7 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
     }
     if (!use_generic && (h[0] != 0 || h[1] != 0)) {   // not a truncated symmetric relation
         use_generic = true;
-        k_cl_reset<<<nb, 256, 0, st>>>(w.root, w.lab, N);
+        launch(k_cl_reset, nb, 256, 0, st, w.root, w.lab, N);
     }
     const unsigned long long n_pend = use_generic ? 0 : h[2];
     g_cl_dbg[0] = h[0] != 0; g_cl_dbg[1] = (long long)h[1]; g_cl_dbg[2] = (long long)h[2]; g_cl_dbg[3] = 0;
@@ -851,13 +916,13 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
         for (int it = 0; it < 1000000; it++) {
             PG_CUDA(cudaMemsetAsync(w.scalars + 3, 0, sizeof(unsigned long long), st));
             if (!sweep) {
-                k_cl_pending<<<(unsigned)div_up((int64_t)n_parked, 256), 256, 0, st>>>(w.pend, n_parked, w.root, w.lab, w.scalars);
+                launch(k_cl_pending, (unsigned)div_up((int64_t)n_parked, 256), 256, 0, st, w.pend, n_parked, w.root, w.lab, w.scalars);
             } else if (use_generic) {
-                if (wide) k_cl_propagate<32, false><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.trunc, w.last, N, w.root, w.lab, w.scalars);
-                else k_cl_propagate<8, false><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.trunc, w.last, N, w.root, w.lab, w.scalars);
+                if (wide) launch(k_cl_propagate<32, false>, eg, 256, 0, st, ball_query_idxs, sl, w.pl, w.trunc, w.last, N, w.root, w.lab, w.scalars);
+                else launch(k_cl_propagate<8, false>, eg, 256, 0, st, ball_query_idxs, sl, w.pl, w.trunc, w.last, N, w.root, w.lab, w.scalars);
             } else {
-                if (wide) k_cl_propagate<32, true><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.trunc, w.last, N, w.root, w.lab, w.scalars);
-                else k_cl_propagate<8, true><<<eg, 256, 0, st>>>(ball_query_idxs, sl, w.pl, w.trunc, w.last, N, w.root, w.lab, w.scalars);
+                if (wide) launch(k_cl_propagate<32, true>, eg, 256, 0, st, ball_query_idxs, sl, w.pl, w.trunc, w.last, N, w.root, w.lab, w.scalars);
+                else launch(k_cl_propagate<8, true>, eg, 256, 0, st, ball_query_idxs, sl, w.pl, w.trunc, w.last, N, w.root, w.lab, w.scalars);
             }
             PG_LAUNCH_CHECK();
             unsigned long long changed = 0;
@@ -873,8 +938,8 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
     bool find_in_label = fast;
     auto finish = [&]() -> int {
         { PG_KTIME("k_cl_label", st);
-        if (find_in_label) k_cl_label<true><<<nb, 256, 0, st>>>(w.pl, w.root, w.lab, N, w.size, w.key0);
-        else k_cl_label<false><<<nb, 256, 0, st>>>(w.pl, w.root, w.lab, N, w.size, w.key0); }
+        if (find_in_label) launch(k_cl_label<true>, nb, 256, 0, st, w.pl, w.root, w.lab, N, w.size, w.key0);
+        else launch(k_cl_label<false>, nb, 256, 0, st, w.pl, w.root, w.lab, N, w.size, w.key0); }
         PG_TRY(scan_fused(KeepLoad{w.key0, w.size, N, threshold}, SizesStore{w.size, w.cid, w.csize, (unsigned long long *)w.scalars},
                           (int64_t)N + 1, (int64_t *)(w.scalars + 4), w.scan_tmp, st));
         PG_LAUNCH_CHECK();
@@ -952,12 +1017,12 @@ extern "C" int pg_bfs_cluster_fill(int32_t N, int32_t nCluster, int32_t sumNPoin
     PG_CUDA(cudaMemsetAsync(w.csize + nCluster, 0, sizeof(int32_t), st));
     PG_TRY(scan_exclusive_i32(w.csize, cluster_offsets, (int64_t)nCluster + 1, nullptr, w.scan_tmp, st));
     // stable sort of (cluster id | dropped, point): members ascend inside every cluster
-    k_cl_keys<<<nb, 256, 0, st>>>(w.key0, w.cid, N, nCluster, w.kB);
+    launch(k_cl_keys, nb, 256, 0, st, w.key0, w.cid, N, nCluster, w.kB);
     int bits = 0;
     while ((1ll << bits) < (long long)nCluster + 1) bits++;
     int res = 0;
     PG_TRY(radix_sort_pairs(w.kB, nullptr, w.kA, w.vA, w.kB, w.vB, N, bits, w.hist, w.scan_tmp, st, &res));
-    k_cl_emit<<<(unsigned)div_up(sumNPoint, 256), 256, 0, st>>>(res == 0 ? w.kA : w.kB, res == 0 ? w.vA : w.vB, sumNPoint,
+    launch(k_cl_emit, (unsigned)div_up(sumNPoint, 256), 256, 0, st, res == 0 ? w.kA : w.kB, res == 0 ? w.vA : w.vB, sumNPoint,
                                                               (int2 *)cluster_idxs);
     PG_LAUNCH_CHECK();
     return PG_OK;

@@ -45,6 +45,35 @@ void set_error(const char *fmt, ...);
         if (_rc != PG_OK) return _rc; \
     } while (0)
 
+// Programmatic dependent launch (sm_90+): every kernel of this library starts with pdl_enter() and is launched through
+// launch(), which sets cudaLaunchAttributeProgrammaticStreamSerialization.  A kernel's blocks then become resident while
+// the kernel before it on the stream is still draining (its blocks have all STARTED -- that is when launch_dependents has
+// been executed by every one of them) and sit at griddepcontrol.wait until that kernel has completed and its writes are
+// visible: stream order as before, but the launch latency between the ~100 short kernels of a step overlaps the tail of
+// the predecessor.  A kernel that runs through launch() MUST call pdl_enter() before it touches memory.
+// PG_B200_NO_PDL=1 in the environment falls back to plain launches (for A/B timing).
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline void launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);      // errors surface through PG_LAUNCH_CHECK
+}
+
 // Kernel timing (pg_kernel_timing): when switched on, a launch wrapped in a KTimer scope is bracketed by
 // two CUDA events on its own stream; pg_kernel_timing_report() sums them per kernel name.  Off by
 // default (one predictable branch per launch); bench.py uses it for the per-kernel roofline numbers.

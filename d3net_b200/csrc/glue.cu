@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(kGsThreads) k_glue_cluster_stats(const float *
                                                                    const float *__restrict__ rand6,
                                                                    GlueParams *__restrict__ params,
                                                                    float *__restrict__ center, float *__restrict__ size) {
+    pdl_enter();
     __shared__ float buf[2][kGsRows * 3];
     __shared__ float red[2][3][kGsThreads / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(kGsThreads) k_glue_cluster_stats(const float *
 
 __global__ void k_glue_cluster_coords(const float *__restrict__ coords, const int2 *__restrict__ cluster_idxs,
                                       const GlueParams *__restrict__ params, int32_t S, int64_t *__restrict__ out) {
+    pdl_enter();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const int2 ci = __ldg(cluster_idxs + s);
@@ -168,6 +170,7 @@ constexpr int kPackWidth = 46;
 __global__ void __launch_bounds__(1024) k_pack_rank(const int2 *__restrict__ proposals_idx, const int32_t *__restrict__ offsets,
                                                     const int64_t *__restrict__ locs_scaled, int32_t nP,
                                                     int32_t *__restrict__ scene_of, int32_t *__restrict__ slot_of) {
+    pdl_enter();
     extern __shared__ int32_t sc[];                 // scene id per proposal
     for (int p = threadIdx.x; p < nP; p += blockDim.x) {
         const int first = __ldg(&proposals_idx[__ldg(offsets + p)].y);
@@ -188,6 +191,7 @@ __global__ void k_pack_rows(const int2 *__restrict__ proposals_idx, const int32_
                             const float *__restrict__ size, const float *__restrict__ feats, const float *__restrict__ score,
                             const int32_t *__restrict__ scene_of, const int32_t *__restrict__ slot_of, int32_t nP, int32_t C,
                             int32_t B, int32_t P, float *__restrict__ out) {
+    pdl_enter();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)nP * kPackWidth) return;
     const int p = (int)(t / kPackWidth), j = (int)(t - (int64_t)p * kPackWidth);
@@ -214,6 +218,7 @@ __global__ void k_collate_points(const float *__restrict__ locs_scaled, const in
                                  const int32_t *__restrict__ instance_ids, const int32_t *__restrict__ batch_offsets,
                                  const int32_t *__restrict__ instance_offsets, int32_t N, int32_t B,
                                  int64_t *__restrict__ out_locs, int64_t *__restrict__ out_sem, int64_t *__restrict__ out_inst) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     int lo = 0, hi = B;                       // last b with batch_offsets[b] <= i
@@ -252,9 +257,9 @@ extern "C" int pg_pack_proposals(const int32_t *proposals_idx, const int32_t *pr
     const size_t smem = (size_t)nProposal * sizeof(int32_t);
     if (smem > 48 * 1024)
         PG_CUDA(cudaFuncSetAttribute(k_pack_rank, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_pack_rank<<<1, 1024, smem, st>>>((const int2 *)proposals_idx, proposals_offset, locs_scaled, nProposal, ws, ws + nProposal);
+    launch(k_pack_rank, 1, 1024, smem, st, (const int2 *)proposals_idx, proposals_offset, locs_scaled, nProposal, ws, ws + nProposal);
     const int64_t total = (int64_t)nProposal * kPackWidth;
-    k_pack_rows<<<(unsigned)div_up(total, 256), 256, 0, st>>>((const int2 *)proposals_idx, proposals_offset, semantic_preds, center,
+    launch(k_pack_rows, (unsigned)div_up(total, 256), 256, 0, st, (const int2 *)proposals_idx, proposals_offset, semantic_preds, center,
                                                               size, feats, score, ws, ws + nProposal, nProposal, C, B, P, out);
     PG_LAUNCH_CHECK();
     return PG_OK;
@@ -278,9 +283,9 @@ extern "C" int pg_cluster_coords(const float *coords, const int32_t *cluster_idx
     const float inv_fs = 1.0f / fs;
     const unsigned grid = (unsigned)(nCluster < kNumSM * 8 ? nCluster : kNumSM * 8);
     { PG_KTIME("k_glue_cluster_stats", st);
-    k_glue_cluster_stats<<<grid, kGsThreads, 0, st>>>(coords, (const int2 *)cluster_idxs, cluster_offsets, nCluster, inv_fs, fs, scale,
+    launch(k_glue_cluster_stats, grid, kGsThreads, 0, st, coords, (const int2 *)cluster_idxs, cluster_offsets, nCluster, inv_fs, fs, scale,
                                                      rand6, params, center, size); }
-    k_glue_cluster_coords<<<(unsigned)div_up(sumNPoint, 256), 256, 0, st>>>(coords, (const int2 *)cluster_idxs, params, sumNPoint,
+    launch(k_glue_cluster_coords, (unsigned)div_up(sumNPoint, 256), 256, 0, st, coords, (const int2 *)cluster_idxs, params, sumNPoint,
                                                                             out_coords);
     PG_LAUNCH_CHECK();
     return PG_OK;
@@ -298,7 +303,7 @@ extern "C" int pg_collate_points(const float *locs_scaled, const int32_t *sem_la
     PG_CHECK_ARG((out_instance_ids == nullptr) == (instance_ids == nullptr) && (instance_ids == nullptr || instance_offsets),
                  "instance_ids in / out / offsets must come together");
     PG_CHECK_ARG(((uintptr_t)out_locs_scaled & 31u) == 0, "out_locs_scaled not 32-byte aligned");
-    k_collate_points<<<(unsigned)div_up(N, 256), 256, 0, st>>>(locs_scaled, sem_labels, instance_ids, batch_offsets,
+    launch(k_collate_points, (unsigned)div_up(N, 256), 256, 0, st, locs_scaled, sem_labels, instance_ids, batch_offsets,
                                                                instance_offsets, N, B, out_locs_scaled, out_sem_labels,
                                                                out_instance_ids);
     PG_LAUNCH_CHECK();

@@ -64,6 +64,7 @@ static int bits_for(int64_t n) {           // bits needed for keys 0 .. n-1 (at 
 // column `col` of the [S, 2] pair list as sort keys; flags pairs outside [0, nP) x [0, N)
 __global__ void k_nms_keys(const int2 *__restrict__ pairs, int32_t S, int32_t nP, int32_t N, uint32_t *__restrict__ keys,
                            unsigned long long *scalars) {
+    pdl_enter();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const int2 r = __ldg(pairs + s);
@@ -74,6 +75,7 @@ __global__ void k_nms_keys(const int2 *__restrict__ pairs, int32_t S, int32_t nP
 // after the sort by proposal: key = point of the row, value = its proposal
 __global__ void k_nms_second_keys(const int2 *__restrict__ pairs, const uint32_t *__restrict__ order, int32_t S, int32_t N,
                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    pdl_enter();
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const int2 r = __ldg(pairs + __ldg(order + s));
@@ -83,6 +85,7 @@ __global__ void k_nms_second_keys(const int2 *__restrict__ pairs, const uint32_t
 
 // first[v] = lower bound of v in the ascending keys, v = 0 .. nV (first[nV] = S)
 __global__ void k_nms_bounds(const uint32_t *__restrict__ keys, int32_t S, int32_t nV, int32_t *__restrict__ first) {
+    pdl_enter();
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v > nV) return;
     int lo = 0, hi = S;
@@ -96,6 +99,7 @@ __global__ void k_nms_bounds(const uint32_t *__restrict__ keys, int32_t S, int32
 // distinct points per proposal (the reference's proposals_mask.sum(1), model/pointgroup.py:582,589)
 __global__ void k_nms_npoint(const uint32_t *__restrict__ gpt, const int32_t *__restrict__ prop_start, int32_t nP,
                              int32_t *__restrict__ npoint) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t nWarps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t a = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); a < nP; a += nWarps) {
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(kCrossThreads) k_cross_iou(const uint32_t *__r
                                                              const uint32_t *__restrict__ pp, const int32_t *__restrict__ row_start,
                                                              const int32_t *__restrict__ npoint, int32_t nP, int use_smem,
                                                              float *__restrict__ out) {
+    pdl_enter();
     extern __shared__ int32_t bins_smem[];
     for (int a = blockIdx.x; a < nP; a += gridDim.x) {
         int32_t *bins = use_smem ? bins_smem : reinterpret_cast<int32_t *>(out + (int64_t)a * nP);
@@ -147,6 +152,7 @@ __global__ void __launch_bounds__(kCrossThreads) k_cross_iou(const uint32_t *__r
 // ---- greedy suppression (lib/utils/eval.py:75-97) ------------------------------------------------------
 // keys that sort ascending = scores descending; NaN scores last, like numpy's argsort of -scores
 __global__ void k_nms_score_keys(const float *__restrict__ scores, int32_t n, uint32_t *__restrict__ keys) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float s = scores[i];
@@ -157,6 +163,7 @@ __global__ void k_nms_score_keys(const float *__restrict__ scores, int32_t n, ui
 // the suppression bitmap; its row then suppresses, in parallel, every later proposal with IoU > threshold.
 __global__ void __launch_bounds__(1024) k_nms_greedy(const float *__restrict__ cross, const uint32_t *__restrict__ order, int32_t n,
                                                      float threshold, int32_t *__restrict__ pick, int32_t *__restrict__ n_pick) {
+    pdl_enter();
     extern __shared__ uint32_t dead[];             // bit k: position k of `order` is suppressed
     __shared__ int s_next, s_count;
     const int words = (n + 31) >> 5;
@@ -193,6 +200,7 @@ __global__ void __launch_bounds__(1024) k_nms_greedy(const float *__restrict__ c
 __global__ void __launch_bounds__(256) k_pick_masks(const int2 *__restrict__ pairs, const int32_t *__restrict__ offsets,
                                                     const int32_t *__restrict__ pick, int32_t nPick, int32_t nP, int32_t N,
                                                     int32_t *__restrict__ out, unsigned long long *bad) {
+    pdl_enter();
     for (int k = blockIdx.x; k < nPick; k += gridDim.x) {
         const int p = __ldg(pick + k);
         if ((unsigned)p >= (unsigned)nP) { if (threadIdx.x == 0) *bad = 1; continue; }
@@ -218,7 +226,7 @@ extern "C" int pg_pick_masks(const int32_t *proposals_idx, const int32_t *propos
     unsigned long long *d_bad = (unsigned long long *)ws;          // 8 bytes: out-of-range flag
     PG_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), st));
     PG_TRY(fill_u32(out, 0u, (size_t)nPick * (size_t)N, st));
-    k_pick_masks<<<(unsigned)(nPick < kNumSM * 8 ? nPick : kNumSM * 8), 256, 0, st>>>((const int2 *)proposals_idx, proposals_offset, pick,
+    launch(k_pick_masks, (unsigned)(nPick < kNumSM * 8 ? nPick : kNumSM * 8), 256, 0, st, (const int2 *)proposals_idx, proposals_offset, pick,
                                                                                    nPick, nProposal, N, out, d_bad);
     PG_LAUNCH_CHECK();
     unsigned long long bad = 0;
@@ -247,10 +255,10 @@ extern "C" int pg_cross_iou(const int32_t *proposals_idx, int32_t nPairs, int32_
     if (S > 0) {
         const unsigned sb = (unsigned)div_up(S, 256);
         // (1) by proposal, (2) by point: LSD order, so the result is sorted by (point, proposal)
-        k_nms_keys<<<sb, 256, 0, st>>>(pairs, S, nProposal, N, w.k0, w.scalars);
+        launch(k_nms_keys, sb, 256, 0, st, pairs, S, nProposal, N, w.k0, w.scalars);
         int res = 0;
         PG_TRY(radix_sort_pairs(w.k0, nullptr, w.kA, w.vA, w.kB, w.vB, S, bits_for(nProposal), w.hist, w.scan_tmp, st, &res));
-        k_nms_second_keys<<<sb, 256, 0, st>>>(pairs, res == 0 ? w.vA : w.vB, S, N, w.k0, w.gp_sorted);
+        launch(k_nms_second_keys, sb, 256, 0, st, pairs, res == 0 ? w.vA : w.vB, S, N, w.k0, w.gp_sorted);
         PG_TRY(radix_sort_pairs(w.k0, w.gp_sorted, w.kA, w.vA, w.kB, w.vB, S, bits_for(N), w.hist, w.scan_tmp, st, &res));
         PG_CUDA(cudaMemcpyAsync(w.pt_sorted, res == 0 ? w.kA : w.kB, (size_t)S * 4, cudaMemcpyDeviceToDevice, st));
         PG_CUDA(cudaMemcpyAsync(w.pp_sorted, res == 0 ? w.vA : w.vB, (size_t)S * 4, cudaMemcpyDeviceToDevice, st));
@@ -260,16 +268,14 @@ extern "C" int pg_cross_iou(const int32_t *proposals_idx, int32_t nPairs, int32_
         gp_sorted = res == 0 ? w.kA : w.kB;
         gpt_sorted = res == 0 ? w.vA : w.vB;
     }
-    k_nms_bounds<<<(unsigned)div_up((int64_t)N + 1, 256), 256, 0, st>>>(pt_sorted, S, N, w.row_start);
-    k_nms_bounds<<<(unsigned)div_up((int64_t)nProposal + 1, 256), 256, 0, st>>>(gp_sorted, S, nProposal, w.prop_start);
-    k_nms_npoint<<<(unsigned)(div_up(nProposal, 8) < kNumSM * 8 ? div_up(nProposal, 8) : kNumSM * 8), 256, 0, st>>>(
-        gpt_sorted, w.prop_start, nProposal, w.npoint);
+    launch(k_nms_bounds, (unsigned)div_up((int64_t)N + 1, 256), 256, 0, st, pt_sorted, S, N, w.row_start);
+    launch(k_nms_bounds, (unsigned)div_up((int64_t)nProposal + 1, 256), 256, 0, st, gp_sorted, S, nProposal, w.prop_start);
+    launch(k_nms_npoint, (unsigned)(div_up(nProposal, 8) < kNumSM * 8 ? div_up(nProposal, 8) : kNumSM * 8), 256, 0, st, gpt_sorted, w.prop_start, nProposal, w.npoint);
     const int use_smem = nProposal <= kCrossSmemBins;
     const size_t smem = use_smem ? (size_t)nProposal * sizeof(int32_t) : 0;
     if (smem > 48 * 1024) PG_CUDA(cudaFuncSetAttribute(k_cross_iou, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { PG_KTIME("k_cross_iou", st);
-    k_cross_iou<<<(unsigned)(nProposal < kNumSM * 8 ? nProposal : kNumSM * 8), kCrossThreads, smem, st>>>(
-        gpt_sorted, w.prop_start, pp_sorted, w.row_start, w.npoint, nProposal, use_smem, cross_ious); }
+    launch(k_cross_iou, (unsigned)(nProposal < kNumSM * 8 ? nProposal : kNumSM * 8), kCrossThreads, smem, st, gpt_sorted, w.prop_start, pp_sorted, w.row_start, w.npoint, nProposal, use_smem, cross_ious); }
     if (npoint) PG_CUDA(cudaMemcpyAsync(npoint, w.npoint, (size_t)nProposal * 4, cudaMemcpyDeviceToDevice, st));
     PG_LAUNCH_CHECK();
     unsigned long long bad = 0;
@@ -300,13 +306,13 @@ extern "C" int pg_nms_instances(const float *cross_ious, const float *scores, in
     int64_t *scan_tmp = a.take<int64_t>(scan_tmp_count((int64_t)n + radix_tmp_count(n)));
     int32_t *d_count = a.take<int32_t>(1);
     if (!a.ok) { set_error("pg_nms_instances: workspace too small (%zu < %zu)", ws_bytes, a.used); return PG_EWORKSPACE; }
-    k_nms_score_keys<<<(unsigned)div_up(n, 256), 256, 0, st>>>(scores, n, k0);
+    launch(k_nms_score_keys, (unsigned)div_up(n, 256), 256, 0, st, scores, n, k0);
     int res = 0;
     PG_TRY(radix_sort_pairs(k0, nullptr, kA, vA, kB, vB, n, 32, hist, scan_tmp, st, &res));
     const size_t smem = (size_t)((n + 31) / 32) * 4;
     if (smem > 48 * 1024) PG_CUDA(cudaFuncSetAttribute(k_nms_greedy, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { PG_KTIME("k_nms_greedy", st);
-    k_nms_greedy<<<1, 1024, smem, st>>>(cross_ious, res == 0 ? vA : vB, n, threshold, pick, d_count); }
+    launch(k_nms_greedy, 1, 1024, smem, st, cross_ious, res == 0 ? vA : vB, n, threshold, pick, d_count); }
     PG_LAUNCH_CHECK();
     int32_t cnt = 0;
     PG_CUDA(cudaMemcpyAsync(&cnt, d_count, sizeof(cnt), cudaMemcpyDeviceToHost, st));

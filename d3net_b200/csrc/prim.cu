@@ -1,6 +1,7 @@
 // Device-wide primitives used by several ops: exclusive scan, stable LSD radix sort of pairs, and
 // hash grouping of int4 keys (first-occurrence numbering).  Hand-written; no CUB/Thrust.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -25,12 +26,18 @@ void set_error(const char *fmt, ...) {
 }
 const char *last_error() { return g_err; }
 
+bool pdl_enabled() {
+    static const bool on = []() { const char *e = getenv("PG_B200_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
 // ---------------------------------------------------------------------------------------------
 // exclusive scan of a plain array (single pass, decoupled look-back: scan.cuh), 16 items per thread through int4 loads
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kScanThreads) k_scan_onepass(const int32_t *__restrict__ in, int32_t *__restrict__ out,
                                                                int64_t n, unsigned long long *tmp, int64_t *__restrict__ total,
                                                                int aligned) {
+    pdl_enter();
     __shared__ int warp_tot[32];
     __shared__ long long s_tile, s_prefix;
     if (threadIdx.x == 0) s_tile = (long long)atomicAdd(tmp, 1ULL);
@@ -81,7 +88,7 @@ int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, int64_t *tota
     const int64_t nb = div_up(n, kScanTile);
     const bool aligned = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
     PG_CUDA(cudaMemsetAsync(tmp, 0, (size_t)(nb + 1) * sizeof(int64_t), st));
-    k_scan_onepass<<<(unsigned)nb, kScanThreads, 0, st>>>(in, out, n, reinterpret_cast<unsigned long long *>(tmp), total,
+    launch(k_scan_onepass, (unsigned)nb, kScanThreads, 0, st, in, out, n, reinterpret_cast<unsigned long long *>(tmp), total,
                                                          aligned ? 1 : 0);
     PG_LAUNCH_CHECK();
     return PG_OK;
@@ -97,22 +104,26 @@ constexpr int kRadixThreads = 256;
 constexpr int kRadixRounds = 8;
 constexpr int kRadixTile = kRadixThreads * kRadixRounds;
 constexpr int kRadixMaxPasses = 4;
-// scratch layout (int32 words): [0, 4*256) global digit counts per pass; [4*256, 4*256 + 16) tile tickets per pass;
-// then per pass nb * 256 look-back words: [31:30] 0 = nothing yet, 1 = the tile's count, 2 = inclusive prefix; [29:0] value
-constexpr int kRadixHead = kRadixMaxPasses * 256 + 16;
+constexpr int kRadixMaxBins = 1024;         // digits of 8, 9 or 10 bits: 9 .. 10 / 17 .. 20 / 25 .. 30 key bits take one pass less
+constexpr int kRadixPassBins = 3072;        // most bins over all passes of one sort: 3 x 1024 (4 passes only happen at 8 bits)
+// scratch layout (int32 words): [0, 3072) global digit counts, pass after pass; [3072, 3072 + 16) tile tickets per pass;
+// then per pass nb * bins look-back words: [31:30] 0 = nothing yet, 1 = the tile's count, 2 = inclusive prefix; [29:0] value
+constexpr int kRadixHead = kRadixPassBins + 16;
 
-__global__ void __launch_bounds__(kRadixThreads) k_radix_hist_all(const uint32_t *__restrict__ keys, int64_t n, int passes,
+__global__ void __launch_bounds__(kRadixThreads) k_radix_hist_all(const uint32_t *__restrict__ keys, int64_t n, int passes, int dbits,
                                                                   int32_t *__restrict__ scratch, int64_t state_words) {
-    __shared__ int h[kRadixMaxPasses][256];
-    for (int p = 0; p < passes; p++) h[p][threadIdx.x] = 0;
+    pdl_enter();
+    __shared__ int h[kRadixPassBins];
+    const int bins = 1 << dbits;
+    for (int i = threadIdx.x; i < passes * bins; i += blockDim.x) h[i] = 0;
     __syncthreads();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t k = keys[i];
-        for (int p = 0; p < passes; p++) atomicAdd(&h[p][(k >> (8 * p)) & 255u], 1);
+        for (int p = 0; p < passes; p++) atomicAdd(&h[p * bins + ((k >> (dbits * p)) & (bins - 1))], 1);
     }
     __syncthreads();
-    for (int p = 0; p < passes; p++)
-        if (h[p][threadIdx.x]) atomicAdd(&scratch[p * 256 + threadIdx.x], h[p][threadIdx.x]);
+    for (int i = threadIdx.x; i < passes * bins; i += blockDim.x)
+        if (h[i]) atomicAdd(&scratch[i], h[i]);
     // the passes' look-back words start from zero
     int32_t *state = scratch + kRadixHead;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < state_words; i += (int64_t)gridDim.x * blockDim.x) state[i] = 0;
@@ -121,24 +132,29 @@ __global__ void __launch_bounds__(kRadixThreads) k_radix_hist_all(const uint32_t
 // Each warp owns a contiguous 256-element slice of the tile (8 rounds of 32 consecutive elements), so the stable
 // order inside the tile is (warp, round, lane): a warp ranks its own slice with nothing but warp-level
 // primitives -- `__match_any_sync` groups equal digits, a per-warp counter row in shared memory carries the
-// running count from round to round.  Keys, values and ranks stay in registers.
-__global__ void __launch_bounds__(kRadixThreads)
+// running count from round to round.  Keys, values and ranks stay in registers.  Thread t owns digits
+// t * PER .. t * PER + PER - 1 in the publish / look-back step.
+template <int DBITS>
+__global__ void __launch_bounds__(kRadixThreads, DBITS <= 9 ? 4 : 2)    // 592 resident tiles: a million keys in one wave
 k_radix_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                  uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
                  const int32_t *__restrict__ ghist, unsigned *ticket, unsigned *state) {
+    pdl_enter();
     constexpr int kWarps = kRadixThreads / 32;
-    __shared__ int wcnt[kWarps][256];                 // per-warp digit counts, then global bases per warp
+    constexpr int BINS = 1 << DBITS, PER = BINS / kRadixThreads;
+    __shared__ int wcnt[kWarps][BINS];                // per-warp digit counts, then global bases per warp
     __shared__ int s_scan[32];
     __shared__ unsigned s_tile;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned lt = lanemask_lt();
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < kWarps * BINS; i += kRadixThreads) (&wcnt[0][0])[i] = 0;
+    // exclusive scan of the pass's global digit counts: where each digit's run starts in the output
+    int gcount[PER], gsum = 0;
 #pragma unroll
-    for (int k = 0; k < kWarps; k++) wcnt[k][threadIdx.x] = 0;
-    // exclusive scan of the pass's global digit counts: where digit `tid`'s run starts in the output
-    const int gcount = ghist[threadIdx.x];
+    for (int q = 0; q < PER; q++) { gcount[q] = ghist[threadIdx.x * PER + q]; gsum += gcount[q]; }
     int unused;
-    const int gincl = block_scan_incl(gcount, s_scan, &unused);          // (two block barriers: s_tile is visible after them)
+    int gstart = block_scan_incl(gsum, s_scan, &unused) - gsum;          // (two block barriers: s_tile is visible after them)
     const unsigned tile = s_tile;
     const int64_t slice = (int64_t)tile * kRadixTile + (int64_t)w * (kRadixRounds * 32);
     uint32_t key[kRadixRounds], val[kRadixRounds];
@@ -150,51 +166,88 @@ k_radix_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restric
         const bool live = i < n;
         key[r] = live ? keys_in[i] : 0u;
         val[r] = live ? (vals_in ? vals_in[i] : (uint32_t)i) : 0u;
-        dig[r] = live ? ((key[r] >> shift) & 255u) : 256u;   // dead lanes never match a real digit
+        dig[r] = live ? ((key[r] >> shift) & (unsigned)(BINS - 1)) : (unsigned)BINS;   // dead lanes never match a real digit
     }
 #pragma unroll
     for (int r = 0; r < kRadixRounds; r++) {
         const unsigned peers = __match_any_sync(0xffffffffu, dig[r]);
         const int before = __popc(peers & lt);
         int run = 0;
-        if (dig[r] < 256u) {
+        if (dig[r] < (unsigned)BINS) {
             run = wcnt[w][dig[r]];                    // equal digits read the same counter, then the leader bumps it
         }
         __syncwarp();
-        if (dig[r] < 256u && before == 0) wcnt[w][dig[r]] = run + __popc(peers);
+        if (dig[r] < (unsigned)BINS && before == 0) wcnt[w][dig[r]] = run + __popc(peers);
         __syncwarp();
         rank[r] = run + before;
     }
     __syncthreads();
-    {   // digit `tid`: the tile's count goes out, the earlier tiles' counts come in, the eight warp counts become bases
-        int c = 0;
+    // per digit: the tile's count goes out, the earlier tiles' counts come in, the eight warp counts become bases
+    int c[PER];
 #pragma unroll
-        for (int k = 0; k < kWarps; k++) c += wcnt[k][threadIdx.x];
-        volatile unsigned *st = state + threadIdx.x;
-        int before = 0;
-        if (tile == 0) st[0] = (2u << 30) | (unsigned)c;
-        else {
-            st[(size_t)tile * 256] = (1u << 30) | (unsigned)c;
-            for (int64_t t = (int64_t)tile - 1;; t--) {
-                unsigned wv;
-                do { wv = st[(size_t)t * 256]; } while ((wv >> 30) == 0u);
-                before += (int)(wv & 0x3fffffffu);
-                if ((wv >> 30) == 2u) break;
+    for (int q = 0; q < PER; q++) {
+        const int d = threadIdx.x * PER + q;
+        c[q] = 0;
+#pragma unroll
+        for (int k = 0; k < kWarps; k++) c[q] += wcnt[k][d];
+        reinterpret_cast<volatile unsigned *>(state)[(size_t)tile * BINS + d] = (tile == 0 ? (2u << 30) : (1u << 30)) | (unsigned)c[q];
+    }
+    int before[PER];
+    if (tile != 0) {
+        // the thread's PER look-back chains advance together: their loads are in flight at the same time
+        volatile unsigned *st = state + threadIdx.x * PER;
+        int64_t at[PER];
+        bool open = false;
+#pragma unroll
+        for (int q = 0; q < PER; q++) { before[q] = 0; at[q] = (int64_t)tile - 1; open = true; }
+        while (open) {
+            unsigned wv[PER];
+            bool together = true;                    // the usual case: all chains at the same tile -> one vector load
+#pragma unroll
+            for (int q = 1; q < PER; q++) together &= at[q] == at[0];
+            if (PER == 4 && together && at[0] >= 0) {
+                const unsigned *p = state + (size_t)at[0] * BINS + threadIdx.x * PER;
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3]) : "l"(p));
+            } else if (PER == 2 && together && at[0] >= 0) {
+                const unsigned *p = state + (size_t)at[0] * BINS + threadIdx.x * PER;
+                asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(wv[0]), "=r"(wv[1]) : "l"(p));
+            } else {
+#pragma unroll
+                for (int q = 0; q < PER; q++) wv[q] = at[q] >= 0 ? st[(size_t)at[q] * BINS + q] : 0u;
             }
-            st[(size_t)tile * 256] = (2u << 30) | (unsigned)(before + c);
+            open = false;
+#pragma unroll
+            for (int q = 0; q < PER; q++) {
+                if (at[q] < 0) continue;
+                const unsigned flag = wv[q] >> 30;
+                if (flag != 0u) {
+                    before[q] += (int)(wv[q] & 0x3fffffffu);
+                    at[q] = flag == 2u ? -1 : at[q] - 1;
+                    if (at[q] < 0) st[(size_t)tile * BINS + q] = (2u << 30) | (unsigned)(before[q] + c[q]);
+                }
+                open |= at[q] >= 0;
+            }
         }
-        int acc = gincl - gcount + before;
+    } else {
+#pragma unroll
+        for (int q = 0; q < PER; q++) before[q] = 0;
+    }
+#pragma unroll
+    for (int q = 0; q < PER; q++) {
+        const int d = threadIdx.x * PER + q;
+        int acc = gstart + before[q];
+        gstart += gcount[q];
 #pragma unroll
         for (int k = 0; k < kWarps; k++) {
-            const int cw = wcnt[k][threadIdx.x];
-            wcnt[k][threadIdx.x] = acc;
+            const int cw = wcnt[k][d];
+            wcnt[k][d] = acc;
             acc += cw;
         }
     }
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < kRadixRounds; r++) {
-        if (dig[r] < 256u) {
+        if (dig[r] < (unsigned)BINS) {
             const int pos = wcnt[w][dig[r]] + rank[r];
             keys_out[pos] = key[r];
             vals_out[pos] = val[r];
@@ -202,7 +255,7 @@ k_radix_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restric
     }
 }
 
-size_t radix_tmp_count(int64_t n) { return (size_t)kRadixHead + (size_t)kRadixMaxPasses * 256 * (size_t)div_up(n > 0 ? n : 1, kRadixTile); }
+size_t radix_tmp_count(int64_t n) { return (size_t)kRadixHead + (size_t)kRadixPassBins * (size_t)div_up(n > 0 ? n : 1, kRadixTile); }
 
 int radix_sort_pairs(const uint32_t *keys_src, const uint32_t *vals_src, uint32_t *keysA, uint32_t *valsA,
                      uint32_t *keysB, uint32_t *valsB, int64_t n, int bits, int32_t *hist, int64_t *scan_tmp,
@@ -210,21 +263,29 @@ int radix_sort_pairs(const uint32_t *keys_src, const uint32_t *vals_src, uint32_
     (void)scan_tmp;
     *result_buf = 0;
     if (n <= 0) return PG_OK;
-    int passes = (bits + 7) / 8;
-    if (passes < 1) passes = 1;
-    if (passes > kRadixMaxPasses) passes = kRadixMaxPasses;
+    if (bits < 1) bits = 1;
+    if (bits > 32) bits = 32;
+    // the fewest passes with digits of at most 10 bits, then the narrowest digit (>= 8 bits) that still makes it
+    static const int max_dbits = []() { const char *e = getenv("PG_RADIX_MAXBITS"); const int v = e ? atoi(e) : 9; return v < 8 ? 8 : v > 10 ? 10 : v; }();
+    const int passes = (bits + max_dbits - 1) / max_dbits;
+    int dbits = (bits + passes - 1) / passes;
+    if (dbits < 8) dbits = 8;
+    const int bins = 1 << dbits;
     const int nb = (int)div_up(n, kRadixTile);
     uint32_t *k[2] = {keysA, keysB}, *v[2] = {valsA, valsB};
     const uint32_t *kin = keys_src, *vin = vals_src;
     PG_CUDA(cudaMemsetAsync(hist, 0, (size_t)kRadixHead * sizeof(int32_t), st));
-    const int64_t state_words = (int64_t)passes * 256 * nb;
+    const int64_t state_words = (int64_t)passes * bins * nb;
     const int hgrid = nb < kNumSM * 8 ? nb : kNumSM * 8;
-    k_radix_hist_all<<<hgrid, kRadixThreads, 0, st>>>(keys_src, n, passes, hist, state_words);
+    launch(k_radix_hist_all, hgrid, kRadixThreads, 0, st, keys_src, n, passes, dbits, hist, state_words);
     int dst = 0;
     for (int p = 0; p < passes; p++) {
-        k_radix_onesweep<<<nb, kRadixThreads, 0, st>>>(kin, vin, k[dst], v[dst], n, 8 * p, hist + p * 256,
-                                                       reinterpret_cast<unsigned *>(hist) + kRadixMaxPasses * 256 + p,
-                                                       reinterpret_cast<unsigned *>(hist) + kRadixHead + (size_t)p * 256 * nb);
+        unsigned *ticket = reinterpret_cast<unsigned *>(hist) + kRadixPassBins + p;
+        unsigned *state = reinterpret_cast<unsigned *>(hist) + kRadixHead + (size_t)p * bins * nb;
+        const int32_t *gh = hist + p * bins;
+        if (dbits == 8) launch(k_radix_onesweep<8>, nb, kRadixThreads, 0, st, kin, vin, k[dst], v[dst], n, dbits * p, gh, ticket, state);
+        else if (dbits == 9) launch(k_radix_onesweep<9>, nb, kRadixThreads, 0, st, kin, vin, k[dst], v[dst], n, dbits * p, gh, ticket, state);
+        else launch(k_radix_onesweep<10>, nb, kRadixThreads, 0, st, kin, vin, k[dst], v[dst], n, dbits * p, gh, ticket, state);
         kin = k[dst];
         vin = v[dst];
         *result_buf = dst;
@@ -246,6 +307,7 @@ uint32_t group_table_cap(int64_t n) {
 // Large fills run as a kernel: the driver may hand a big cudaMemsetAsync to a copy engine, where it queues behind an
 // upload in flight on another stream (measured: the end-to-end loop lost its copy / compute overlap, 12.6 -> 15.3 ms).
 __global__ void k_fill_u32(uint32_t *__restrict__ p, uint32_t v, size_t count) {
+    pdl_enter();
     const size_t n16 = count / 4;
     const uint4 q = make_uint4(v, v, v, v);
     uint4 *p16 = reinterpret_cast<uint4 *>(p);
@@ -262,7 +324,7 @@ int fill_u32(void *ptr, uint32_t value, size_t count, cudaStream_t st) {
     }
     if ((uintptr_t)ptr & 15u) { set_error("fill_u32: unaligned fill of a non-byte pattern"); return PG_EINVAL; }
     const size_t want = (count / 4 + 255) / 256 + 1;
-    k_fill_u32<<<(unsigned)(want < (size_t)kNumSM * 16 ? want : (size_t)kNumSM * 16), 256, 0, st>>>((uint32_t *)ptr, value, count);
+    launch(k_fill_u32, (unsigned)(want < (size_t)kNumSM * 16 ? want : (size_t)kNumSM * 16), 256, 0, st, (uint32_t *)ptr, value, count);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }
@@ -271,6 +333,7 @@ int fill_u32(void *ptr, uint32_t value, size_t count, cudaStream_t st) {
 // table is built slot_gid holds the smallest point index of the slot's group (unsigned atomicMin), afterwards its group id.
 __global__ void k_group_insert(const int4 *__restrict__ keys, int64_t n, int32_t *slot_rep, int32_t *slot_min,
                                uint32_t cap, int32_t *__restrict__ pslot) {
+    pdl_enter();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const int4 k = keys[i];
@@ -312,19 +375,23 @@ struct GroupPublishStore {
     }
 };
 
-// every point takes its group's id and counts itself; *cnt_max (optional) receives the largest group size: the
+// every point takes its group's id and counts itself; WITH_MAX: *cnt_max receives the largest group size -- the
 // increment that completes the fullest group returns its final size, so the maximum over all increments is it
+// (without it the increment is a fire-and-forget reduction)
+template <bool WITH_MAX>
 __global__ void __launch_bounds__(256) k_group_assign(const int32_t *__restrict__ pslot, const int32_t *__restrict__ slot_gid,
                                                       int64_t n, int32_t *__restrict__ gid, int32_t *__restrict__ cnt,
                                                       int64_t *cnt_max) {
+    pdl_enter();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int mine = 0;
     if (i < n) {
         int g = slot_gid[pslot[i]];
         gid[i] = g;
-        mine = atomicAdd(&cnt[g], 1) + 1;
+        if (WITH_MAX) mine = atomicAdd(&cnt[g], 1) + 1;
+        else atomicAdd(&cnt[g], 1);
     }
-    if (cnt_max) {
+    if (WITH_MAX) {
         __shared__ int s_max;
         if (threadIdx.x == 0) s_max = 0;
         __syncthreads();
@@ -349,10 +416,11 @@ int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot, int3
         PG_TRY(fill_u32(tab.slot_gid, 0xffffffffu, tab.cap, st));
     }
     PG_TRY(fill_u32(cnt, 0u, (size_t)(cnt_len > n ? cnt_len : n), st));
-    k_group_insert<<<nb, T, 0, st>>>(keys, n, tab.slot_rep, tab.slot_gid, tab.cap, pslot);
+    launch(k_group_insert, nb, T, 0, st, keys, n, tab.slot_rep, tab.slot_gid, tab.cap, pslot);
     PG_TRY(scan_fused(GroupFlagLoad{pslot, tab.slot_gid}, GroupPublishStore{pslot, tab.slot_gid, keys, tab.slot_key}, n, nGroups,
                       scan_tmp, st));
-    k_group_assign<<<nb, T, 0, st>>>(pslot, tab.slot_gid, n, gid, cnt, cnt_max);
+    if (cnt_max) launch(k_group_assign<true>, nb, T, 0, st, pslot, tab.slot_gid, n, gid, cnt, cnt_max);
+    else launch(k_group_assign<false>, nb, T, 0, st, pslot, tab.slot_gid, n, gid, cnt, cnt_max);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

@@ -86,6 +86,7 @@ __device__ __forceinline__ int scan_pad(int i) { return i + (i >> 5); }
 template <typename Load, typename Store>
 __global__ void __launch_bounds__(kScanThreads) k_scan_fused(Load load, Store store, int64_t n, unsigned long long *tmp,
                                                              int64_t *__restrict__ total) {
+    pdl_enter();
     __shared__ int warp_tot[32];
     __shared__ long long s_tile, s_prefix;
     __shared__ int s_val[kScanTile + kScanTile / 32], s_pre[kScanTile + kScanTile / 32];
@@ -128,7 +129,7 @@ int scan_fused(Load load, Store store, int64_t n, int64_t *total, int64_t *tmp, 
     }
     const int64_t nb = div_up(n, kScanTile);
     if (!tmp_is_zero) PG_CUDA(cudaMemsetAsync(tmp, 0, (size_t)(nb + 1) * sizeof(int64_t), st));
-    k_scan_fused<<<(unsigned)nb, kScanThreads, 0, st>>>(load, store, n, reinterpret_cast<unsigned long long *>(tmp), total);
+    launch(k_scan_fused<Load, Store>, (unsigned)nb, kScanThreads, 0, st, load, store, n, reinterpret_cast<unsigned long long *>(tmp), total);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

@@ -23,6 +23,7 @@ __device__ __forceinline__ unsigned long long pack_key(float v, int row) {
 
 template <int MODE>
 __global__ void k_seg_init(void *slots, int64_t n) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (MODE == kMaxArg) ((unsigned long long *)slots)[i] = pack_key(-INFINITY, -1);
         else if (MODE == kMax) ((unsigned *)slots)[i] = f2ord(-INFINITY);
@@ -32,6 +33,7 @@ __global__ void k_seg_init(void *slots, int64_t n) {
 
 template <int MODE>
 __global__ void k_seg_decode(void *slots, float *__restrict__ out, int32_t *__restrict__ maxidx, int64_t n) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         if (MODE == kMaxArg) {
             unsigned long long k = ((const unsigned long long *)slots)[i];
@@ -58,6 +60,7 @@ __device__ __forceinline__ void seg_merge(float v2, int a2, float &best, int &ar
 template <int MODE, int V>
 __global__ void __launch_bounds__(256) k_seg_reduce(const float *__restrict__ inp, const int32_t *__restrict__ offsets,
                                                     void *slots, int32_t nRows, int32_t nP, int32_t C, int32_t R) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int64_t r0 = tile * R, r1 = r0 + R;
@@ -146,7 +149,7 @@ static int seg_reduce_launch(const float *inp, const int32_t *offsets, float *ou
     if (nslot == 0) return PG_OK;
     PG_CHECK_ARG(offsets && out && slots && (inp || nRows == 0), "null pointer");
     const unsigned ig = (unsigned)(div_up(nslot, 256) < kNumSM * 8 ? div_up(nslot, 256) : kNumSM * 8);
-    k_seg_init<MODE><<<ig, 256, 0, st>>>(slots, nslot);
+    launch(k_seg_init<MODE>, ig, 256, 0, st, slots, nslot);
     if (nRows > 0) {
         int V = 1;
         if (C % 4 == 0 && (uintptr_t)inp % 16 == 0) V = 4;
@@ -155,11 +158,11 @@ static int seg_reduce_launch(const float *inp, const int32_t *offsets, float *ou
         if (R < 32) R = 32;
         const int64_t tiles = div_up(nRows, R);
         const unsigned grid = (unsigned)div_up(tiles, 8);
-        if (V == 4) k_seg_reduce<MODE, 4><<<grid, 256, 0, st>>>(inp, offsets, slots, nRows, nP, C, R);
-        else if (V == 2) k_seg_reduce<MODE, 2><<<grid, 256, 0, st>>>(inp, offsets, slots, nRows, nP, C, R);
-        else k_seg_reduce<MODE, 1><<<grid, 256, 0, st>>>(inp, offsets, slots, nRows, nP, C, R);
+        if (V == 4) launch(k_seg_reduce<MODE, 4>, grid, 256, 0, st, inp, offsets, slots, nRows, nP, C, R);
+        else if (V == 2) launch(k_seg_reduce<MODE, 2>, grid, 256, 0, st, inp, offsets, slots, nRows, nP, C, R);
+        else launch(k_seg_reduce<MODE, 1>, grid, 256, 0, st, inp, offsets, slots, nRows, nP, C, R);
     }
-    k_seg_decode<MODE><<<ig, 256, 0, st>>>(slots, out, maxidx, nslot);
+    launch(k_seg_decode<MODE>, ig, 256, 0, st, slots, out, maxidx, nslot);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }
@@ -167,6 +170,7 @@ static int seg_reduce_launch(const float *inp, const int32_t *offsets, float *ou
 // roipool_bp: d_feats[argmax][c] += d_out[p][c]  (roipool.cu:42-49)
 __global__ void k_roipool_bp(float *d_feats, const int32_t *__restrict__ maxidx, const float *__restrict__ d_out,
                              int64_t n, int32_t C) {
+    pdl_enter();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int a = __ldg(maxidx + i);
         if (a >= 0) atomicAdd(d_feats + (int64_t)a * C + (i % C), __ldg(d_out + i));
@@ -187,6 +191,7 @@ constexpr int kMeanTile = kMeanThreads * kMeanPer;    // 2048 floats per buffer
 __global__ void __launch_bounds__(kMeanThreads) k_sec_mean(const float *__restrict__ inp,
                                                            const int32_t *__restrict__ offsets,
                                                            float *__restrict__ out, int32_t nP, int32_t C) {
+    pdl_enter();
     __shared__ float buf[2][kMeanTile];
     const int tid = threadIdx.x;
     const int rowsPerTile = kMeanTile / C;            // C <= kMeanTile guaranteed by the launcher
@@ -265,6 +270,7 @@ __global__ void __launch_bounds__(kMeanThreads) k_sec_mean(const float *__restri
 // any C: one thread per (proposal, channel), straight from global memory
 __global__ void k_sec_mean_wide(const float *__restrict__ inp, const int32_t *__restrict__ offsets,
                                 float *__restrict__ out, int32_t nP, int32_t C) {
+    pdl_enter();
     const int64_t n = (int64_t)nP * C;
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
         const int p = (int)(t / C), c = (int)(t - (int64_t)p * C);
@@ -286,6 +292,7 @@ __global__ void k_sec_mean_wide(const float *__restrict__ inp, const int32_t *__
 __global__ void __launch_bounds__(256) k_iou_count(const int32_t *__restrict__ pidx, const int32_t *__restrict__ poff,
                                                    const int64_t *__restrict__ labels, int32_t *counts, int32_t nInst,
                                                    int32_t nP) {
+    pdl_enter();
     const int S = __ldg(poff + nP);                                   // rows of proposals_idx (known on the device only)
     const int lane = threadIdx.x & 31;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -310,6 +317,7 @@ __global__ void __launch_bounds__(256) k_iou_count(const int32_t *__restrict__ p
 
 __global__ void __launch_bounds__(256) k_iou_final(const int32_t *__restrict__ poff, const int32_t *__restrict__ pointnum,
                                                    float *iou, int32_t nInst, int64_t total) {
+    pdl_enter();
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= total) return;
     const int p = (int)(t / nInst), g = (int)(t - (int64_t)p * nInst);
@@ -347,7 +355,7 @@ extern "C" int pg_roipool_bp(float *d_feats, const int32_t *offsets, const int32
     if (n == 0) return PG_OK;
     PG_CHECK_ARG(d_feats && maxidx && d_out, "null pointer");
     const unsigned grid = (unsigned)(div_up(n, 256) < kNumSM * 16 ? div_up(n, 256) : kNumSM * 16);
-    k_roipool_bp<<<grid, 256, 0, (cudaStream_t)stream>>>(d_feats, maxidx, d_out, n, C);
+    launch(k_roipool_bp, grid, 256, 0, (cudaStream_t)stream, d_feats, maxidx, d_out, n, C);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }
@@ -371,10 +379,10 @@ extern "C" int pg_sec_mean(const float *inp, const int32_t *offsets, float *out,
     PG_KTIME("k_sec_mean", st);
     if (C <= 4 * kMeanThreads) {
         const unsigned grid = (unsigned)(nProposal < kNumSM * 8 ? nProposal : kNumSM * 8);
-        k_sec_mean<<<grid, kMeanThreads, 0, st>>>(inp, offsets, out, nProposal, C);
+        launch(k_sec_mean, grid, kMeanThreads, 0, st, inp, offsets, out, nProposal, C);
     } else {
         const int64_t n = (int64_t)nProposal * C;
-        k_sec_mean_wide<<<(unsigned)div_up(n, 128), 128, 0, st>>>(inp, offsets, out, nProposal, C);
+        launch(k_sec_mean_wide, (unsigned)div_up(n, 128), 128, 0, st, inp, offsets, out, nProposal, C);
     }
     PG_LAUNCH_CHECK();
     return PG_OK;
@@ -391,9 +399,9 @@ extern "C" int pg_get_iou(const int32_t *proposals_idx, const int32_t *proposals
     PG_CHECK_ARG(proposals_idx && instance_labels, "null pointer");
     PG_TRY(fill_u32(proposals_iou, 0u, (size_t)total, st));
     { PG_KTIME("k_iou_count", st);
-    k_iou_count<<<kNumSM * 8, 256, 0, st>>>(proposals_idx, proposals_offset, instance_labels,
+    launch(k_iou_count, kNumSM * 8, 256, 0, st, proposals_idx, proposals_offset, instance_labels,
                                            reinterpret_cast<int32_t *>(proposals_iou), nInstance, nProposal); }
-    k_iou_final<<<(unsigned)div_up(total, 256), 256, 0, st>>>(proposals_offset, instance_pointnum, proposals_iou, nInstance, total);
+    launch(k_iou_final, (unsigned)div_up(total, 256), 256, 0, st, proposals_offset, instance_pointnum, proposals_iou, nInstance, total);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

@@ -45,6 +45,7 @@ static VoxWs vox_layout(void *ws, size_t ws_bytes, int64_t N) {
 
 // int64 [N,4] -> int4 keys; every column narrowed to int32 like Point<3>/Int (voxelize.cpp:95-97)
 __global__ void k_vox_keys(const int64_t *__restrict__ coords, int64_t N, int4 *__restrict__ keys) {
+    pdl_enter();
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const longlong2 *p = reinterpret_cast<const longlong2 *>(coords) + i * 2;
@@ -59,6 +60,7 @@ constexpr int kVoxRankMax = 32;        // largest voxel (points) served by the s
 // The points of every voxel side by side (voxel v: grouped[voff[v] .. voff[v] + cnt[v]), in claim order).
 __global__ void k_vox_scatter(const int32_t *__restrict__ input_map, const int32_t *__restrict__ voff, int64_t N,
                               int32_t *cursor, uint32_t *__restrict__ grouped) {
+    pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int v = __ldg(input_map + i);
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(256) k_vox_rank(const int64_t *__restrict__ co
                                                   const int32_t *__restrict__ cnt, const int32_t *__restrict__ voff,
                                                   const uint32_t *__restrict__ grouped, int64_t N, int32_t W, int mode,
                                                   int64_t *__restrict__ out_coords, int32_t *__restrict__ out_map) {
+    pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int v = __ldg(input_map + i);
@@ -121,6 +124,7 @@ template <bool VEC>
 __global__ void k_vox_fill(const int64_t *__restrict__ coords, const int32_t *__restrict__ cnt,
                            const int32_t *__restrict__ voff, const uint32_t *__restrict__ sorted, int32_t M,
                            int32_t W, int mode, int64_t *__restrict__ out_coords, int32_t *__restrict__ out_map) {
+    pdl_enter();
     const int64_t total = (int64_t)M * W;
     if (VEC) {
         const int64_t quads = total >> 2;
@@ -204,6 +208,7 @@ template <int V>
 __global__ void __launch_bounds__(256) k_voxelize_fp(const float *__restrict__ feats, float *__restrict__ out,
                                                      const int32_t *__restrict__ rules, int32_t M, int32_t W,
                                                      int32_t Cv, int average) {
+    pdl_enter();
     using T = typename Vec<V>::T;
     const T *__restrict__ f = reinterpret_cast<const T *>(feats);
     T *__restrict__ o = reinterpret_cast<T *>(out);
@@ -242,6 +247,7 @@ template <int V, int G, int NS>
 __global__ void __launch_bounds__(256, (V * NS <= 6 ? 8 : (V * NS <= 8 ? 6 : 4))) k_voxelize_fp_rows(const float *__restrict__ feats, float *__restrict__ out,
                                                           const int32_t *__restrict__ rules, int32_t M, int32_t W,
                                                           int32_t Cv, int average) {
+    pdl_enter();
     using T = typename Vec<V>::T;
     constexpr int kRows = 32 / G;                     // rows per warp
     const T *__restrict__ f = reinterpret_cast<const T *>(feats);
@@ -279,6 +285,7 @@ __global__ void __launch_bounds__(256, (V * NS <= 6 ? 8 : (V * NS <= 8 ? 6 : 4))
 template <int V, typename I>
 __global__ void __launch_bounds__(256) k_gather_rows(const float *__restrict__ src, const I *__restrict__ idx,
                                                      float *__restrict__ dst, int64_t nIdx, int32_t Cv) {
+    pdl_enter();
     using T = typename Vec<V>::T;
     const T *__restrict__ s = reinterpret_cast<const T *>(src);
     T *__restrict__ d = reinterpret_cast<T *>(dst);
@@ -295,6 +302,7 @@ template <int V>
 __global__ void __launch_bounds__(256) k_voxelize_bp(const float *__restrict__ d_out, float *d_feats,
                                                      const int32_t *__restrict__ rules, int32_t M, int32_t W,
                                                      int32_t Cv, int average) {
+    pdl_enter();
     using T = typename Vec<V>::T;
     const T *__restrict__ g = reinterpret_cast<const T *>(d_out);
     T *df = reinterpret_cast<T *>(d_feats);
@@ -335,12 +343,12 @@ static int voxelize_launch(bool fp, const float *src, float *dst, const int32_t 
     const unsigned rgrid = (unsigned)(row_blocks < (int64_t)kNumSM * 64 ? row_blocks : (int64_t)kNumSM * 64);
 #define PG_VOX(VV)                                                                                     \
     if (rows) {                                                                                        \
-        if (Cv <= 64) k_voxelize_fp_rows<VV, 32, 2><<<rgrid, 256, 0, st>>>(src, dst, rules, M, W, Cv, average);      \
-        else if (Cv <= 96) k_voxelize_fp_rows<VV, 32, 3><<<rgrid, 256, 0, st>>>(src, dst, rules, M, W, Cv, average); \
-        else k_voxelize_fp_rows<VV, 32, 4><<<rgrid, 256, 0, st>>>(src, dst, rules, M, W, Cv, average);               \
+        if (Cv <= 64) launch(k_voxelize_fp_rows<VV, 32, 2>, rgrid, 256, 0, st, src, dst, rules, M, W, Cv, average);      \
+        else if (Cv <= 96) launch(k_voxelize_fp_rows<VV, 32, 3>, rgrid, 256, 0, st, src, dst, rules, M, W, Cv, average); \
+        else launch(k_voxelize_fp_rows<VV, 32, 4>, rgrid, 256, 0, st, src, dst, rules, M, W, Cv, average);               \
     }                                                                                                  \
-    else if (fp) k_voxelize_fp<VV><<<grid, 256, 0, st>>>(src, dst, rules, M, W, Cv, average);          \
-    else k_voxelize_bp<VV><<<grid, 256, 0, st>>>(src, dst, rules, M, W, Cv, average)
+    else if (fp) launch(k_voxelize_fp<VV>, grid, 256, 0, st, src, dst, rules, M, W, Cv, average);          \
+    else launch(k_voxelize_bp<VV>, grid, 256, 0, st, src, dst, rules, M, W, Cv, average)
     { PG_KTIME(fp ? "k_voxelize_fp" : "k_voxelize_bp", st);
     if (V == 4) { PG_VOX(4); } else if (V == 2) { PG_VOX(2); } else { PG_VOX(1); } }
 #undef PG_VOX
@@ -370,7 +378,7 @@ extern "C" int pg_voxelize_idx_map(const int64_t *coords, int64_t N, int mode, i
     VoxWs w = vox_layout(ws, ws_bytes, N);
     if (!w.ok) { set_error("pg_voxelize_idx_map: workspace too small (%zu < %zu)", ws_bytes, w.used); return PG_EWORKSPACE; }
     PG_CUDA(cudaMemsetAsync(w.scalars, 0, 4 * sizeof(int64_t), st));
-    k_vox_keys<<<(unsigned)div_up(N, 256), 256, 0, st>>>(coords, N, w.keys);
+    launch(k_vox_keys, (unsigned)div_up(N, 256), 256, 0, st, coords, N, w.keys);
     PG_TRY(group_int4(w.keys, N, w.tab, w.pslot, input_map, w.cnt, w.scalars, w.scan_tmp, st, w.scalars + 1));   // + the largest voxel
     PG_LAUNCH_CHECK();
     int64_t h[2];
@@ -398,9 +406,9 @@ extern "C" int pg_voxelize_idx_fill(const int64_t *coords, const int32_t *input_
         int32_t *cursor = reinterpret_cast<int32_t *>(w.kA);
         PG_TRY(fill_u32(cursor, 0u, (size_t)M, st));
         PG_TRY(fill_u32(output_map, 0u, (size_t)M * W, st));           // the rows' zero padding
-        k_vox_scatter<<<(unsigned)div_up(N, 256), 256, 0, st>>>(input_map, w.voff, N, cursor, w.vA);
+        launch(k_vox_scatter, (unsigned)div_up(N, 256), 256, 0, st, input_map, w.voff, N, cursor, w.vA);
         PG_KTIME("k_vox_rank", st);
-        k_vox_rank<<<(unsigned)div_up(N, 256), 256, 0, st>>>(coords, input_map, w.cnt, w.voff, w.vA, N, W, mode, output_coords, output_map);
+        launch(k_vox_rank, (unsigned)div_up(N, 256), 256, 0, st, coords, input_map, w.cnt, w.voff, w.vA, N, W, mode, output_coords, output_map);
         PG_LAUNCH_CHECK();
         return PG_OK;
     }
@@ -416,8 +424,8 @@ extern "C" int pg_voxelize_idx_fill(const int64_t *coords, const int32_t *input_
     const int64_t units = vec ? (total >> 2 > (int64_t)M * 4 ? total >> 2 : (int64_t)M * 4) : total;
     const unsigned grid = (unsigned)(div_up(units, 256) < (int64_t)kNumSM * 32 ? div_up(units, 256) : (int64_t)kNumSM * 32);
     { PG_KTIME("k_vox_fill", st);
-    if (vec) k_vox_fill<true><<<grid, 256, 0, st>>>(coords, w.cnt, w.voff, sorted, M, W, mode, output_coords, output_map);
-    else k_vox_fill<false><<<grid, 256, 0, st>>>(coords, w.cnt, w.voff, sorted, M, W, mode, output_coords, output_map); }
+    if (vec) launch(k_vox_fill<true>, grid, 256, 0, st, coords, w.cnt, w.voff, sorted, M, W, mode, output_coords, output_map);
+    else launch(k_vox_fill<false>, grid, 256, 0, st, coords, w.cnt, w.voff, sorted, M, W, mode, output_coords, output_map); }
     PG_LAUNCH_CHECK();
     return PG_OK;
 }
@@ -454,8 +462,8 @@ extern "C" int pg_gather_rows(const float *src, const void *idx, int idx_is_int6
     const int64_t total = nIdx * Cv;
     const unsigned grid = (unsigned)(div_up(total, 256) < (int64_t)kNumSM * 64 ? div_up(total, 256) : (int64_t)kNumSM * 64);
 #define PG_GATHER(VV)                                                                                              \
-    if (idx_is_int64) k_gather_rows<VV, int64_t><<<grid, 256, 0, st>>>(src, (const int64_t *)idx, dst, nIdx, Cv); \
-    else k_gather_rows<VV, int32_t><<<grid, 256, 0, st>>>(src, (const int32_t *)idx, dst, nIdx, Cv)
+    if (idx_is_int64) launch(k_gather_rows<VV, int64_t>, grid, 256, 0, st, src, (const int64_t *)idx, dst, nIdx, Cv); \
+    else launch(k_gather_rows<VV, int32_t>, grid, 256, 0, st, src, (const int32_t *)idx, dst, nIdx, Cv)
     if (V == 4) { PG_GATHER(4); } else if (V == 2) { PG_GATHER(2); } else { PG_GATHER(1); }
 #undef PG_GATHER
     PG_LAUNCH_CHECK();
