@@ -55,8 +55,10 @@ __device__ __forceinline__ int cell_coord(float x, double inv_s) {
 }
 
 __global__ void k_bq_keys(const float *__restrict__ xyz, const int32_t *__restrict__ batch_idxs, int32_t n,
-                          double inv_s, int4 *__restrict__ keys) {
+                          double inv_s, int4 *__restrict__ keys, Fill table, Fill cnt) {
     pdl_enter();
+    grid_fill(table);      // the grouping's hash table and counts start clean
+    grid_fill(cnt);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float x = __ldg(xyz + 3 * (int64_t)i), y = __ldg(xyz + 3 * (int64_t)i + 1), z = __ldg(xyz + 3 * (int64_t)i + 2);
@@ -985,14 +987,14 @@ extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs,
     const double s = fabs((double)radius) * 1.0001;
     const double inv_s = (s > 0.0 && isfinite(s)) ? 1.0 / s : 0.0;   // r = 0 / inf / NaN: one cell per scene
     PG_CUDA(cudaMemsetAsync(w.scalars, 0, 8 * sizeof(int64_t), st));
-    launch(k_bq_keys, (unsigned)div_up(n, 256), 256, 0, st, xyz, batch_idxs, n, inv_s, w.keys);
-    PG_TRY(group_int4(w.keys, n, w.tab, w.pslot, w.cell, w.ccnt, w.scalars, w.scan_tmp, st, nullptr, (int64_t)n + 1));
-    PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
-    // scratch of the scatter, adjacent in the workspace: the cells' cursors, the complement of their smallest and their
-    // largest point index
+    launch(k_bq_keys, (unsigned)div_up(n, 256), 256, 0, st, xyz, batch_idxs, n, inv_s, w.keys, group_table_fill(w.tab), Fill{(uint32_t *)w.ccnt, (size_t)n + 1, 0u});
+    // scratch of the scatter, adjacent in the workspace (cleared by the grouping's last kernel): the cells' cursors, the
+    // complement of their smallest and their largest point index
     uint32_t *sorted_pt = w.kA, *cmin = w.kB, *cmax = w.vB;
     int32_t *cursor = reinterpret_cast<int32_t *>(w.vA);
-    PG_TRY(fill_u32(cursor, 0u, ((size_t)((char *)w.vB - (char *)w.vA) + align_up((size_t)n * 4)) / 4, st));   // to the padded end of vB
+    PG_TRY(group_int4(w.keys, n, w.tab, w.pslot, w.cell, w.ccnt, w.scalars, w.scan_tmp, st, nullptr,
+                      Fill{w.vA, ((size_t)((char *)w.vB - (char *)w.vA) + align_up((size_t)n * 4)) / 4, 0u}));   // to the padded end of vB
+    PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
     launch(k_bq_scatter, (unsigned)div_up(n, 256), 256, 0, st, w.cell, w.cstart, n, cursor, sorted_pt, cmin, cmax);
     { PG_KTIME("k_bq_neighbours", st);
     launch(k_bq_neighbours, kNumSM * PG_RESIDENT(k_bq_neighbours, 256, 0) * 2, 256, 0, st, w.keys, w.tab, sorted_pt, w.cstart, w.ccnt, w.scalars, w.nbr, w.kc, w.dense, cmin, cmax, w.crange); }

@@ -115,8 +115,9 @@ __global__ void k_cl_prep(const int32_t *__restrict__ label, const int32_t *__re
                           const int2 *__restrict__ start_len, int32_t N, int64_t nActive, int hook,
                           uint2 *__restrict__ pl, uint32_t *__restrict__ trunc, int32_t *__restrict__ last,
                           int32_t *__restrict__ root, int32_t *__restrict__ lab, uint32_t *__restrict__ skey, int shift,
-                          unsigned long long *scalars, const int4 *__restrict__ samples) {
+                          unsigned long long *scalars, const int4 *__restrict__ samples, Fill sizes) {
     pdl_enter();
+    grid_fill(sizes);      // the label pass's counters
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     bool full = false;
     if (v < N) {
@@ -816,7 +817,6 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
     const bool wide = nActive / N >= 12;          // lanes per neighbour list: 32 for long lists, 8 for short
     const unsigned eg = kNumSM * 8;
     PG_CUDA(cudaMemsetAsync(w.scalars, 0, 12 * sizeof(unsigned long long), st));
-    PG_TRY(fill_u32(w.size, 0u, (size_t)N + 1, st));
     // sweep order = ascending segment start, on the top 16 bits of the position (two radix passes)
     int abits = 0;
     while ((1ll << abits) <= nActive) abits++;
@@ -839,7 +839,7 @@ static int bfs_count_impl(const int32_t *semantic_label, const int32_t *ball_que
     }
     launch(k_cl_prep, (unsigned)div_up((int64_t)N + 32, 256), 256, 0, st, semantic_label, ball_query_idxs, sl, N, nActive,
                                                                      generic ? 0 : 1, w.pl, w.trunc, w.last, w.root, w.lab,
-                                                                     w.key0, shift, w.scalars, samples);
+                                                                     w.key0, shift, w.scalars, samples, Fill{(uint32_t *)w.size, (size_t)N + 1, 0u});
     if (!use_generic) {
         // the cell pass pays off on long lists only: it reads ~27 cells' worth of candidates per cell, which on
         // short lists (raw coordinates, ~5 neighbours per point) is more than the edges themselves

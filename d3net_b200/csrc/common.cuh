@@ -126,6 +126,27 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
+// A second job for a kernel that runs before a scratch buffer's first use anyway: clear it, grid-stride, instead of a
+// fill launch of its own (a large cudaMemsetAsync may be handed to a copy engine and queue behind an upload -- prim.cu).
+struct Fill {
+    uint32_t *p;
+    size_t n;       // 32-bit words
+    uint32_t v;
+};
+__device__ __forceinline__ void grid_fill(const Fill &f) {
+    if (f.n == 0) return;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (size_t)gridDim.x * blockDim.x;
+    if (((uintptr_t)f.p & 15u) == 0) {
+        const size_t n16 = f.n >> 2;
+        const uint4 q = make_uint4(f.v, f.v, f.v, f.v);
+        uint4 *p16 = reinterpret_cast<uint4 *>(f.p);
+        for (size_t i = t; i < n16; i += nt) p16[i] = q;
+        if (t < (f.n & 3)) f.p[(n16 << 2) + t] = f.v;
+    } else {
+        for (size_t i = t; i < f.n; i += nt) f.p[i] = f.v;
+    }
+}
+
 // float <-> order-preserving uint32 (total order on non-NaN floats)
 __device__ __forceinline__ unsigned f2ord(float f) {
     unsigned u = __float_as_uint(f);
@@ -174,11 +195,14 @@ struct GroupTable {
     int4 *slot_key;     // [cap] or null: the slot's key itself, for lookups that should not chase slot_rep -> keys[]
 };
 uint32_t group_table_cap(int64_t n);
-// cnt_max (optional, device, zeroed by the caller): the largest group size.  cnt_len: how many entries of cnt to zero
-// (>= n; callers that scan cnt over n + 1 entries pass n + 1).
+// cnt_max (optional, device, zeroed by the caller): the largest group size.
+// The CALLER's key kernel clears the table and the counts on its way (grid_fill of group_table_fill() and of cnt, which
+// no kernel has touched yet at that point); `extra` is cleared by the last kernel of the grouping for whoever comes next.
 int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot /*[n] scratch*/,
                int32_t *gid /*[n]*/, int32_t *cnt /*[n]*/, int64_t *nGroups, int64_t *scan_tmp,
-               cudaStream_t st, int64_t *cnt_max = nullptr, int64_t cnt_len = 0);
+               cudaStream_t st, int64_t *cnt_max = nullptr, Fill extra = Fill{nullptr, 0, 0});
+// slot_rep and slot_gid are adjacent in every workspace layout: one range of 0xffffffff
+inline Fill group_table_fill(const GroupTable &tab) { return Fill{reinterpret_cast<uint32_t *>(tab.slot_rep), (size_t)tab.cap * 2, 0xffffffffu}; }
 
 __device__ __forceinline__ int group_lookup(const int4 *keys, const GroupTable &tab, int4 k) {
     unsigned h = hash4(k.x, k.y, k.z, k.w) & (tab.cap - 1);

@@ -381,8 +381,9 @@ struct GroupPublishStore {
 template <bool WITH_MAX>
 __global__ void __launch_bounds__(256) k_group_assign(const int32_t *__restrict__ pslot, const int32_t *__restrict__ slot_gid,
                                                       int64_t n, int32_t *__restrict__ gid, int32_t *__restrict__ cnt,
-                                                      int64_t *cnt_max) {
+                                                      int64_t *cnt_max, Fill extra) {
     pdl_enter();
+    grid_fill(extra);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int mine = 0;
     if (i < n) {
@@ -403,24 +404,19 @@ __global__ void __launch_bounds__(256) k_group_assign(const int32_t *__restrict_
 }
 
 int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot, int32_t *gid, int32_t *cnt,
-               int64_t *nGroups, int64_t *scan_tmp, cudaStream_t st, int64_t *cnt_max, int64_t cnt_len) {
+               int64_t *nGroups, int64_t *scan_tmp, cudaStream_t st, int64_t *cnt_max, Fill extra) {
     if (n <= 0) {
         PG_CUDA(cudaMemsetAsync(nGroups, 0, sizeof(int64_t), st));
         return PG_OK;
     }
+    if (tab.slot_gid != tab.slot_rep + tab.cap) { set_error("group_int4: slot_rep and slot_gid must be adjacent"); return PG_EINVAL; }
     const int T = 256;
     const unsigned nb = (unsigned)div_up(n, T);
-    if (tab.slot_gid == tab.slot_rep + tab.cap) PG_TRY(fill_u32(tab.slot_rep, 0xffffffffu, (size_t)tab.cap * 2, st));
-    else {
-        PG_TRY(fill_u32(tab.slot_rep, 0xffffffffu, tab.cap, st));
-        PG_TRY(fill_u32(tab.slot_gid, 0xffffffffu, tab.cap, st));
-    }
-    PG_TRY(fill_u32(cnt, 0u, (size_t)(cnt_len > n ? cnt_len : n), st));
     launch(k_group_insert, nb, T, 0, st, keys, n, tab.slot_rep, tab.slot_gid, tab.cap, pslot);
     PG_TRY(scan_fused(GroupFlagLoad{pslot, tab.slot_gid}, GroupPublishStore{pslot, tab.slot_gid, keys, tab.slot_key}, n, nGroups,
                       scan_tmp, st));
-    if (cnt_max) launch(k_group_assign<true>, nb, T, 0, st, pslot, tab.slot_gid, n, gid, cnt, cnt_max);
-    else launch(k_group_assign<false>, nb, T, 0, st, pslot, tab.slot_gid, n, gid, cnt, cnt_max);
+    if (cnt_max) launch(k_group_assign<true>, nb, T, 0, st, pslot, tab.slot_gid, n, gid, cnt, cnt_max, extra);
+    else launch(k_group_assign<false>, nb, T, 0, st, pslot, tab.slot_gid, n, gid, cnt, cnt_max, extra);
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

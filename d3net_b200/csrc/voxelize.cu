@@ -44,8 +44,10 @@ static VoxWs vox_layout(void *ws, size_t ws_bytes, int64_t N) {
 }
 
 // int64 [N,4] -> int4 keys; every column narrowed to int32 like Point<3>/Int (voxelize.cpp:95-97)
-__global__ void k_vox_keys(const int64_t *__restrict__ coords, int64_t N, int4 *__restrict__ keys) {
+__global__ void k_vox_keys(const int64_t *__restrict__ coords, int64_t N, int4 *__restrict__ keys, Fill table, Fill cnt) {
     pdl_enter();
+    grid_fill(table);      // the grouping's hash table and counts start clean
+    grid_fill(cnt);
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const longlong2 *p = reinterpret_cast<const longlong2 *>(coords) + i * 2;
@@ -59,8 +61,9 @@ constexpr int kVoxRankMax = 32;        // largest voxel (points) served by the s
 
 // The points of every voxel side by side (voxel v: grouped[voff[v] .. voff[v] + cnt[v]), in claim order).
 __global__ void k_vox_scatter(const int32_t *__restrict__ input_map, const int32_t *__restrict__ voff, int64_t N,
-                              int32_t *cursor, uint32_t *__restrict__ grouped) {
+                              int32_t *cursor, uint32_t *__restrict__ grouped, Fill rows) {
     pdl_enter();
+    grid_fill(rows);
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= N) return;
     const int v = __ldg(input_map + i);
@@ -378,8 +381,9 @@ extern "C" int pg_voxelize_idx_map(const int64_t *coords, int64_t N, int mode, i
     VoxWs w = vox_layout(ws, ws_bytes, N);
     if (!w.ok) { set_error("pg_voxelize_idx_map: workspace too small (%zu < %zu)", ws_bytes, w.used); return PG_EWORKSPACE; }
     PG_CUDA(cudaMemsetAsync(w.scalars, 0, 4 * sizeof(int64_t), st));
-    launch(k_vox_keys, (unsigned)div_up(N, 256), 256, 0, st, coords, N, w.keys);
-    PG_TRY(group_int4(w.keys, N, w.tab, w.pslot, input_map, w.cnt, w.scalars, w.scan_tmp, st, w.scalars + 1));   // + the largest voxel
+    launch(k_vox_keys, (unsigned)div_up(N, 256), 256, 0, st, coords, N, w.keys, group_table_fill(w.tab), Fill{(uint32_t *)w.cnt, (size_t)N, 0u});
+    // + the largest voxel; the fill phase's cursors (kA) are cleared on the way
+    PG_TRY(group_int4(w.keys, N, w.tab, w.pslot, input_map, w.cnt, w.scalars, w.scan_tmp, st, w.scalars + 1, Fill{w.kA, (size_t)N, 0u}));
     PG_LAUNCH_CHECK();
     int64_t h[2];
     PG_CUDA(cudaMemcpyAsync(h, w.scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -404,9 +408,8 @@ extern "C" int pg_voxelize_idx_fill(const int64_t *coords, const int32_t *input_
     if (maxActive <= kVoxRankMax) {
         // no sort: points side by side per voxel, then every point finds its column by counting (see k_vox_rank)
         int32_t *cursor = reinterpret_cast<int32_t *>(w.kA);
-        PG_TRY(fill_u32(cursor, 0u, (size_t)M, st));
-        PG_TRY(fill_u32(output_map, 0u, (size_t)M * W, st));           // the rows' zero padding
-        launch(k_vox_scatter, (unsigned)div_up(N, 256), 256, 0, st, input_map, w.voff, N, cursor, w.vA);
+        // the cursors were cleared by the map phase; the scatter clears the rows (their zero padding) for the rank pass
+        launch(k_vox_scatter, (unsigned)div_up(N, 256), 256, 0, st, input_map, w.voff, N, cursor, w.vA, Fill{(uint32_t *)output_map, (size_t)M * W, 0u});
         PG_KTIME("k_vox_rank", st);
         launch(k_vox_rank, (unsigned)div_up(N, 256), 256, 0, st, coords, input_map, w.cnt, w.voff, w.vA, N, W, mode, output_coords, output_map);
         PG_LAUNCH_CHECK();
