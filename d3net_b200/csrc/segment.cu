@@ -267,6 +267,91 @@ __global__ void __launch_bounds__(kMeanThreads) k_sec_mean(const float *__restri
     }
 }
 
+// Narrow rows (C <= 32: the xyz means of clusters_voxelization): warp-specialised.  Warp 0 does nothing but the add
+// chains (lane c = channel c) -- the serial chain of the floor-sized proposal IS the op's run time, 4 cycles per row at
+// best -- while warps 1..3 fetch, divide and stage the NEXT tile in the other buffer; the block meets once per tile.
+// (With everybody dividing and then waiting for the chains: 5.5 cycles per row.)
+constexpr int kMeanWsProducers = kMeanThreads - 32;               // 96 threads
+constexpr int kMeanWsPer = 16;
+constexpr int kMeanWsTile = kMeanWsProducers * kMeanWsPer;       // 1536 floats per buffer
+
+// CT: the row width when it is known at compile time (3: the model's call; shared-memory offsets become immediates), 0 = C.
+template <int CT>
+__global__ void __launch_bounds__(kMeanThreads) k_sec_mean_narrow(const float *__restrict__ inp, const int32_t *__restrict__ offsets,
+                                                                  float *__restrict__ out, int32_t nP, int32_t C_) {
+    pdl_enter();
+    const int C = CT ? CT : C_;
+    __shared__ float buf[2][kMeanWsTile];
+    const int tid = threadIdx.x;
+    const bool chain = tid < 32;
+    const int ptid = tid - 32;                           // producer index 0..95
+    const int rowsPerTile = kMeanWsTile / C;
+    const int tileFloats = rowsPerTile * C;
+    for (int p = blockIdx.x; p < nP; p += gridDim.x) {
+        const int64_t start = __ldg(offsets + p), end = __ldg(offsets + p + 1);
+        const int64_t len = end - start;
+        const float count = (float)(int)len;
+        const float *base = inp + start * C;
+        const int64_t total = len > 0 ? len * C : 0;
+        float a = 0.f;
+        float reg[kMeanWsPer];
+        auto fetch = [&](int64_t pos) {
+#pragma unroll
+            for (int k = 0; k < kMeanWsPer; k++) {
+                const int64_t e = pos + k * kMeanWsProducers + ptid;
+                reg[k] = (k * kMeanWsProducers + ptid < tileFloats && e < total) ? __ldg(base + e) : 0.f;
+            }
+        };
+        auto stage = [&](int b) {
+#pragma unroll
+            for (int k = 0; k < kMeanWsPer; k++) buf[b][k * kMeanWsProducers + ptid] = __fdiv_rn(reg[k], count);
+        };
+        // tile 0 into buffer 0, tile 1 into the producers' registers
+        if (!chain && total > 0) {
+            fetch(0);
+            stage(0);
+            if (tileFloats < total) fetch(tileFloats);
+        }
+        __syncthreads();
+        int cur = 0;
+        for (int64_t pos = 0; pos < total; pos += tileFloats) {
+            const int64_t nflt = (total - pos < tileFloats) ? (total - pos) : tileFloats;
+            if (chain) {
+                if (tid < C) {
+                    const int rows = (int)(nflt / C);
+                    const float *b = &buf[cur][tid];
+                    // A warp issues in order and every add waits 4 cycles for the one before it: the loop holds nothing but
+                    // the adds and, in their shadow, the shared-memory loads of the operands 8 rows ahead (two register
+                    // sets, no moves).
+                    int r = 0;
+                    float q[8], nx[8];
+                    if (rows >= 8) {
+#pragma unroll
+                        for (int u = 0; u < 8; u++) q[u] = b[u * C];
+                        for (; r + 24 <= rows; r += 16) {
+                            const float *bb = b + r * C;
+#pragma unroll
+                            for (int u = 0; u < 8; u++) { a = __fadd_rn(a, q[u]); nx[u] = bb[(8 + u) * C]; }
+#pragma unroll
+                            for (int u = 0; u < 8; u++) { a = __fadd_rn(a, nx[u]); q[u] = bb[(16 + u) * C]; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++) a = __fadd_rn(a, q[u]);
+                        r += 8;
+                    }
+                    for (; r < rows; r++) a = __fadd_rn(a, b[r * C]);
+                }
+            } else if (pos + tileFloats < total) {
+                stage(cur ^ 1);                                              // tile t + 1, fetched one round ago
+                if (pos + 2 * (int64_t)tileFloats < total) fetch(pos + 2 * (int64_t)tileFloats);
+            }
+            __syncthreads();
+            cur ^= 1;
+        }
+        if (chain && tid < C) out[(int64_t)p * C + tid] = a;
+    }
+}
+
 // any C: one thread per (proposal, channel), straight from global memory
 __global__ void k_sec_mean_wide(const float *__restrict__ inp, const int32_t *__restrict__ offsets,
                                 float *__restrict__ out, int32_t nP, int32_t C) {
@@ -377,7 +462,11 @@ extern "C" int pg_sec_mean(const float *inp, const int32_t *offsets, float *out,
     PG_CHECK_ARG(offsets && out, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     PG_KTIME("k_sec_mean", st);
-    if (C <= 4 * kMeanThreads) {
+    if (C <= 32) {
+        const unsigned grid = (unsigned)(nProposal < kNumSM * 8 ? nProposal : kNumSM * 8);
+        if (C == 3) launch(k_sec_mean_narrow<3>, grid, kMeanThreads, 0, st, inp, offsets, out, nProposal, C);
+        else launch(k_sec_mean_narrow<0>, grid, kMeanThreads, 0, st, inp, offsets, out, nProposal, C);
+    } else if (C <= 4 * kMeanThreads) {
         const unsigned grid = (unsigned)(nProposal < kNumSM * 8 ? nProposal : kNumSM * 8);
         launch(k_sec_mean, grid, kMeanThreads, 0, st, inp, offsets, out, nProposal, C);
     } else {

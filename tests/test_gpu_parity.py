@@ -493,7 +493,7 @@ def test_bfs_empty(ops):
 # ------------------------------------------------------------------------------------------------
 # roipool / sec_mean / sec_min / sec_max
 # ------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("C", [1, 3, 5, 16, 40, 134])
+@pytest.mark.parametrize("C", [1, 3, 5, 16, 32, 33, 40, 134])
 def test_roipool_and_sec(ops, oracle, C):
     rng = np.random.default_rng(200 + C)
     off = random_segments(rng, 300, 400, big=60000 if C <= 16 else 3000)
