@@ -759,22 +759,30 @@ struct SizesStore {
     }
 };
 
-// sort key per point: cluster id, or nCluster for points of dropped components (they sort last)
-__global__ void k_cl_keys(const uint32_t *__restrict__ key0, const int32_t *__restrict__ cid, int32_t N, int32_t nCluster,
-                          uint32_t *__restrict__ keys) {
+// sort key per point: cluster id, or nCluster for points of dropped components (they sort last).  One extra block
+// turns the cluster sizes into the offsets (a few hundred to a few thousand entries: not worth a launch of its own).
+__global__ void __launch_bounds__(256) k_cl_keys(const uint32_t *__restrict__ key0, const int32_t *__restrict__ cid, int32_t N,
+                                                 int32_t nCluster, uint32_t *__restrict__ keys, const int32_t *__restrict__ csize,
+                                                 int32_t *__restrict__ cluster_offsets) {
     pdl_enter();
+    if (blockIdx.x == gridDim.x - 1) {                       // offsets[c] = sizes before c; offsets[nCluster] = the total
+        __shared__ int warp_tot[32];
+        int carry = 0;
+        for (int c0 = 0; c0 <= nCluster; c0 += 256) {
+            const int c = c0 + threadIdx.x;
+            const int x = c < nCluster ? csize[c] : 0;
+            int tot;
+            const int incl = block_scan_incl(x, warp_tot, &tot);
+            if (c <= nCluster) cluster_offsets[c] = carry + incl - x;
+            carry += tot;
+        }
+        return;
+    }
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= N) return;
     const uint32_t l = key0[v];
     const int c = cid[l], next = cid[l + 1];
     keys[v] = (next != c) ? (uint32_t)c : (uint32_t)nCluster;
-}
-
-__global__ void k_cl_emit(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int32_t S,
-                          int2 *__restrict__ cluster_idxs) {
-    pdl_enter();
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < S) cluster_idxs[k] = make_int2((int)keys[k], (int)vals[k]);
 }
 
 }  // namespace pg
@@ -1013,17 +1021,13 @@ extern "C" int pg_bfs_cluster_fill(int32_t N, int32_t nCluster, int32_t sumNPoin
     ClWs w = cl_layout(ws, ws_bytes, N);
     if (!w.ok) { set_error("pg_bfs_cluster_fill: workspace too small"); return PG_EWORKSPACE; }
     const unsigned nb = (unsigned)div_up(N, 256);
-    // offsets = exclusive scan of the cluster sizes (+ the total as the last entry)
-    PG_CUDA(cudaMemsetAsync(w.csize + nCluster, 0, sizeof(int32_t), st));
-    PG_TRY(scan_exclusive_i32(w.csize, cluster_offsets, (int64_t)nCluster + 1, nullptr, w.scan_tmp, st));
-    // stable sort of (cluster id | dropped, point): members ascend inside every cluster
-    launch(k_cl_keys, nb, 256, 0, st, w.key0, w.cid, N, nCluster, w.kB);
+    // stable sort of (cluster id | dropped, point): members ascend inside every cluster; the key kernel's extra block writes
+    // the offsets (exclusive scan of the cluster sizes + the total), the last radix pass the (cluster, point) rows
+    launch(k_cl_keys, nb + 1, 256, 0, st, w.key0, w.cid, N, nCluster, w.kB, w.csize, cluster_offsets);
     int bits = 0;
     while ((1ll << bits) < (long long)nCluster + 1) bits++;
     int res = 0;
-    PG_TRY(radix_sort_pairs(w.kB, nullptr, w.kA, w.vA, w.kB, w.vB, N, bits, w.hist, w.scan_tmp, st, &res));
-    launch(k_cl_emit, (unsigned)div_up(sumNPoint, 256), 256, 0, st, res == 0 ? w.kA : w.kB, res == 0 ? w.vA : w.vB, sumNPoint,
-                                                              (int2 *)cluster_idxs);
+    PG_TRY(radix_sort_pairs(w.kB, nullptr, w.kA, w.vA, w.kB, w.vB, N, bits, w.hist, w.scan_tmp, st, &res, (int2 *)cluster_idxs, sumNPoint));
     PG_LAUNCH_CHECK();
     return PG_OK;
 }

@@ -182,7 +182,9 @@ int fill_u32(void *ptr, uint32_t value, size_t count, cudaStream_t st);
 size_t radix_tmp_count(int64_t n);  // int32 count for the histogram scratch
 int radix_sort_pairs(const uint32_t *keys_src, const uint32_t *vals_src, uint32_t *keysA, uint32_t *valsA,
                      uint32_t *keysB, uint32_t *valsB, int64_t n, int bits, int32_t *hist, int64_t *scan_tmp,
-                     cudaStream_t st, int *result_buf);
+                     cudaStream_t st, int *result_buf, int2 *pairs_out = nullptr, int64_t pairs_n = 0);
+// pairs_out: the LAST pass writes its first pairs_n sorted (key, value) pairs there as int2 rows instead of the A / B
+// buffers (bfs_cluster's (cluster, point) rows: one launch less than sorting and then interleaving).
 
 // Group n int4 keys: gid[i] = group id numbered by first occurrence in input order; *nGroups (device
 // int64) = number of groups; cnt[g] = group size.  The open-addressing table (cap slots, cap a power

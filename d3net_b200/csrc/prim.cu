@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_onepass(const int32_t *__
     }
 }
 
-size_t scan_tmp_count(int64_t n) { return (size_t)div_up(n > 0 ? n : 1, kScanTile) + 2; }
+size_t scan_tmp_count(int64_t n) { return (size_t)div_up(n > 0 ? n : 1, kFusedTile) + 2; }   // the smaller of the two tile sizes
 
 int scan_exclusive_i32(const int32_t *in, int32_t *out, int64_t n, int64_t *total, int64_t *tmp,
                        cudaStream_t st) {
@@ -135,10 +135,11 @@ __global__ void __launch_bounds__(kRadixThreads) k_radix_hist_all(const uint32_t
 // running count from round to round.  Keys, values and ranks stay in registers.  Thread t owns digits
 // t * PER .. t * PER + PER - 1 in the publish / look-back step.
 template <int DBITS>
-__global__ void __launch_bounds__(kRadixThreads, DBITS <= 9 ? 4 : 2)    // 592 resident tiles: a million keys in one wave
+__global__ void __launch_bounds__(kRadixThreads)    // (capped at 64 registers for 4 blocks per SM: spills, 35 -> 48 us per pass)
 k_radix_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restrict__ vals_in,
                  uint32_t *__restrict__ keys_out, uint32_t *__restrict__ vals_out, int64_t n, int shift,
-                 const int32_t *__restrict__ ghist, unsigned *ticket, unsigned *state) {
+                 const int32_t *__restrict__ ghist, unsigned *ticket, unsigned *state, int2 *__restrict__ pairs_out,
+                 int64_t pairs_n) {
     pdl_enter();
     constexpr int kWarps = kRadixThreads / 32;
     constexpr int BINS = 1 << DBITS, PER = BINS / kRadixThreads;
@@ -249,8 +250,12 @@ k_radix_onesweep(const uint32_t *__restrict__ keys_in, const uint32_t *__restric
     for (int r = 0; r < kRadixRounds; r++) {
         if (dig[r] < (unsigned)BINS) {
             const int pos = wcnt[w][dig[r]] + rank[r];
-            keys_out[pos] = key[r];
-            vals_out[pos] = val[r];
+            if (pairs_out) {                          // last pass of a sort whose caller wants (key, value) rows
+                if (pos < pairs_n) pairs_out[pos] = make_int2((int)key[r], (int)val[r]);
+            } else {
+                keys_out[pos] = key[r];
+                vals_out[pos] = val[r];
+            }
         }
     }
 }
@@ -259,7 +264,7 @@ size_t radix_tmp_count(int64_t n) { return (size_t)kRadixHead + (size_t)kRadixPa
 
 int radix_sort_pairs(const uint32_t *keys_src, const uint32_t *vals_src, uint32_t *keysA, uint32_t *valsA,
                      uint32_t *keysB, uint32_t *valsB, int64_t n, int bits, int32_t *hist, int64_t *scan_tmp,
-                     cudaStream_t st, int *result_buf) {
+                     cudaStream_t st, int *result_buf, int2 *pairs_out, int64_t pairs_n) {
     (void)scan_tmp;
     *result_buf = 0;
     if (n <= 0) return PG_OK;
@@ -283,9 +288,10 @@ int radix_sort_pairs(const uint32_t *keys_src, const uint32_t *vals_src, uint32_
         unsigned *ticket = reinterpret_cast<unsigned *>(hist) + kRadixPassBins + p;
         unsigned *state = reinterpret_cast<unsigned *>(hist) + kRadixHead + (size_t)p * bins * nb;
         const int32_t *gh = hist + p * bins;
-        if (dbits == 8) launch(k_radix_onesweep<8>, nb, kRadixThreads, 0, st, kin, vin, k[dst], v[dst], n, dbits * p, gh, ticket, state);
-        else if (dbits == 9) launch(k_radix_onesweep<9>, nb, kRadixThreads, 0, st, kin, vin, k[dst], v[dst], n, dbits * p, gh, ticket, state);
-        else launch(k_radix_onesweep<10>, nb, kRadixThreads, 0, st, kin, vin, k[dst], v[dst], n, dbits * p, gh, ticket, state);
+        int2 *po = p == passes - 1 ? pairs_out : nullptr;      // the last pass may write (key, value) rows instead
+        if (dbits == 8) launch(k_radix_onesweep<8>, nb, kRadixThreads, 0, st, kin, vin, k[dst], v[dst], n, dbits * p, gh, ticket, state, po, pairs_n);
+        else if (dbits == 9) launch(k_radix_onesweep<9>, nb, kRadixThreads, 0, st, kin, vin, k[dst], v[dst], n, dbits * p, gh, ticket, state, po, pairs_n);
+        else launch(k_radix_onesweep<10>, nb, kRadixThreads, 0, st, kin, vin, k[dst], v[dst], n, dbits * p, gh, ticket, state, po, pairs_n);
         kin = k[dst];
         vin = v[dst];
         *result_buf = dst;

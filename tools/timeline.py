@@ -3,7 +3,9 @@
     python tools/timeline.py [--overlap] [--fused-cluster] [--fused-glue] [--out gpurun_out/timeline.json]
 
 Prints the union-busy time of the device over one step, the idle gaps above 8 us with the kernels either side of them,
-and a per-stream summary.  Not a benchmark: the profiler adds host overhead per launch (the gaps are upper bounds).
+and per-kernel totals.  Not a benchmark: the profiler adds host overhead per launch (the gaps are upper bounds).
+Programmatic dependent launch is switched off unless --pdl is given: with it a kernel's CUPTI interval starts when its
+first block becomes resident, i.e. it includes the wait for its predecessor, and per-kernel totals are over-counted.
 """
 import argparse
 import json
@@ -21,10 +23,13 @@ def main():
     ap.add_argument("--overlap", action="store_true")
     ap.add_argument("--fused-cluster", action="store_true")
     ap.add_argument("--fused-glue", action="store_true")
+    ap.add_argument("--pdl", action="store_true")
     ap.add_argument("--scenes", type=int, default=8)
     ap.add_argument("--points", type=int, default=150_000)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "timeline.json"))
     a = ap.parse_args()
+    if not a.pdl:
+        os.environ["PG_B200_NO_PDL"] = "1"
     from torch.profiler import profile, ProfilerActivity
     from d3net_b200 import chain, scenes, pointgroup_ops as ops
     dev = torch.device("cuda", 0)
