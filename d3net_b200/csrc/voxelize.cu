@@ -1,5 +1,7 @@
 // voxelize_idx (GPU hash grouping + stable sort), voxelize_fp / voxelize_bp (segment mean scatter /
 // gather), point_recover.  Reference behaviour: lib/pointgroup_ops/src/voxelize/voxelize.{cpp,cu}.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pg {
@@ -210,7 +212,7 @@ __device__ __forceinline__ void vred(float4 *p, float4 v) { atomicAdd(p, v); }
 template <int V>
 __global__ void __launch_bounds__(256) k_voxelize_fp(const float *__restrict__ feats, float *__restrict__ out,
                                                      const int32_t *__restrict__ rules, int32_t M, int32_t W,
-                                                     int32_t Cv, int average) {
+                                                     int32_t Cv, int average, int skip_above) {
     pdl_enter();
     using T = typename Vec<V>::T;
     const T *__restrict__ f = reinterpret_cast<const T *>(feats);
@@ -223,6 +225,7 @@ __global__ void __launch_bounds__(256) k_voxelize_fp(const float *__restrict__ f
         row_col(t, Cv, v, c);
         const int32_t *r = rules + v * W;
         const int n = __ldg(r);
+        if (n > skip_above) continue;                    // a long list: k_voxelize_fp_long's row
         const float mult = (average && n > 0) ? __fdiv_rn(1.0f, (float)n) : 1.0f;
         T acc;
         vzero<V>(acc);
@@ -238,6 +241,112 @@ __global__ void __launch_bounds__(256) k_voxelize_fp(const float *__restrict__ f
             vmuladd(acc, mult, __ldg(f + (int64_t)r0 * Cv + c));
         }
         __stcs(o + t, acc);
+    }
+}
+
+// Long lists on narrow rows (the 14^3 cluster grids: C = 16, a voxel of the floor-sized proposal holds hundreds of points).
+// The adds of one (voxel, column) are a serial chain in list order -- that is the semantics -- but a thread that also
+// FETCHES its operands four at a time spends a memory round trip per four points: the longest list (~400 points, ~100 round
+// trips) was the kernel's run time while the rest of the machine idled.  Here a WARP takes a long row: 32 lanes gather
+// batches of 32 points' rows straight into an eight-stage shared-memory ring with cp.async (seven batches in flight while
+// lanes 0 .. Cv-1 add the oldest), the point indices run two batches ahead of the gathers.  Rows of at most kLongMin points
+// stay with the flat kernel, which skips the rows this one takes.  (One batch in flight through registers: 76 us for the
+// floor proposal's ~1500-point voxels.)
+constexpr int kLongMinDefault = 24;
+constexpr int kLongCv = 4;                             // vectors per row this kernel is built for (C = 16 as float4)
+
+constexpr int kLongStages = 8;                         // batches of 32 points in flight per warp: most of a 300-point row at once
+constexpr int kLongWarps = 2;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// float4 rows only (cp.async moves 16 bytes per lane and vector): C = 16
+__global__ void __launch_bounds__(kLongWarps * 32) k_voxelize_fp_long(const float *__restrict__ feats, float *__restrict__ out,
+                                                                      const int32_t *__restrict__ rules, int32_t M, int32_t W,
+                                                                      int average, int kLongMin) {
+    pdl_enter();
+    using T = float4;
+    constexpr int Cv = kLongCv, S = kLongStages;
+    __shared__ T stage[kLongWarps][S][32 * Cv];
+    const T *__restrict__ f = reinterpret_cast<const T *>(feats);
+    T *__restrict__ o = reinterpret_cast<T *>(out);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t nWarps = (int64_t)gridDim.x * kLongWarps;
+    const int64_t w0 = (int64_t)blockIdx.x * kLongWarps + warp;
+    // A warp's rows are w0, w0 + nWarps, ... (long rows come in runs -- the voxels of one big proposal -- so consecutive rows
+    // must go to different warps); it looks at the lengths of 32 of them at once (lane = row: one memory round trip per
+    // 32 rows instead of one per row -- 350 k rows, 3 k of them long), the next 32 lengths already in flight, and serves the
+    // long ones.
+    auto len_of = [&](int64_t k0) {
+        const int64_t vm = w0 + (k0 + lane) * nWarps;
+        return vm < M ? __ldg(rules + vm * W) : 0;
+    };
+    int nnext = len_of(0);
+    for (int64_t k0 = 0; w0 + k0 * nWarps < M; k0 += 32) {
+      const int nmine = nnext;
+      nnext = len_of(k0 + 32);
+      unsigned todo = __ballot_sync(0xffffffffu, nmine > kLongMin);
+      while (todo) {
+        const int bit = __ffs((int)todo) - 1;
+        todo &= todo - 1u;
+        const int64_t v = w0 + (k0 + bit) * nWarps;
+        const int n = __shfl_sync(0xffffffffu, nmine, bit);
+        const int32_t *r = rules + v * W;
+        const float mult = average ? __fdiv_rn(1.0f, (float)n) : 1.0f;
+        const int nb = (n + 31) >> 5;
+        T acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        // the point indices run two batches ahead of the gathers, the gathers S - 1 batches ahead of the adds
+        auto idx_of = [&](int bq) { return (bq < nb && bq * 32 + lane < n) ? __ldg(r + 1 + bq * 32 + lane) : 0; };
+        // lane l issues vectors l, l + 32, l + 64, l + 96 of the batch's 32 x Cv: point (item >> 2), column (item & 3)
+        auto issue = [&](int bq, int pidx) {
+            if (bq < nb) {
+                T *dst = stage[warp][bq % S];
+#pragma unroll
+                for (int k = 0; k < Cv; k++) {
+                    const int item = k * 32 + lane;
+                    const int src = __shfl_sync(0xffffffffu, pidx, item >> 2);
+                    if (bq * 32 + (item >> 2) < n) cp_async16(dst + item, f + (int64_t)src * Cv + (item & 3));
+                }
+            }
+            cp_async_commit();                         // (an empty group keeps the count uniform)
+        };
+        int p0 = idx_of(0), p1 = idx_of(1);
+#pragma unroll
+        for (int bq = 0; bq < S - 1; bq++) {
+            issue(bq, p0);
+            p0 = p1;
+            p1 = idx_of(bq + 2);
+        }
+        for (int bq = 0; bq < nb; bq++) {
+            cp_async_wait<S - 2>();                     // batch bq has landed (this lane's part)
+            __syncwarp();                               // ... and everybody else's
+            if (lane < Cv) {
+                const T *st = stage[warp][bq % S];
+                const int cnt = n - bq * 32 < 32 ? n - bq * 32 : 32;
+                // eight operands out of shared memory at a time, then their ordered adds
+                int p = 0;
+                for (; p + 8 <= cnt; p += 8) {
+                    T x[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) x[u] = st[(p + u) * Cv + lane];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) vmuladd(acc, mult, x[u]);
+                }
+                for (; p < cnt; p++) vmuladd(acc, mult, st[p * Cv + lane]);
+            }
+            __syncwarp();
+            issue(bq + S - 1, p0);                      // into stage (bq - 1) % S, consumed one round ago
+            p0 = p1;
+            p1 = idx_of(bq + S + 1);
+        }
+        cp_async_wait<0>();
+        if (lane < Cv) __stcs(o + v * Cv + lane, acc);
+      }
     }
 }
 
@@ -342,6 +451,12 @@ static int voxelize_launch(bool fp, const float *src, float *dst, const int32_t 
     // point lists (the 14^3 cluster grids, C = 16, up to hundreds of points per voxel) keep the flat kernel, whose
     // four-deep gather pipeline along the point list is what matters there (measured: 0.17 vs 0.23 ms)
     const bool rows = fp && Cv >= 32;
+    // narrow rows whose lists CAN be long: a warp per long row first, the flat kernel for the rest
+    static const int kLongMin = []() { const char *e = getenv("PG_VOX_LONGMIN"); return e ? atoi(e) : kLongMinDefault; }();
+    const bool long_rows = fp && !rows && V == 4 && Cv == kLongCv && maxActive > kLongMin;
+    const int64_t lblocks = div_up(M, kLongWarps);
+    const int64_t lwave = (int64_t)kNumSM * PG_RESIDENT(k_voxelize_fp_long, kLongWarps * 32, 0);     // one wave: no late blocks
+    const unsigned lgrid = (unsigned)(lblocks < lwave ? lblocks : lwave);
     const int64_t row_blocks = div_up(M, 8);
     const unsigned rgrid = (unsigned)(row_blocks < (int64_t)kNumSM * 64 ? row_blocks : (int64_t)kNumSM * 64);
 #define PG_VOX(VV)                                                                                     \
@@ -350,7 +465,10 @@ static int voxelize_launch(bool fp, const float *src, float *dst, const int32_t 
         else if (Cv <= 96) launch(k_voxelize_fp_rows<VV, 32, 3>, rgrid, 256, 0, st, src, dst, rules, M, W, Cv, average); \
         else launch(k_voxelize_fp_rows<VV, 32, 4>, rgrid, 256, 0, st, src, dst, rules, M, W, Cv, average);               \
     }                                                                                                  \
-    else if (fp) launch(k_voxelize_fp<VV>, grid, 256, 0, st, src, dst, rules, M, W, Cv, average);          \
+    else if (fp) {                                                                                     \
+        if (long_rows) launch(k_voxelize_fp_long, lgrid, kLongWarps * 32, 0, st, src, dst, rules, M, W, average, kLongMin);  \
+        launch(k_voxelize_fp<VV>, grid, 256, 0, st, src, dst, rules, M, W, Cv, average, long_rows ? kLongMin : 0x7fffffff); \
+    }                                                                                                  \
     else launch(k_voxelize_bp<VV>, grid, 256, 0, st, src, dst, rules, M, W, Cv, average)
     { PG_KTIME(fp ? "k_voxelize_fp" : "k_voxelize_bp", st);
     if (V == 4) { PG_VOX(4); } else if (V == 2) { PG_VOX(2); } else { PG_VOX(1); } }

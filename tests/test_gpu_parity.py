@@ -104,6 +104,27 @@ def test_voxelize_fp_bp(ops, oracle, C, mode):
     np.testing.assert_array_equal(npy(f.grad), oracle.voxelization_bp(g, om, n, mode))
 
 
+@pytest.mark.parametrize("mode", [4, 3])
+def test_voxelize_fp_long_lists(ops, oracle, mode):
+    """C = 16 rows with a few very long point lists (the cluster grids of the floor-sized proposals): the warp-per-row
+    kernel takes lists above its threshold -- here up to 3000 points, many batches of its gather ring --
+    the flat kernel the rest; sums must keep the reference's list order bit for bit."""
+    rng = np.random.default_rng(77)
+    parts = [np.tile(np.array([[0, 1, 1, 1]]), (3000, 1)), np.tile(np.array([[0, 2, 2, 2]]), (1025, 1)),
+             np.tile(np.array([[1, 3, 3, 3]]), (1024, 1)), np.tile(np.array([[1, 0, 5, 9]]), (25, 1)),
+             np.tile(np.array([[0, 4, 4, 4]]), (24, 1)),
+             np.column_stack([rng.integers(0, 2, 6000), rng.integers(0, 3, (6000, 3))]),       # ~110 points per voxel
+             np.column_stack([rng.integers(0, 2, 4000), rng.integers(5, 14, (4000, 3))])]      # short lists
+    coords = np.concatenate(parts).astype(np.int64)
+    coords = coords[rng.permutation(coords.shape[0])]
+    n = coords.shape[0]
+    _, _, om = oracle.voxelization_idx(coords, 2, 4)
+    assert om.shape[1] - 1 >= 3000
+    feats = (rng.standard_normal((n, 16)) * np.exp(rng.uniform(-8, 8, (n, 1)))).astype(np.float32)
+    out = ops.voxelization(cu(feats), cu(om), mode)
+    np.testing.assert_array_equal(npy(out), oracle.voxelization(feats, om, mode))
+
+
 def test_voxelize_fp_signed_zero_and_specials(ops, oracle):
     om = np.array([[2, 0, 1], [1, 2, 0], [0, 0, 0]], np.int32)
     feats = np.array([[-0.0, np.inf, 1e-45], [-0.0, -np.inf, 1e-45], [-0.0, np.nan, -1e38]], np.float32)
