@@ -156,6 +156,11 @@ static int seg_reduce_launch(const float *inp, const int32_t *offsets, float *ou
         else if (C % 2 == 0 && (uintptr_t)inp % 8 == 0) V = 2;
         int R = 4096 / (C > 0 ? C : 1);
         if (R < 32) R = 32;
+        // ... but enough tiles for ~32 warps per SM: a lane's loop is a chain of memory round trips (four rows in flight), and
+        // on narrow rows (C = 3: 1365 rows per tile, 1.4 k tiles for 1.9 M rows) 34 of them in a row on 8 warps per SM were
+        // the kernel's run time (sec_max 0.070 ms for 23 MB)
+        const int64_t spread = nRows / ((int64_t)kNumSM * 32);
+        if (R > spread) R = (int)(spread > 128 ? spread : 128);
         const int64_t tiles = div_up(nRows, R);
         const unsigned grid = (unsigned)div_up(tiles, 8);
         if (V == 4) launch(k_seg_reduce<MODE, 4>, grid, 256, 0, st, inp, offsets, slots, nRows, nP, C, R);
