@@ -21,9 +21,12 @@
 //     every predicate outcome is recorded as one bit (32 candidates per word) and the sorted candidate
 //     indices are kept (4 bytes each), so
 //   fill turns bits into indices without touching a coordinate.
-//   Segments of `idx` are laid out in query (= cell) order: deterministic, and neighbouring points own
-//   neighbouring segments, which is what makes the consumer (bfs_cluster) cache-friendly.
+//   Segments of `idx` are laid out in query (= cell) order: neighbouring points own neighbouring segments, which is
+//   what makes the consumer (bfs_cluster) cache-friendly.  Cells are numbered as they are claimed (roughly by first
+//   appearance; PG_BQ_ORDERED_CELLS=1: exactly), points inside a cell in claim order: the PLACEMENT of the segments may
+//   differ from run to run -- as the reference's does (atomicAdd, bfs_cluster.cu:47) -- every list's content is fixed.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "ballquery.cuh"
@@ -996,7 +999,8 @@ extern "C" int pg_ballquery_prepare(const float *xyz, const int32_t *batch_idxs,
     uint32_t *sorted_pt = w.kA, *cmin = w.kB, *cmax = w.vB;
     int32_t *cursor = reinterpret_cast<int32_t *>(w.vA);
     PG_TRY(group_int4(w.keys, n, w.tab, w.pslot, w.cell, w.ccnt, w.scalars, w.scan_tmp, st, nullptr,
-                      Fill{w.vA, ((size_t)((char *)w.vB - (char *)w.vA) + align_up((size_t)n * 4)) / 4, 0u}));   // to the padded end of vB
+                      Fill{w.vA, ((size_t)((char *)w.vB - (char *)w.vA) + align_up((size_t)n * 4)) / 4, 0u},   // to the padded end of vB
+                      getenv("PG_BQ_ORDERED_CELLS") != nullptr));         // cells numbered as they are claimed (scalars[0] is zero)
     PG_TRY(scan_exclusive_i32(w.ccnt, w.cstart, (int64_t)n + 1, nullptr, w.scan_tmp, st));
     launch(k_bq_scatter, (unsigned)div_up(n, 256), 256, 0, st, w.cell, w.cstart, n, cursor, sorted_pt, cmin, cmax);
     { PG_KTIME("k_bq_neighbours", st);

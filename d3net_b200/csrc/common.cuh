@@ -202,7 +202,8 @@ uint32_t group_table_cap(int64_t n);
 // no kernel has touched yet at that point); `extra` is cleared by the last kernel of the grouping for whoever comes next.
 int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot /*[n] scratch*/,
                int32_t *gid /*[n]*/, int32_t *cnt /*[n]*/, int64_t *nGroups, int64_t *scan_tmp,
-               cudaStream_t st, int64_t *cnt_max = nullptr, Fill extra = Fill{nullptr, 0, 0});
+               cudaStream_t st, int64_t *cnt_max = nullptr, Fill extra = Fill{nullptr, 0, 0}, bool first_occurrence = true);
+// first_occurrence = false: any dense numbering (roughly by first appearance, not reproducible); *nGroups must be zero on entry.
 // slot_rep and slot_gid are adjacent in every workspace layout: one range of 0xffffffff
 inline Fill group_table_fill(const GroupTable &tab) { return Fill{reinterpret_cast<uint32_t *>(tab.slot_rep), (size_t)tab.cap * 2, 0xffffffffu}; }
 

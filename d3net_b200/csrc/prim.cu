@@ -359,6 +359,53 @@ __global__ void k_group_insert(const int4 *__restrict__ keys, int64_t n, int32_t
     pslot[i] = (int)h;
 }
 
+// Grouping WITHOUT first-occurrence numbering (the ball query's grid: any dense numbering of the cells will do): the thread
+// that claims a slot numbers its group on the spot -- claimed slots are counted per block (ballots + one shared-memory
+// pass), one atomicAdd per block on the group counter -- so the ids come out in roughly ascending order of first
+// appearance (blocks start in index order), which keeps neighbouring cells neighbours in memory, but not exactly, and not
+// the same from run to run.  No minimum per slot, no flag / scan / publish pass.
+__global__ void __launch_bounds__(256) k_group_insert_claim(const int4 *__restrict__ keys, int64_t n, int32_t *slot_rep,
+                                                            int32_t *slot_gid, uint32_t cap, int32_t *__restrict__ pslot,
+                                                            int4 *__restrict__ slot_key, unsigned long long *nGroups) {
+    pdl_enter();
+    __shared__ int s_warp[8];
+    __shared__ unsigned long long s_base;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool won = false;
+    unsigned h = 0;
+    int4 k = make_int4(0, 0, 0, 0);
+    if (i < n) {
+        k = keys[i];
+        h = hash4(k.x, k.y, k.z, k.w) & (cap - 1);
+        for (;;) {
+            int rep = slot_rep[h];
+            if (rep < 0) {
+                const int prev = atomicCAS(&slot_rep[h], -1, (int)i);
+                if (prev < 0) { won = true; break; }
+                rep = prev;
+            }
+            const int4 o = keys[rep];
+            if (o.x == k.x && o.y == k.y && o.z == k.z && o.w == k.w) break;
+            h = (h + 1) & (cap - 1);
+        }
+        pslot[i] = (int)h;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned wm = __ballot_sync(0xffffffffu, won);
+    if (lane == 0) s_warp[warp] = __popc(wm);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; w++) { const int t = s_warp[w]; s_warp[w] = tot; tot += t; }
+        s_base = tot ? atomicAdd(nGroups, (unsigned long long)tot) : 0ULL;
+    }
+    __syncthreads();
+    if (won) {
+        slot_gid[h] = (int)s_base + s_warp[warp] + __popc(wm & lanemask_lt());
+        if (slot_key) slot_key[h] = k;
+    }
+}
+
 // flag -> scan -> publish as ONE pass (scan.cuh): element i's value is "i is the first (lowest-index) point of its
 // group", its exclusive prefix is then the group's id, which the first point writes into the slot.  Reading the flag and
 // overwriting the slot's minimum with the id in the same pass is safe: only point i compares the slot with i, and it
@@ -410,7 +457,7 @@ __global__ void __launch_bounds__(256) k_group_assign(const int32_t *__restrict_
 }
 
 int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot, int32_t *gid, int32_t *cnt,
-               int64_t *nGroups, int64_t *scan_tmp, cudaStream_t st, int64_t *cnt_max, Fill extra) {
+               int64_t *nGroups, int64_t *scan_tmp, cudaStream_t st, int64_t *cnt_max, Fill extra, bool first_occurrence) {
     if (n <= 0) {
         PG_CUDA(cudaMemsetAsync(nGroups, 0, sizeof(int64_t), st));
         return PG_OK;
@@ -418,9 +465,14 @@ int group_int4(const int4 *keys, int64_t n, GroupTable tab, int32_t *pslot, int3
     if (tab.slot_gid != tab.slot_rep + tab.cap) { set_error("group_int4: slot_rep and slot_gid must be adjacent"); return PG_EINVAL; }
     const int T = 256;
     const unsigned nb = (unsigned)div_up(n, T);
-    launch(k_group_insert, nb, T, 0, st, keys, n, tab.slot_rep, tab.slot_gid, tab.cap, pslot);
-    PG_TRY(scan_fused(GroupFlagLoad{pslot, tab.slot_gid}, GroupPublishStore{pslot, tab.slot_gid, keys, tab.slot_key}, n, nGroups,
-                      scan_tmp, st));
+    if (!first_occurrence) {
+        launch(k_group_insert_claim, nb, T, 0, st, keys, n, tab.slot_rep, tab.slot_gid, tab.cap, pslot, tab.slot_key,
+               reinterpret_cast<unsigned long long *>(nGroups));            // *nGroups: zeroed by the caller
+    } else {
+        launch(k_group_insert, nb, T, 0, st, keys, n, tab.slot_rep, tab.slot_gid, tab.cap, pslot);
+        PG_TRY(scan_fused(GroupFlagLoad{pslot, tab.slot_gid}, GroupPublishStore{pslot, tab.slot_gid, keys, tab.slot_key}, n, nGroups,
+                          scan_tmp, st));
+    }
     if (cnt_max) launch(k_group_assign<true>, nb, T, 0, st, pslot, tab.slot_gid, n, gid, cnt, cnt_max, extra);
     else launch(k_group_assign<false>, nb, T, 0, st, pslot, tab.slot_gid, n, gid, cnt, cnt_max, extra);
     PG_LAUNCH_CHECK();
