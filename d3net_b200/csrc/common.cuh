@@ -51,6 +51,13 @@ void set_error(const char *fmt, ...);
 // been executed by every one of them) and sit at griddepcontrol.wait until that kernel has completed and its writes are
 // visible: stream order as before, but the launch latency between the ~100 short kernels of a step overlaps the tail of
 // the predecessor.  A kernel that runs through launch() MUST call pdl_enter() before it touches memory.
+// HAZARD (seen once, in an experiment): with the trigger at the kernel's start a kernel's blocks can be resident while the
+// kernel TWO before it is still running (its predecessor's blocks have all started and sit at their own wait), and ptxas
+// moves loads it knows to be read-only -- `const __restrict__` parameters, __ldg: LDG.E.CONSTANT -- ABOVE the wait (the PTX
+// order is right; neither a "memory" clobber nor a branch on a value the asm produces stops it).  Such a load reads what
+// the last two kernels of this library on the stream have not written yet.  So: data produced by the previous two kernels
+// must not be the first thing a kernel reads through a read-only pointer; tests/test_abi.py disassembles the library and
+// fails on any memory instruction ahead of ACQBULK outside a short, justified list.
 // PG_B200_NO_PDL=1 in the environment falls back to plain launches (for A/B timing).
 __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.launch_dependents;");
