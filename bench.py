@@ -154,8 +154,9 @@ KERNEL_NOTES = {
     "k_bq_cells_dense": "ball-query count over dense cells: exact fp32 distance tests on coordinates staged in shared memory "
                         "-- FP32-issue / barrier bound, not DRAM bound (DESIGN.md section 2a)",
     "k_bq_fill_mask": "decodes 1 bit per (query, candidate) into the neighbour index lists: writes 4 B per neighbour",
-    "k_cl_verify<trusted>": "edge sweep of the union-find; algorithmic bytes count every list once although settled cells "
-                            "are never read",
+    "k_cl_verify<trusted>": "edge sweep of the union-find; `GBps` / `frac` credit every list once (the op's compulsory bytes) "
+                            "although the grid-assisted sweep never reads the lists of settled cells -- an algorithmic saving, "
+                            "not bandwidth: what it moves is `dram_GBps` (latency-bound on one snapshot load per edge)",
 }
 COMPUTE_BOUND = ("k_bq_cells_dense", "k_bq_test_dense", "k_bq_cells_small", "k_bq_cells_medium")
 
@@ -681,7 +682,12 @@ def run_b200(args, rank, world, local, emit=print):
             if name in COMPUTE_BOUND:
                 row["bound"] = "fp32-issue (not DRAM): see roofline.note"
             if name in traffic_db:
+                # what the kernel really moved (ncu dram__bytes, committed capture) over the time measured now
                 row["dram_bytes_per_step"] = traffic_db[name]
+                row["dram_GBps"] = round(traffic_db[name] / (ms_step / 1e3) / 1e9, 1) if ms_step > 0 else None
+                row["dram_frac"] = round(row["dram_GBps"] / peak, 4) if row["dram_GBps"] else None
+            if name in KERNEL_NOTES:
+                row["note"] = KERNEL_NOTES[name]
             per_kernel[name] = row
         dom = next(iter(per_kernel))
         dom_ms = per_kernel[dom]["ms_per_step"]
