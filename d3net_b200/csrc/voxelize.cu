@@ -57,6 +57,20 @@ __global__ void k_vox_keys(const int64_t *__restrict__ coords, int64_t N, int4 *
     keys[i] = make_int4((int)a.x, (int)a.y, (int)b.x, (int)b.y);
 }
 
+// The largest voxel, as a pass of its own: taking it from the counting atomics' return values made every one of them a
+// round trip instead of a fire-and-forget reduction (k_group_assign 14 -> 37 us per call).  Plain pointers on purpose: the
+// counts are written by the kernel just before and the group count by the one before that -- read-only loads could be
+// moved above the dependency wait (common.cuh, HAZARD).
+__global__ void k_max_i32(const int32_t *v, const int64_t *n_dev, int64_t *out) {
+    pdl_enter();
+    const int64_t n = *n_dev;
+    int m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, v[i]);
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax((unsigned long long *)out, (unsigned long long)m);
+}
+
 constexpr int kVoxRankMax = 32;        // largest voxel (points) served by the sort-free fill: a thread per point counts
                                        // its voxel's segment, so long segments (cluster grids: hundreds of points per voxel,
                                        // different ones in every lane) diverge and scatter -- those keep the sort
@@ -500,8 +514,9 @@ extern "C" int pg_voxelize_idx_map(const int64_t *coords, int64_t N, int mode, i
     if (!w.ok) { set_error("pg_voxelize_idx_map: workspace too small (%zu < %zu)", ws_bytes, w.used); return PG_EWORKSPACE; }
     PG_CUDA(cudaMemsetAsync(w.scalars, 0, 4 * sizeof(int64_t), st));
     launch(k_vox_keys, (unsigned)div_up(N, 256), 256, 0, st, coords, N, w.keys, group_table_fill(w.tab), Fill{(uint32_t *)w.cnt, (size_t)N, 0u});
-    // + the largest voxel; the fill phase's cursors (kA) are cleared on the way
-    PG_TRY(group_int4(w.keys, N, w.tab, w.pslot, input_map, w.cnt, w.scalars, w.scan_tmp, st, w.scalars + 1, Fill{w.kA, (size_t)N, 0u}));
+    // the fill phase's cursors (kA) are cleared on the way; then the largest voxel
+    PG_TRY(group_int4(w.keys, N, w.tab, w.pslot, input_map, w.cnt, w.scalars, w.scan_tmp, st, nullptr, Fill{w.kA, (size_t)N, 0u}));
+    launch(k_max_i32, kNumSM * 4, 256, 0, st, w.cnt, w.scalars, w.scalars + 1);
     PG_LAUNCH_CHECK();
     int64_t h[2];
     PG_CUDA(cudaMemcpyAsync(h, w.scalars, sizeof(h), cudaMemcpyDeviceToHost, st));
