@@ -156,8 +156,13 @@ class _Fork:
     def __init__(self, dev):
         global _pool
         if _pool is None:
+            import os
+            import sys
             from concurrent.futures import ThreadPoolExecutor
             _pool = ThreadPoolExecutor(max_workers=2, thread_name_prefix="pg-chain")
+            # three threads issue short launches: hand the interpreter lock over more often than every 5 ms (the default
+            # switch interval is as long as the whole step)
+            sys.setswitchinterval(float(os.environ.get("PG_CHAIN_SWITCH_S", "0.0002")))
         if dev not in _streams:
             _streams[dev] = tuple(torch.cuda.Stream(device=dev) for _ in range(3))
         self.dev, self.main, self.side, self.used, self.jobs = dev, torch.cuda.current_stream(), _streams[dev], 0, []
