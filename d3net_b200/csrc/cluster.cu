@@ -473,7 +473,7 @@ __global__ void k_cl_cell_main(const uint32_t *__restrict__ sorted_pt, const int
                                const uint2 *__restrict__ pl, const uint32_t *__restrict__ snap, uint2 *__restrict__ cellsum,
                                int32_t *__restrict__ cthr) {
     pdl_enter();
-    const int64_t nCells = bq_scalars[0];
+    const int64_t nCells = ld_after_wait(bq_scalars);
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += (int64_t)gridDim.x * blockDim.x) {
         const int nq = __ldg(ccnt + c), qs = __ldg(cstart + c);
         const uint32_t p0 = __ldg(sorted_pt + qs);
@@ -513,7 +513,7 @@ __global__ void k_cl_cell_settle(const int32_t *__restrict__ nbr, const int64_t 
                                  const uint2 *__restrict__ cellsum, const int32_t *__restrict__ cthr,
                                  int32_t *__restrict__ cstate) {
     pdl_enter();
-    const int64_t nCells = bq_scalars[0];
+    const int64_t nCells = ld_after_wait(bq_scalars);
     for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < nCells; c += (int64_t)gridDim.x * blockDim.x) {
         const uint2 me = cellsum[c];
         int L = cthr[3 * c];

@@ -56,12 +56,25 @@ void set_error(const char *fmt, ...);
 // moves loads it knows to be read-only -- `const __restrict__` parameters, __ldg: LDG.E.CONSTANT -- ABOVE the wait (the PTX
 // order is right; neither a "memory" clobber nor a branch on a value the asm produces stops it).  Such a load reads what
 // the last two kernels of this library on the stream have not written yet.  So: data produced by the previous two kernels
-// must not be the first thing a kernel reads through a read-only pointer; tests/test_abi.py disassembles the library and
-// fails on any memory instruction ahead of ACQBULK outside a short, justified list.
+// must not be the first thing a kernel reads through a read-only pointer (ld_after_wait below is the plain load for such
+// scalars); tests/test_abi.py disassembles the library and fails on any memory instruction ahead of ACQBULK.
 // PG_B200_NO_PDL=1 in the environment falls back to plain launches (for A/B timing).
 __device__ __forceinline__ void pdl_enter() {
     asm volatile("griddepcontrol.launch_dependents;");
     asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+// A kernel's FIRST look at a scalar another kernel may have produced: a plain (coherent) load in a volatile asm, which
+// ptxas keeps behind the wait (it moves only loads it knows to be read-only: see HAZARD above).
+__device__ __forceinline__ long long ld_after_wait(const int64_t *p) {
+    long long v;
+    asm volatile("ld.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int ld_after_wait(const int32_t *p) {
+    int v;
+    asm volatile("ld.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
 bool pdl_enabled();

@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) k_seg_reduce(const float *__restrict__ in
     const int lane = threadIdx.x & 31;
     const int64_t tile = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     int64_t r0 = tile * R, r1 = r0 + R;
-    const int first = __ldg(offsets), last = __ldg(offsets + nP);
+    const int first = ld_after_wait(offsets), last = ld_after_wait(offsets + nP);
     if (r0 < first) r0 = first;
     if (r1 > last) r1 = last;
     if (r1 > nRows) r1 = nRows;
